@@ -1,0 +1,409 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (DCNv3Function -> ctypes ->
+libdcnv3_b200.so), against
+
+  * the golden fixtures the reference's own dcnv3_core_pytorch produced (tests/golden/),
+  * the CPU oracles on the same seeded inputs (oracle/: test infrastructure),
+  * known answers and size-independent properties at the BASELINE shapes.
+
+Tolerances (north_star): integer corner indices / bounds bytes bit-exact; fp32 rtol 1e-5 /
+atol 1e-4; fp16 / bf16 rtol 1e-2 (atol stated per check).  Backward tolerance includes the
+atomic-summation order of grad_input (fp32 adds of O(36) terms: a few ulp).
+Mirrors the reference's test.py (fixture :19-30, channel sweep :257-260) and adds what it
+lacks: fp16/bf16, stride/dilation/pad sweeps, non-square maps, index tests.
+"""
+import zlib
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from cases import CASES, op_args
+from util_golden import load_golden
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def fn():
+    from yolo_dual_b200.ops_dcnv3.functions import DCNv3Function
+    return DCNv3Function
+
+
+def run_cuda(fn_, x, off, m, go, args, dtype=None):
+    """forward + backward through the product path; returns CPU tensors (storage dtype)."""
+    dt = dtype or x.dtype
+    xs, os_, ms = (t.to(DEV, dt).contiguous().requires_grad_(True) for t in (x, off, m))
+    out = fn_.apply(xs, os_, ms, *args, 256)
+    res = [out.detach().cpu()]
+    if go is not None:
+        out.backward(go.to(DEV, dt))
+        res += [xs.grad.cpu(), os_.grad.cpu(), ms.grad.cpu()]
+    torch.cuda.synchronize()
+    return res
+
+
+def assert_close_scaled(got, want, rtol, atol, what):
+    """allclose after dividing both sides by max(1, max|want|) (errors scale with the data)."""
+    scale = max(1.0, float(want.abs().max()))
+    torch.testing.assert_close(got.double() / scale, want.double() / scale, rtol=rtol, atol=atol,
+                               msg=lambda s: f"{what}: {s}")
+
+
+def near_cell_border(offset, c, eps):
+    from test_oracle_golden import frac_margin
+    near = frac_margin(offset, c, eps)
+    N, Ho, Wo, _ = offset.shape
+    return near, (~near).unsqueeze(-1).expand(*near.shape, 2).reshape(N, Ho, Wo, -1)
+
+
+# ------------------------------------------------------------------------------------------
+# 1. golden fixtures (the reference's own outputs)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("c", CASES, ids=[c["name"] for c in CASES])
+def test_golden(c, fn):
+    g = load_golden(c["name"])
+    out, gi, go_, gm = run_cuda(fn, g["input"], g["offset"], g["mask"], g["grad_out"], op_args(c))
+    tol = dict(rtol=1e-5, atol=1e-4)  # north_star fp32 bar (also used for the f64 fixtures)
+    assert_close_scaled(out, g["output"], what="output", **tol)
+    assert_close_scaled(gi, g["grad_input"], what="grad_input", **tol)
+    assert_close_scaled(gm, g["grad_mask"], what="grad_mask", **tol)
+    near, keep = near_cell_border(g["offset"], c, 1e-4)
+    assert near.float().mean() < 0.01
+    assert_close_scaled(go_ * keep, g["grad_offset"] * keep, what="grad_offset", **tol)
+
+
+# ------------------------------------------------------------------------------------------
+# 2. CUDA vs the pixel-space oracle (same arithmetic contract): all dtypes, both kernel families
+# ------------------------------------------------------------------------------------------
+def _case(N, H, W, G, gc, k=3, s=1, pad=1, dil=1, scale=1.0):
+    return (N, H, W, G, gc), (k, k, s, s, pad, pad, dil, dil, G, gc, scale)
+
+
+SHAPES = {
+    # reference sweep test.py:257-260 -> every launcher branch there; here vec + generic paths
+    "D1": _case(2, 8, 8, 2, 1, scale=2.0),
+    "D16": _case(2, 8, 8, 2, 16, scale=2.0),
+    "D30": _case(2, 8, 8, 2, 30, scale=2.0),
+    "D32": _case(2, 8, 8, 2, 32, scale=2.0),
+    "D64": _case(2, 8, 8, 2, 64, scale=2.0),
+    "D71": _case(2, 8, 8, 2, 71, scale=2.0),
+    "D1025": _case(2, 8, 8, 2, 1025, scale=2.0),
+    "D24_vec_nonpow2": _case(1, 9, 7, 3, 24),           # gc % 8 == 0 but 3 lanes/group: generic
+    "cfg1": _case(2, 80, 80, 4, 16),                    # BASELINE config #1
+    "stride2": _case(2, 17, 23, 4, 16, s=2, scale=1.5),
+    "k5dil2": _case(1, 20, 18, 2, 8, k=5, pad=4, dil=2),
+    "pad0": _case(1, 12, 12, 4, 8, pad=0),
+    "G32gc8": _case(1, 10, 10, 32, 8),
+    "gc128": _case(1, 10, 10, 2, 128),                  # 32 lanes (fp32) per group
+    "gc256": _case(1, 6, 6, 1, 256),                    # 64 fp32 lanes: generic for fp32, vec for 16-bit
+}
+
+
+@pytest.mark.parametrize("dist", ["ref", "unit"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.float16, torch.bfloat16],
+                         ids=["f32", "f64", "f16", "bf16"])
+@pytest.mark.parametrize("shape", list(SHAPES), ids=list(SHAPES))
+def test_vs_pixel_oracle(shape, dtype, dist, fn, pixel_oracle):
+    from oracle.dcnv3_oracle import make_inputs
+    (N, H, W, G, gc), args = SHAPES[shape]
+    kh, kw, sh, sw, ph, pw, dh, dw = args[:8]
+    x, off, m, go = make_inputs(N, H, W, G, gc, kh, kw, sh, sw, ph, pw, dh, dw, dist=dist,
+                                seed=zlib.crc32(f"{shape}/{dist}".encode()) % 1000, dtype=torch.float32)
+    # the oracle sees exactly the values the kernel sees (storage-rounded), in op-math precision
+    om = torch.float64 if dtype == torch.float64 else torch.float32
+    xr, offr, mr, gor = (t.to(dtype).to(om) for t in (x, off, m, go))
+    want_out = pixel_oracle.forward(xr, offr, mr, *args)
+    want_gi, want_go, want_gm = pixel_oracle.backward(xr, offr, mr, gor, *args)
+    out, gi, go_, gm = run_cuda(fn, x, off, m, go, args, dtype=dtype)
+    assert out.dtype == dtype and gi.dtype == dtype and go_.dtype == dtype and gm.dtype == dtype
+    if dtype == torch.float64:
+        tol = dict(rtol=1e-10, atol=1e-11)
+    elif dtype == torch.float32:
+        tol = dict(rtol=1e-5, atol=1e-5)     # tighter than the 1e-4 bar: same arithmetic contract
+    else:
+        tol = dict(rtol=1e-2, atol=2e-3)     # one storage rounding of an fp32-accumulated value
+    assert_close_scaled(out, want_out, what="output", **tol)
+    assert_close_scaled(gi, want_gi, what="grad_input", **tol)
+    assert_close_scaled(gm, want_gm, what="grad_mask", **tol)
+    assert_close_scaled(go_, want_go, what="grad_offset", **tol)
+
+
+# ------------------------------------------------------------------------------------------
+# 3. integer contract: bit-exact corner indices and bounds bytes
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.float16, torch.bfloat16],
+                         ids=["f32", "f64", "f16", "bf16"])
+@pytest.mark.parametrize("shape,dist,scale", [
+    ("cfg1", "unit", 1.0), ("cfg1", "ref", 1.0), ("cfg1", "ref", 2.0), ("stride2", "unit", 1.5),
+    ("k5dil2", "unit", 1.0), ("pad0", "ref", 0.7)])
+def test_indices_bit_exact(shape, dist, scale, dtype, pixel_oracle):
+    from oracle.dcnv3_oracle import make_inputs
+    from yolo_dual_b200.ops_dcnv3.functions import dcnv3_debug_indices
+    (N, H, W, G, gc), args = SHAPES[shape]
+    kh, kw, sh, sw, ph, pw, dh, dw = args[:8]
+    _, off, _, _ = make_inputs(N, H, W, G, gc, kh, kw, sh, sw, ph, pw, dh, dw, dist=dist, seed=9)
+    off = off.to(dtype)
+    om = torch.float64 if dtype == torch.float64 else torch.float32
+    want_hw, want_bd = pixel_oracle.indices(off.to(om), H, W, kh, kw, sh, sw, ph, pw, dh, dw, G, scale)
+    hw, bd = dcnv3_debug_indices(off.to(DEV), H, W, kh, kw, sh, sw, ph, pw, dh, dw, G, scale)
+    assert torch.equal(bd.cpu(), want_bd), f"{(bd.cpu() != want_bd).sum()} bounds bytes differ"
+    assert torch.equal(hw.cpu(), want_hw), f"{(hw.cpu() != want_hw).sum()} corner indices differ"
+    assert int((want_bd & 1).sum()) > 0
+
+
+# ------------------------------------------------------------------------------------------
+# 4. known answers through the CUDA path
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16], ids=["f32", "f16", "bf16"])
+def test_kat_avgpool_cuda(dtype, fn):
+    gen = torch.Generator().manual_seed(5)
+    N, H, W, G, gc = 2, 11, 13, 2, 8
+    x = torch.randn(N, H, W, G * gc, generator=gen).to(dtype)
+    off = torch.zeros(N, H, W, G * 18, dtype=dtype)
+    m = torch.full((N, H, W, G * 9), 1.0 / 9, dtype=dtype)
+    args = (3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0)
+    (out,) = run_cuda(fn, x, off, m, None, args)
+    mq = float(m.flatten()[0])  # 1/9 as stored
+    want = F.avg_pool2d(x.float().permute(0, 3, 1, 2), 3, 1, 1, count_include_pad=True).permute(0, 2, 3, 1) * 9 * mq
+    tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=1e-2, atol=2e-3)
+    torch.testing.assert_close(out.float(), want.contiguous(), **tol)
+
+
+@pytest.mark.parametrize("p,ox,oy", [(0, 0, 0), (5, 1, -1), (8, -2, 1), (3, 0, 2)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_kat_shift_cuda(p, ox, oy, dtype, fn):
+    gen = torch.Generator().manual_seed(6)
+    N, H, W, G, gc = 1, 7, 9, 2, 8
+    x = torch.randn(N, H, W, G * gc, generator=gen).to(dtype)
+    off = torch.zeros(N, H, W, G, 9, 2)
+    off[..., 0], off[..., 1] = ox, oy
+    m = torch.zeros(N, H, W, G, 9)
+    m[..., p] = 1.0
+    dx, dy = p // 3 - 1 + ox, p % 3 - 1 + oy
+    want = torch.zeros_like(x)
+    for h in range(H):
+        for w in range(W):
+            if 0 <= h + dy < H and 0 <= w + dx < W:
+                want[0, h, w] = x[0, h + dy, w + dx]
+    args = (3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0)
+    (out,) = run_cuda(fn, x, off.reshape(N, H, W, -1).to(dtype), m.reshape(N, H, W, -1).to(dtype), None, args)
+    assert torch.equal(out, want)  # weights are exactly 0 / 1: bit-exact in every dtype
+
+
+def test_kat_bounds_cuda(fn):
+    gen = torch.Generator().manual_seed(7)
+    N, H, W, G, gc = 1, 6, 6, 2, 4
+    x = torch.randn(N, H, W, G * gc, generator=gen)
+    off = torch.full((N, H, W, G * 18), 100.0)
+    off[..., ::4] = -100.0
+    m = torch.full((N, H, W, G * 9), 1.0 / 9)
+    go = torch.randn(N, H, W, G * gc, generator=gen)
+    out, gi, go_, gm = run_cuda(fn, x, off, m, go, (3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0))
+    for t in (out, gi, go_, gm):
+        assert float(t.abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------
+# 5. fused softmax variant: same API, mask carries logits
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.float16, torch.bfloat16],
+                         ids=["f32", "f64", "f16", "bf16"])
+@pytest.mark.parametrize("shape", ["cfg1", "D30", "k5dil2", "stride2", "G32gc8"])
+def test_fused_softmax(shape, dtype, pixel_oracle):
+    from oracle.dcnv3_oracle import make_inputs
+    from yolo_dual_b200.ops_dcnv3.functions import DCNv3SoftmaxFunction
+    (N, H, W, G, gc), args = SHAPES[shape]
+    kh, kw, sh, sw, ph, pw, dh, dw = args[:8]
+    P = kh * kw
+    x, off, _, go = make_inputs(N, H, W, G, gc, kh, kw, sh, sw, ph, pw, dh, dw, dist="unit", seed=4)
+    Ho, Wo = off.shape[1:3]
+    logits = torch.randn(N, Ho, Wo, G * P, generator=torch.Generator().manual_seed(8)) * 2
+    om = torch.float64 if dtype == torch.float64 else torch.float32
+    xr, offr, lr, gor = (t.to(dtype).to(om) for t in (x, off, logits, go))
+    # oracle: softmax in op-math on the stored logits, pixel oracle, Jacobian by hand
+    prob = torch.softmax(lr.view(N, Ho, Wo, G, P), -1)
+    pm = prob.reshape(N, Ho, Wo, G * P).contiguous()
+    want_out = pixel_oracle.forward(xr, offr, pm, *args)
+    want_gi, want_go, gm = pixel_oracle.backward(xr, offr, pm, gor, *args)
+    gmv = gm.view(N, Ho, Wo, G, P)
+    want_gl = (prob * (gmv - (prob * gmv).sum(-1, keepdim=True))).reshape(N, Ho, Wo, G * P)
+    out, gi, go_, gl = run_cuda(DCNv3SoftmaxFunction, x, off, logits, go, args, dtype=dtype)
+    tol = {torch.float64: dict(rtol=1e-9, atol=1e-10), torch.float32: dict(rtol=1e-5, atol=1e-5)}.get(
+        dtype, dict(rtol=1e-2, atol=2e-3))
+    assert_close_scaled(out, want_out, what="output", **tol)
+    assert_close_scaled(gi, want_gi, what="grad_input", **tol)
+    assert_close_scaled(go_, want_go, what="grad_offset", **tol)
+    assert_close_scaled(gl, want_gl, what="grad_logits", **tol)
+
+
+# ------------------------------------------------------------------------------------------
+# 6. 16-bit grad_input accumulated in the storage dtype (ACC_STORAGE): looser, stated bound
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+def test_grad_accum_storage(dtype, fn, pixel_oracle):
+    from oracle.dcnv3_oracle import make_inputs
+    from yolo_dual_b200.ops_dcnv3.functions import get_grad_accum, set_grad_accum
+    (N, H, W, G, gc), args = SHAPES["cfg1"]
+    x, off, m, go = make_inputs(N, H, W, G, gc, dist="unit", seed=2)
+    xr, offr, mr, gor = (t.to(dtype).float() for t in (x, off, m, go))
+    want_gi, want_go, want_gm = pixel_oracle.backward(xr, offr, mr, gor, *args)
+    prev = get_grad_accum()
+    set_grad_accum("storage")
+    try:
+        _, gi, go_, gm = run_cuda(fn, x, off, m, go, args, dtype=dtype)
+    finally:
+        set_grad_accum(prev)
+    # ~36 contributions per element, each add rounded to the storage dtype
+    eps = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+    assert_close_scaled(gi, want_gi, rtol=6 * eps, atol=6 * eps, what="grad_input")
+    assert_close_scaled(gm, want_gm, rtol=1e-2, atol=2e-3, what="grad_mask")
+    assert_close_scaled(go_, want_go, rtol=1e-2, atol=2e-3, what="grad_offset")
+
+
+# ------------------------------------------------------------------------------------------
+# 7. BASELINE shapes, size-independent properties (the oracle is too slow there)
+# ------------------------------------------------------------------------------------------
+SITES = {"P3": (16, 80, 80, 8, 16), "P4": (16, 40, 40, 16, 16), "P5": (16, 20, 20, 32, 16)}
+
+
+@pytest.mark.parametrize("site", list(SITES))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_full_size_properties(site, dtype, fn):
+    N, H, W, G, gc = SITES[site]
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    C, P = G * gc, 9
+    x = torch.randn(N, H, W, C, device=DEV, generator=gen).to(dtype)
+    x2 = torch.randn(N, H, W, C, device=DEV, generator=gen).to(dtype)
+    off = torch.randn(N, H, W, G * P * 2, device=DEV, generator=gen).to(dtype)
+    m = torch.softmax(torch.randn(N, H, W, G, P, device=DEV, generator=gen), -1).reshape(N, H, W, G * P).to(dtype)
+    go = torch.randn(N, H, W, C, device=DEV, generator=gen).to(dtype)
+    args = (3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0, 256)
+    lowp = dtype != torch.float32
+    tol = dict(rtol=1e-2, atol=4e-2) if lowp else dict(rtol=1e-4, atol=1e-4)
+
+    xg = x.clone().requires_grad_(True)
+    og = off.clone().requires_grad_(True)
+    mg = m.clone().requires_grad_(True)
+    y = fn.apply(xg, og, mg, *args)
+    y.backward(go)
+    # (a) the op is linear in `input`: f(x + x2) = f(x) + f(x2)
+    y2 = fn.apply(x2, off, m, *args)
+    y12 = fn.apply((x.float() + x2.float()).to(dtype), off, m, *args)
+    torch.testing.assert_close(y12.float(), y.detach().float() + y2.float(), **tol)
+    # (b) adjoint identity <go, f(x)> == <grad_input, x>  (scatter is the transpose of the gather)
+    lhs = (go.double() * y.detach().double()).sum()
+    rhs = (xg.grad.double() * x.double()).sum()
+    assert abs(float(lhs - rhs)) <= (2e-2 if lowp else 1e-4) * max(1.0, abs(float(lhs)))
+    # (c) grad_mask is the directional derivative in mask: f is linear in mask too
+    lhs_m = (mg.grad.double() * m.double()).sum()
+    assert abs(float(lhs_m - lhs)) <= (2e-2 if lowp else 1e-4) * max(1.0, abs(float(lhs)))
+    # (d) zero offsets + uniform mask == 3x3 average pooling
+    z = torch.zeros_like(off)
+    u = torch.full_like(m, 1.0 / 9)
+    ya = fn.apply(x, z, u, *args)
+    want = F.avg_pool2d(x.float().permute(0, 3, 1, 2), 3, 1, 1, count_include_pad=True).permute(0, 2, 3, 1)
+    want = want * 9 * float(u.flatten()[0])
+    torch.testing.assert_close(ya.float(), want.contiguous(), **(dict(rtol=1e-2, atol=1e-2) if lowp else dict(rtol=1e-5, atol=1e-5)))
+    # (e) grad_offset against a central finite difference of <go, f> along a random direction (fp32 only)
+    if not lowp:
+        d = torch.randn_like(off)
+        h = 1e-2
+        fp = (go.double() * fn.apply(x, off + h * d, m, *args).double()).sum()
+        fm = (go.double() * fn.apply(x, off - h * d, m, *args).double()).sum()
+        fd = float(fp - fm) / (2 * h)
+        an = float((og.grad.double() * d.double()).sum())
+        assert abs(fd - an) <= 2e-2 * max(1.0, abs(an)), (fd, an)
+
+
+# ------------------------------------------------------------------------------------------
+# 8. error behaviour of the boundary (reference: dcnv3_cuda.cu:29-34,48-53; dcnv3_cpu.cpp:25,36)
+# ------------------------------------------------------------------------------------------
+def test_errors(fn):
+    args = (3, 3, 1, 1, 1, 1, 1, 1, 2, 8, 1.0, 256)
+    x = torch.randn(2, 6, 6, 16)
+    off = torch.zeros(2, 6, 6, 36)
+    m = torch.zeros(2, 6, 6, 18)
+    with pytest.raises(NotImplementedError):
+        fn.apply(x, off, m, *args)  # CPU tensors: no CPU path, as in the reference
+    xc, oc, mc = x.to(DEV), off.to(DEV), m.to(DEV)
+    with pytest.raises(RuntimeError, match="contiguous"):
+        fn.apply(xc.permute(0, 2, 1, 3), oc, mc, *args)
+    with pytest.raises(RuntimeError, match="wont match"):
+        fn.apply(xc, oc, mc, 3, 3, 1, 1, 1, 1, 1, 1, 2, 4, 1.0, 256)
+    with pytest.raises(RuntimeError, match="im2col_step"):
+        fn.apply(torch.randn(3, 6, 6, 16, device=DEV), torch.zeros(3, 6, 6, 36, device=DEV),
+                 torch.zeros(3, 6, 6, 18, device=DEV), 3, 3, 1, 1, 1, 1, 1, 1, 2, 8, 1.0, 2)
+    with pytest.raises(RuntimeError, match="dtypes differ"):
+        fn.apply(xc.half(), oc, mc, *args)
+    with pytest.raises(RuntimeError, match="offset shape"):
+        fn.apply(xc, oc[:, :5].contiguous(), mc, *args)
+    # empty batch is legal and launches nothing
+    e = fn.apply(torch.empty(0, 6, 6, 16, device=DEV), torch.empty(0, 6, 6, 36, device=DEV),
+                 torch.empty(0, 6, 6, 18, device=DEV), *args)
+    assert e.shape == (0, 6, 6, 16)
+
+
+def test_unaligned_views_take_generic_path(fn, pixel_oracle):
+    """A contiguous view whose data_ptr is not 16-byte aligned must still be exact."""
+    from oracle.dcnv3_oracle import make_inputs
+    N, H, W, G, gc = 1, 6, 6, 2, 8
+    args = (3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0)
+    x, off, m, go = make_inputs(N, H, W, G, gc, dist="unit", seed=3)
+    buf = torch.zeros(x.numel() + 1, device=DEV)
+    xv = buf[1:].view_as(x)
+    xv.copy_(x)
+    assert xv.data_ptr() % 16 != 0 and xv.is_contiguous()
+    out = fn.apply(xv, off.to(DEV), m.to(DEV), *args, 256).cpu()
+    torch.testing.assert_close(out, pixel_oracle.forward(x, off, m, *args), rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------
+# 9. the nn.Module on top (reference modules/dcnv3.py:50-135)
+# ------------------------------------------------------------------------------------------
+def test_module_fresh_init_is_average_pool():
+    from yolo_dual_b200.ops_dcnv3.modules import DCNv3
+    torch.manual_seed(0)
+    mod = DCNv3(channels=32, group=2).to(DEV).eval()
+    x = torch.randn(2, 9, 11, 32, device=DEV)
+    with torch.no_grad():
+        y = mod(x)
+        z = mod.input_proj(x)
+        want = F.avg_pool2d(z.permute(0, 3, 1, 2), 3, 1, 1, count_include_pad=True).permute(0, 2, 3, 1)
+        want = mod.output_proj(want)
+    torch.testing.assert_close(y, want, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_module_matches_oracle_composition(fused):
+    """Module forward/backward == the same module with the op swapped for the float oracle."""
+    from oracle.dcnv3_oracle import core_torch
+    from yolo_dual_b200.ops_dcnv3.modules import DCNv3
+    torch.manual_seed(1)
+    mod = DCNv3(channels=32, group=4, offset_scale=1.5, fused_softmax=fused).to(DEV)
+    with torch.no_grad():  # leave the all-zero init so offsets / masks matter
+        mod.offset.weight.normal_(0, 0.3)
+        mod.offset.bias.normal_(0, 0.5)
+        mod.mask.weight.normal_(0, 0.3)
+    mod.eval()  # BN in eval: deterministic
+    x = torch.randn(2, 10, 12, 32, device=DEV, requires_grad=True)
+    y = mod(x)
+    y.square().sum().backward()
+    got = [y.detach().cpu(), x.grad.cpu(), mod.offset.weight.grad.cpu(), mod.mask.weight.grad.cpu(),
+           mod.input_proj.weight.grad.cpu()]
+
+    ref = DCNv3(channels=32, group=4, offset_scale=1.5).cpu()
+    ref.load_state_dict({k: v.cpu() for k, v in mod.state_dict().items()})
+    ref.eval()
+    xc = x.detach().cpu().requires_grad_(True)
+    N, H, W, _ = xc.shape
+    z = ref.input_proj(xc)
+    x1 = ref.dw_conv(xc.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+    off = ref.offset(x1)
+    msk = F.softmax(ref.mask(x1).reshape(N, H, W, ref.group, -1), -1).reshape(N, H, W, -1)
+    yc = ref.output_proj(core_torch(z, off, msk, 3, 3, 1, 1, 1, 1, 1, 1, ref.group, ref.group_channels, 1.5))
+    yc.square().sum().backward()
+    want = [yc.detach(), xc.grad, ref.offset.weight.grad, ref.mask.weight.grad, ref.input_proj.weight.grad]
+    for a, b, name in zip(got, want, ("y", "dx", "dW_offset", "dW_mask", "dW_in")):
+        assert_close_scaled(a, b, rtol=1e-3, atol=1e-4, what=name)

@@ -1,0 +1,64 @@
+"""Build recipe for the native library: plain nvcc, sm_100a only, in-tree output.
+
+    python -m yolo_dual_b200.build [--force] [--verbose]
+
+The reference builds a torch CUDAExtension with no arch flags
+(models/ops_dcnv3/setup.py:39-59, ~50 s); this library has no torch headers and
+compiles in ~15 s.  The .so is git-ignored but travels to the GPU box in-tree.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(CSRC, "libdcnv3_b200.so")
+SOURCES = ["dcnv3_b200.cu"]
+HEADERS = ["dcnv3_common.cuh", "dcnv3_kernels.cuh", os.path.join(ROOT, "include", "dcnv3_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC",
+    "-I", os.path.join(ROOT, "include"),
+]
+
+
+def _nvcc():
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: the dcnv3_b200 library cannot be built here")
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + \
+           [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    env = dict(os.environ)
+    env.pop("CC", None)   # the image exports a gcc wrapper nvcc should not pick up
+    env.pop("CXX", None)
+    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or r.returncode:
+        sys.stderr.write(r.stdout)
+    if r.returncode:
+        raise RuntimeError("nvcc failed:\n" + r.stdout[-4000:])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,355 @@
+// dcnv3_b200 — C-ABI entry points (include/dcnv3_b200.h) and kernel dispatch.
+//
+// Replaces the reference's ATen host wrappers
+// (/root/reference/models/ops_dcnv3/src/cuda/dcnv3_cuda.cu:21-85, :87-173) and
+// launchers (dcnv3_im2col_cuda.cuh:841-868, :870-1045).  No torch headers: the
+// caller owns every buffer and passes the stream.
+#include "dcnv3_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "dcnv3_kernels.cuh"
+
+using namespace dcnv3;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return (int)e;
+}
+
+size_t dtype_size(int dtype) {
+    switch (dtype) {
+        case DCNV3_B200_F32: return 4;
+        case DCNV3_B200_F16: return 2;
+        case DCNV3_B200_BF16: return 2;
+        case DCNV3_B200_F64: return 8;
+        default: return 0;
+    }
+}
+
+// Validates the geometry (the reference's AT_ASSERTMs, dcnv3_cuda.cu:48-53, plus what it
+// never checked) and derives Ho/Wo (dcnv3_cuda.cu:40-45).
+int make_geo(const dcnv3_b200_geometry *g, Geo &q) {
+    if (!g) return fail(DCNV3_B200_ENULL, "geometry is null");
+    if (g->N < 0 || g->H <= 0 || g->W <= 0)
+        return fail(DCNV3_B200_EINVAL, "bad input extent N=%d H=%d W=%d", g->N, g->H, g->W);
+    if (g->group <= 0 || g->group_channels <= 0)
+        return fail(DCNV3_B200_EINVAL, "group (%d) and group_channels (%d) must be positive",
+                    g->group, g->group_channels);
+    if (g->kernel_h <= 0 || g->kernel_w <= 0 || g->stride_h <= 0 || g->stride_w <= 0 ||
+        g->pad_h < 0 || g->pad_w < 0 || g->dilation_h <= 0 || g->dilation_w <= 0)
+        return fail(DCNV3_B200_EINVAL,
+                    "bad kernel geometry k=(%d,%d) stride=(%d,%d) pad=(%d,%d) dil=(%d,%d)",
+                    g->kernel_h, g->kernel_w, g->stride_h, g->stride_w, g->pad_h, g->pad_w,
+                    g->dilation_h, g->dilation_w);
+    q.N = g->N; q.H = g->H; q.W = g->W; q.G = g->group; q.gc = g->group_channels;
+    q.kh = g->kernel_h; q.kw = g->kernel_w; q.sh = g->stride_h; q.sw = g->stride_w;
+    q.ph = g->pad_h; q.pw = g->pad_w; q.dh = g->dilation_h; q.dw = g->dilation_w;
+    q.scale = g->offset_scale;
+    const long long C = (long long)q.G * q.gc;
+    if (C > (1 << 24)) return fail(DCNV3_B200_ERANGE, "too many channels (%lld)", C);
+    q.C = (int)C;
+    q.Ho = (q.H + 2 * q.ph - (q.dh * (q.kh - 1) + 1)) / q.sh + 1;
+    q.Wo = (q.W + 2 * q.pw - (q.dw * (q.kw - 1) + 1)) / q.sw + 1;
+    if (q.H + 2 * q.ph < q.dh * (q.kh - 1) + 1 || q.W + 2 * q.pw < q.dw * (q.kw - 1) + 1 ||
+        q.Ho <= 0 || q.Wo <= 0)
+        return fail(DCNV3_B200_EINVAL, "kernel window larger than the padded input (Ho=%d Wo=%d)",
+                    q.Ho, q.Wo);
+    q.P = q.kh * q.kw;
+    q.half_h = (q.dh * (q.kh - 1)) >> 1;
+    q.half_w = (q.dw * (q.kw - 1)) >> 1;
+    // per-image element counts are addressed with 32-bit ints inside the kernels
+    if ((long long)q.H * q.W * q.C >= (1LL << 31) ||
+        (long long)q.Ho * q.Wo * q.G * q.P * 2 >= (1LL << 31))
+        return fail(DCNV3_B200_ERANGE, "one image exceeds 2^31 elements");
+    return 0;
+}
+
+int check_device() {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(DCNV3_B200_EDEVICE, "no CUDA device: %s (this library has no CPU path)",
+                    cudaGetErrorString(e));
+    }
+    static int ok_mask[64] = {0};  // benign race: idempotent
+    if (dev < 64 && ok_mask[dev]) return 0;
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceGetAttribute");
+    if (major != 10)
+        return fail(DCNV3_B200_EDEVICE,
+                    "device %d has compute capability %d.x; dcnv3_b200 is built for sm_100a only",
+                    dev, major);
+    if (dev < 64) ok_mask[dev] = 1;
+    return 0;
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+struct Plan {
+    bool vec;
+    int vec_per_pix, lanes_per_group;
+    unsigned total_vec;
+};
+
+// Can this call take the 16-byte-vector kernels?
+template <typename T>
+Plan plan_vec(const Geo &q, size_t n_pix, bool logits, std::initializer_list<const void *> ptrs,
+              const void *off) {
+    Plan pl{false, 0, 0, 0};
+    if (sizeof(T) > 4) return pl;  // f64 always generic
+    constexpr int VEC = 16 / (int)sizeof(T);
+    if (q.gc % VEC) return pl;
+    const int L = q.gc / VEC;
+    if (!is_pow2(L) || L > 32) return pl;
+    if (logits && !(q.kh == 3 && q.kw == 3)) return pl;
+    for (const void *p : ptrs)
+        if (!aligned16(p)) return pl;
+    if (reinterpret_cast<uintptr_t>(off) & (2 * sizeof(T) - 1)) return pl;
+    const unsigned long long tv = (unsigned long long)n_pix * (q.C / VEC);
+    if (tv >= (1ull << 31)) return pl;
+    pl.vec = true;
+    pl.vec_per_pix = q.C / VEC;
+    pl.lanes_per_group = L;
+    pl.total_vec = (unsigned)tv;
+    return pl;
+}
+
+unsigned blocks_for(size_t threads) { return (unsigned)((threads + kThreads - 1) / kThreads); }
+
+// ------------------------------------------------------------------ forward
+template <typename T>
+int forward_t(const void *in_, const void *off_, const void *mask_, void *out_, const Geo &q,
+              bool logits, cudaStream_t st) {
+    const T *in = (const T *)in_, *off = (const T *)off_, *mask = (const T *)mask_;
+    T *out = (T *)out_;
+    const size_t n_pix = (size_t)q.N * q.Ho * q.Wo;
+    if (n_pix == 0) return 0;
+    const Plan pl = plan_vec<T>(q, n_pix, logits, {in_, out_}, off_);
+    if constexpr (sizeof(T) <= 4) {
+        if (pl.vec) {
+            const unsigned grid = blocks_for(pl.total_vec);
+            const bool k9 = (q.kh == 3 && q.kw == 3);
+#define LAUNCH_FWD(KP, LG)                                                               \
+    fwd_vec_kernel<T, KP, LG><<<grid, kThreads, 0, st>>>(in, off, mask, out, q,          \
+                                                         pl.vec_per_pix, pl.lanes_per_group, \
+                                                         pl.total_vec)
+            if (k9 && logits) LAUNCH_FWD(9, true);
+            else if (k9) LAUNCH_FWD(9, false);
+            else LAUNCH_FWD(0, false);
+#undef LAUNCH_FWD
+            return 0;
+        }
+    }
+    const size_t total = n_pix * q.C;
+    if (blocks_for(total) == 0 || total / kThreads >= (1ull << 31))
+        return fail(DCNV3_B200_ERANGE, "output too large for one launch");
+    if (logits) fwd_any_kernel<T, true><<<blocks_for(total), kThreads, 0, st>>>(in, off, mask, out, q, total);
+    else fwd_any_kernel<T, false><<<blocks_for(total), kThreads, 0, st>>>(in, off, mask, out, q, total);
+    return 0;
+}
+
+// ----------------------------------------------------------------- backward
+template <typename T, typename A>
+int backward_launch(const T *in, const T *off, const T *mask, const T *gout, A *acc, T *goff,
+                    T *gmask, const Geo &q, bool logits, const Plan &pl, size_t n_pix,
+                    cudaStream_t st) {
+    if constexpr (sizeof(T) <= 4) {
+        if (pl.vec) {
+            const unsigned grid = blocks_for(pl.total_vec);
+            const bool k9 = (q.kh == 3 && q.kw == 3);
+#define LAUNCH_BWD(KP, LG)                                                                  \
+    bwd_vec_kernel<T, A, KP, LG><<<grid, kThreads, 0, st>>>(in, off, mask, gout, acc, goff, \
+                                                            gmask, q, pl.vec_per_pix,       \
+                                                            pl.lanes_per_group, pl.total_vec)
+            if (k9 && logits) LAUNCH_BWD(9, true);
+            else if (k9) LAUNCH_BWD(9, false);
+            else LAUNCH_BWD(0, false);
+#undef LAUNCH_BWD
+            return 0;
+        }
+    }
+    const size_t n_units = n_pix * q.G;
+    const size_t threads = n_units * 32;
+    if (threads / kThreads >= (1ull << 31))
+        return fail(DCNV3_B200_ERANGE, "too many (pixel, group) units for one launch");
+    if (logits) {
+        if (q.P > kMaxSoftmaxP)
+            return fail(DCNV3_B200_EINVAL, "fused softmax supports at most %d sampling points (got %d)",
+                        kMaxSoftmaxP, q.P);
+        bwd_any_kernel<T, A, true><<<blocks_for(threads), kThreads, 0, st>>>(in, off, mask, gout, acc, goff, gmask, q, n_units);
+    } else {
+        bwd_any_kernel<T, A, false><<<blocks_for(threads), kThreads, 0, st>>>(in, off, mask, gout, acc, goff, gmask, q, n_units);
+    }
+    return 0;
+}
+
+template <typename T>
+int backward_t(const void *in_, const void *off_, const void *mask_, const void *gout_,
+               void *gin_, void *goff_, void *gmask_, void *ws, size_t ws_bytes, const Geo &q,
+               bool logits, int grad_accum, cudaStream_t st) {
+    using M = typename OpMath<T>::type;
+    const T *in = (const T *)in_, *off = (const T *)off_, *mask = (const T *)mask_;
+    const T *gout = (const T *)gout_;
+    T *gin = (T *)gin_, *goff = (T *)goff_, *gmask = (T *)gmask_;
+    const size_t n_in = (size_t)q.N * q.H * q.W * q.C;
+    const size_t n_pix = (size_t)q.N * q.Ho * q.Wo;
+    if (n_in == 0) return 0;
+    cudaError_t e;
+    constexpr bool lowp = sizeof(T) == 2;
+    if (lowp && grad_accum == DCNV3_B200_ACC_OPMATH) {
+        // reference semantics (dcnv3_cuda.cu:126-133,168-170): fp32 accumulation, one rounding
+        const size_t need = n_in * sizeof(float);
+        if (!ws || ws_bytes < need)
+            return fail(DCNV3_B200_EWORKSPACE, "workspace of %zu bytes required, got %zu", need, ws ? ws_bytes : 0);
+        if (!aligned16(ws)) return fail(DCNV3_B200_EALIGN, "workspace must be 16-byte aligned");
+        float *acc = (float *)ws;
+        if ((e = cudaMemsetAsync(acc, 0, need, st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
+        if (n_pix) {
+            const Plan pl = plan_vec<T>(q, n_pix, logits, {in_, gout_, ws}, off_);
+            int rc = backward_launch<T, float>(in, off, mask, gout, acc, goff, gmask, q, logits, pl, n_pix, st);
+            if (rc) return rc;
+        }
+        if constexpr (lowp) {
+            const bool v8 = aligned16(gin_);
+            const size_t n8 = v8 ? n_in / 8 : 0;
+            cast_ws_kernel<T><<<blocks_for(n8 + 1), kThreads, 0, st>>>(acc, gin, n8, n_in);
+        }
+        return 0;
+    }
+    // accumulate straight into grad_input (f32/f64 storage, or 16-bit ACC_STORAGE)
+    if ((e = cudaMemsetAsync(gin, 0, n_in * sizeof(T), st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_input)");
+    if (n_pix == 0) return 0;
+    const Plan pl = plan_vec<T>(q, n_pix, logits, {in_, gout_, gin_}, off_);
+    if constexpr (lowp) return backward_launch<T, T>(in, off, mask, gout, gin, goff, gmask, q, logits, pl, n_pix, st);
+    else return backward_launch<T, M>(in, off, mask, gout, (M *)gin, goff, gmask, q, logits, pl, n_pix, st);
+}
+
+int finish(cudaStream_t st, const char *what) {
+    (void)st;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dcnv3_b200_version(void) { return DCNV3_B200_VERSION; }
+
+const char *dcnv3_b200_last_error(void) { return g_err; }
+
+int dcnv3_b200_output_size(const dcnv3_b200_geometry *geo, int *Ho, int *Wo) {
+    Geo q;
+    int rc = make_geo(geo, q);
+    if (rc) return rc;
+    if (Ho) *Ho = q.Ho;
+    if (Wo) *Wo = q.Wo;
+    return 0;
+}
+
+int dcnv3_b200_forward(const void *input, const void *offset, const void *mask, void *output,
+                       int dtype, const dcnv3_b200_geometry *geo, int mask_is_logits,
+                       void *cuda_stream) {
+    g_err[0] = 0;
+    Geo q;
+    int rc = make_geo(geo, q);
+    if (rc) return rc;
+    if (!dtype_size(dtype)) return fail(DCNV3_B200_EINVAL, "unknown dtype %d", dtype);
+    if (mask_is_logits != 0 && mask_is_logits != 1) return fail(DCNV3_B200_EINVAL, "mask_is_logits must be 0 or 1");
+    if (q.N == 0) return 0;
+    if (!input || !offset || !mask || !output) return fail(DCNV3_B200_ENULL, "null tensor pointer");
+    if ((rc = check_device())) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const bool lg = mask_is_logits != 0;
+    switch (dtype) {
+        case DCNV3_B200_F32: rc = forward_t<float>(input, offset, mask, output, q, lg, st); break;
+        case DCNV3_B200_F16: rc = forward_t<__half>(input, offset, mask, output, q, lg, st); break;
+        case DCNV3_B200_BF16: rc = forward_t<__nv_bfloat16>(input, offset, mask, output, q, lg, st); break;
+        default: rc = forward_t<double>(input, offset, mask, output, q, lg, st); break;
+    }
+    if (rc) return rc;
+    return finish(st, "dcnv3_b200_forward launch");
+}
+
+size_t dcnv3_b200_backward_workspace_bytes(int dtype, const dcnv3_b200_geometry *geo, int grad_accum) {
+    Geo q;
+    if (make_geo(geo, q)) return 0;
+    if (dtype_size(dtype) == 2 && grad_accum == DCNV3_B200_ACC_OPMATH)
+        return (size_t)q.N * q.H * q.W * q.C * sizeof(float);
+    return 0;
+}
+
+int dcnv3_b200_backward(const void *input, const void *offset, const void *mask,
+                        const void *grad_output, void *grad_input, void *grad_offset,
+                        void *grad_mask, void *workspace, size_t workspace_bytes, int dtype,
+                        const dcnv3_b200_geometry *geo, int mask_is_logits, int grad_accum,
+                        void *cuda_stream) {
+    g_err[0] = 0;
+    Geo q;
+    int rc = make_geo(geo, q);
+    if (rc) return rc;
+    if (!dtype_size(dtype)) return fail(DCNV3_B200_EINVAL, "unknown dtype %d", dtype);
+    if (mask_is_logits != 0 && mask_is_logits != 1) return fail(DCNV3_B200_EINVAL, "mask_is_logits must be 0 or 1");
+    if (grad_accum != DCNV3_B200_ACC_OPMATH && grad_accum != DCNV3_B200_ACC_STORAGE)
+        return fail(DCNV3_B200_EINVAL, "unknown grad_accum %d", grad_accum);
+    if (q.N == 0) return 0;
+    if (!input || !offset || !mask || !grad_output || !grad_input || !grad_offset || !grad_mask)
+        return fail(DCNV3_B200_ENULL, "null tensor pointer");
+    if ((rc = check_device())) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const bool lg = mask_is_logits != 0;
+#define BWD(T) backward_t<T>(input, offset, mask, grad_output, grad_input, grad_offset, grad_mask, \
+                             workspace, workspace_bytes, q, lg, grad_accum, st)
+    switch (dtype) {
+        case DCNV3_B200_F32: rc = BWD(float); break;
+        case DCNV3_B200_F16: rc = BWD(__half); break;
+        case DCNV3_B200_BF16: rc = BWD(__nv_bfloat16); break;
+        default: rc = BWD(double); break;
+    }
+#undef BWD
+    if (rc) return rc;
+    return finish(st, "dcnv3_b200_backward launch");
+}
+
+int dcnv3_b200_debug_indices(const void *offset, int32_t *hw_low, uint8_t *bounds, int dtype,
+                             const dcnv3_b200_geometry *geo, void *cuda_stream) {
+    g_err[0] = 0;
+    Geo q;
+    int rc = make_geo(geo, q);
+    if (rc) return rc;
+    if (!dtype_size(dtype)) return fail(DCNV3_B200_EINVAL, "unknown dtype %d", dtype);
+    if (q.N == 0) return 0;
+    if (!offset || !hw_low || !bounds) return fail(DCNV3_B200_ENULL, "null tensor pointer");
+    if ((rc = check_device())) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t total = (size_t)q.N * q.Ho * q.Wo * q.G * q.P;
+    const unsigned grid = blocks_for(total);
+    switch (dtype) {
+        case DCNV3_B200_F32: indices_kernel<float><<<grid, kThreads, 0, st>>>((const float *)offset, hw_low, bounds, q, total); break;
+        case DCNV3_B200_F16: indices_kernel<__half><<<grid, kThreads, 0, st>>>((const __half *)offset, hw_low, bounds, q, total); break;
+        case DCNV3_B200_BF16: indices_kernel<__nv_bfloat16><<<grid, kThreads, 0, st>>>((const __nv_bfloat16 *)offset, hw_low, bounds, q, total); break;
+        default: indices_kernel<double><<<grid, kThreads, 0, st>>>((const double *)offset, hw_low, bounds, q, total); break;
+    }
+    return finish(st, "dcnv3_b200_debug_indices launch");
+}
+
+}  // extern "C"

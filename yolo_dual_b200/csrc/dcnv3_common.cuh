@@ -1,0 +1,230 @@
+// dcnv3_b200 — device-side building blocks shared by every kernel.
+//
+// Semantics follow the reference CUDA kernels
+// (/root/reference/models/ops_dcnv3/src/cuda/dcnv3_im2col_cuda.cuh); each block
+// cites the lines it reproduces.  Nothing here is derived from that file's
+// structure: the reference is one-thread-per-scalar SIMT, this is a
+// 16-byte-vector-per-thread design for sm_100a.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dcnv3 {
+
+// ---------------------------------------------------------------------------
+// geometry passed by value to every kernel
+// ---------------------------------------------------------------------------
+struct Geo {
+    int N, H, W, G, gc, C;
+    int kh, kw, sh, sw, ph, pw, dh, dw;
+    int Ho, Wo, P;
+    int half_h, half_w;  // (dilation*(kernel-1)) >> 1, cuh:232,235
+    float scale;         // offset_scale
+};
+
+// storage type -> op-math type (at::opmath_type, cuh:30): float for 16/32-bit, double for f64
+template <typename T> struct OpMath { using type = float; };
+template <> struct OpMath<double> { using type = double; };
+
+__device__ __forceinline__ float to_math(float v) { return v; }
+__device__ __forceinline__ float to_math(__half v) { return __half2float(v); }
+__device__ __forceinline__ float to_math(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ double to_math(double v) { return v; }
+
+template <typename T> __device__ __forceinline__ T from_math(float v);
+template <> __device__ __forceinline__ float from_math<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_math<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_math<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <typename T> __device__ __forceinline__ T from_math(double v);
+template <> __device__ __forceinline__ double from_math<double>(double v) { return v; }
+
+// Separately rounded IEEE ops: the location arithmetic below must never be
+// contracted into FMAs, or floor() flips on cell borders and the corner
+// indices stop being bit-exact against the CPU oracle (SURVEY §7 hard part 1).
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ int floor_to_int(float v) { return __float2int_rd(v); }
+__device__ __forceinline__ int floor_to_int(double v) { return __double2int_rd(v); }
+
+// ---------------------------------------------------------------------------
+// One sampling point: location (cuh:249-260), gate (cuh:262-263), corners and
+// validity (cuh:39-42,57,62,67,72), fractional weights (cuh:44-46).
+// ---------------------------------------------------------------------------
+enum : unsigned { B_INSIDE = 1u, B_C1 = 2u, B_C2 = 4u, B_C3 = 8u, B_C4 = 16u };
+
+template <typename M> struct Point {
+    int h_low, w_low;
+    M lh, lw, hh, hw;
+    unsigned bits;  // B_INSIDE | corner validity, 0 when the gate is closed
+};
+
+// Top-left of the kernel window in op-math, cuh:232-236 and :249-252.
+template <typename M>
+__device__ __forceinline__ void window_origin(const Geo &q, int ho, int wo, M &p0h_, M &p0w_) {
+    const M s = (M)q.scale;
+    const int p0_w = q.half_w - q.pw + wo * q.sw;
+    const int p0_h = q.half_h - q.ph + ho * q.sh;
+    p0w_ = sub_rn((M)p0_w, mul_rn((M)q.half_w, s));
+    p0h_ = sub_rn((M)p0_h, mul_rn((M)q.half_h, s));
+}
+
+// i indexes kernel_w (outer loop), j kernel_h (inner): p = i*kh + j, cuh:253-254.
+template <typename M>
+__device__ __forceinline__ void locate(const Geo &q, M p0h_, M p0w_, int i, int j, M off_w,
+                                       M off_h, Point<M> &t) {
+    const M s = (M)q.scale;
+    const M loc_w = add_rn(p0w_, mul_rn(add_rn((M)(i * q.dw), off_w), s));
+    const M loc_h = add_rn(p0h_, mul_rn(add_rn((M)(j * q.dh), off_h), s));
+    const bool inside = loc_h > (M)-1 && loc_w > (M)-1 && loc_h < (M)q.H && loc_w < (M)q.W;
+    t.bits = 0u;
+    t.h_low = 0;
+    t.w_low = 0;
+    t.lh = t.lw = t.hh = t.hw = (M)0;
+    if (inside) {
+        const int h_low = floor_to_int(loc_h);
+        const int w_low = floor_to_int(loc_w);
+        t.h_low = h_low;
+        t.w_low = w_low;
+        t.lh = sub_rn(loc_h, (M)h_low);
+        t.lw = sub_rn(loc_w, (M)w_low);
+        t.hh = sub_rn((M)1, t.lh);
+        t.hw = sub_rn((M)1, t.lw);
+        const bool h0 = h_low >= 0, w0 = w_low >= 0;
+        const bool h1 = h_low + 1 <= q.H - 1, w1 = w_low + 1 <= q.W - 1;
+        t.bits = B_INSIDE | (h0 && w0 ? B_C1 : 0u) | (h0 && w1 ? B_C2 : 0u) |
+                 (h1 && w0 ? B_C3 : 0u) | (h1 && w1 ? B_C4 : 0u);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// 16-byte channel vectors
+// ---------------------------------------------------------------------------
+template <typename T> struct Vec { static constexpr int N = 16 / (int)sizeof(T); };
+
+__device__ __forceinline__ uint4 ldg128(const void *p) {
+    return __ldg(reinterpret_cast<const uint4 *>(p));
+}
+
+// unpack 16 bytes of storage into op-math floats
+__device__ __forceinline__ void unpack(const uint4 &r, float (&v)[4], const float *) {
+    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y);
+    v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+}
+__device__ __forceinline__ void unpack(const uint4 &r, float (&v)[8], const __half *) {
+    const unsigned w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[k]));
+        v[2 * k] = f.x; v[2 * k + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void unpack(const uint4 &r, float (&v)[8], const __nv_bfloat16 *) {
+    const unsigned w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // bf16 -> f32 is a 16-bit shift
+        v[2 * k] = __uint_as_float(w[k] << 16);
+        v[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+    }
+}
+
+// pack op-math floats back to 16 bytes of storage (round to nearest even)
+__device__ __forceinline__ uint4 pack(const float (&v)[4], const float *) {
+    return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
+                      __float_as_uint(v[3]));
+}
+__device__ __forceinline__ uint4 pack(const float (&v)[8], const __half *) {
+    unsigned w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __half2 h = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+        w[k] = *reinterpret_cast<const unsigned *>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ uint4 pack(const float (&v)[8], const __nv_bfloat16 *) {
+    unsigned w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+        w[k] = *reinterpret_cast<const unsigned *>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// (offset_x, offset_y) of one point: one 8-byte (f32) or 4-byte (16-bit) load
+__device__ __forceinline__ float2 load_offset_pair(const float *p) {
+    return __ldg(reinterpret_cast<const float2 *>(p));
+}
+__device__ __forceinline__ float2 load_offset_pair(const __half *p) {
+    const unsigned u = __ldg(reinterpret_cast<const unsigned *>(p));
+    return __half22float2(*reinterpret_cast<const __half2 *>(&u));
+}
+__device__ __forceinline__ float2 load_offset_pair(const __nv_bfloat16 *p) {
+    const unsigned u = __ldg(reinterpret_cast<const unsigned *>(p));
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+
+// ---------------------------------------------------------------------------
+// vector reductions into global memory (sm_90+ PTX; REDG.E.ADD.{F32x4,F16x8,BF16x8})
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4_f32(float *p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b),
+                 "f"(c), "f"(d)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_v4_f16x2(__half *p, const uint4 &v) {
+    asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_v4_bf16x2(__nv_bfloat16 *p, const uint4 &v) {
+    asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+// grad_input[corner] += w * tg[0..VEC) for one corner, in the accumulation type A
+template <int VEC> struct RedAdd;
+template <> struct RedAdd<4> {
+    __device__ static __forceinline__ void run(float *dst, const float (&tg)[4], float w) {
+        red_add_v4_f32(dst, w * tg[0], w * tg[1], w * tg[2], w * tg[3]);
+    }
+};
+template <> struct RedAdd<8> {
+    // fp32 accumulation buffer (workspace), 8 channels = two v4.f32 reductions
+    __device__ static __forceinline__ void run(float *dst, const float (&tg)[8], float w) {
+        red_add_v4_f32(dst, w * tg[0], w * tg[1], w * tg[2], w * tg[3]);
+        red_add_v4_f32(dst + 4, w * tg[4], w * tg[5], w * tg[6], w * tg[7]);
+    }
+    __device__ static __forceinline__ void run(__half *dst, const float (&tg)[8], float w) {
+        float t[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[k] = w * tg[k];
+        red_add_v4_f16x2(dst, pack(t, (const __half *)nullptr));
+    }
+    __device__ static __forceinline__ void run(__nv_bfloat16 *dst, const float (&tg)[8], float w) {
+        float t[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[k] = w * tg[k];
+        red_add_v4_bf16x2(dst, pack(t, (const __nv_bfloat16 *)nullptr));
+    }
+};
+
+// scalar atomics for the generic path
+__device__ __forceinline__ void atomic_add(float *p, float v) { atomicAdd(p, v); }
+__device__ __forceinline__ void atomic_add(double *p, double v) { atomicAdd(p, v); }
+__device__ __forceinline__ void atomic_add(__half *p, float v) { atomicAdd(p, __float2half_rn(v)); }
+__device__ __forceinline__ void atomic_add(__nv_bfloat16 *p, float v) { atomicAdd(p, __float2bfloat16_rn(v)); }
+
+template <typename M> __device__ __forceinline__ M shfl_xor(M v, int m) {
+    return __shfl_xor_sync(0xffffffffu, v, m);
+}
+
+}  // namespace dcnv3

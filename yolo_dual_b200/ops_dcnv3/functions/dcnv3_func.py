@@ -1,0 +1,234 @@
+"""DCNv3Function — autograd front of the B200-native DCNv3 core.
+
+Mirrors the reference's ``DCNv3Function``
+(/root/reference/models/ops_dcnv3/build/lib.linux-x86_64-cpython-38/functions/dcnv3_func.py:19-89):
+same class name, same 15 positional arguments in the same order, same return
+arity from ``backward`` (3 grads + 12 ``None``), same ONNX symbolic.  Underneath,
+the pybind module ``DCNv3`` (dcnv3_func.py:16,39,54) is replaced by the C-ABI
+library ``libdcnv3_b200.so`` (include/dcnv3_b200.h) called through ctypes.
+
+Deliberate differences, all documented in DESIGN.md:
+  * bf16 is accepted (the reference dispatches double/float/half only,
+    src/cuda/dcnv3_cuda.cu:69,147);
+  * ``im2col_step`` keeps its position and the reference's divisibility check
+    (dcnv3_cuda.cu:46-49) but the whole batch is always one launch;
+  * 16-bit gradients come back in the storage dtype after fp32 accumulation
+    (same as dcnv3_cuda.cu:126-133,168-170) unless ``set_grad_accum('storage')``;
+  * ``DCNv3SoftmaxFunction`` is the same op with the softmax over the sampling
+    points fused in (``mask`` carries logits).
+
+``dcnv3_core_pytorch`` (dcnv3_func.py:148-189) is NOT exported from the product
+package: it is the oracle and lives under ``oracle/`` as test infrastructure.
+There is no CPU path (reference: src/cpu/dcnv3_cpu.cpp:25,36 raise too).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from ... import _lib
+
+_DTYPES = {
+    torch.float32: _lib.F32,
+    torch.float16: _lib.F16,
+    torch.bfloat16: _lib.BF16,
+    torch.float64: _lib.F64,
+}
+
+_GRAD_ACCUM = {"opmath": _lib.ACC_OPMATH, "storage": _lib.ACC_STORAGE}
+_grad_accum = _GRAD_ACCUM[os.environ.get("DCNV3_B200_GRAD_ACCUM", "opmath")]
+
+
+def set_grad_accum(mode: str) -> None:
+    """How grad_input is accumulated for fp16/bf16 storage.
+
+    'opmath'  (default) fp32 workspace, rounded once — the reference's semantics;
+    'storage' packed 16-bit vector reductions straight into grad_input (faster, one
+              rounding per contribution)."""
+    global _grad_accum
+    _grad_accum = _GRAD_ACCUM[mode]
+
+
+def get_grad_accum() -> str:
+    return {v: k for k, v in _GRAD_ACCUM.items()}[_grad_accum]
+
+
+def _geometry(input, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w,
+              group, group_channels, offset_scale):
+    N, H, W, _ = input.shape
+    return _lib.Geometry(int(N), int(H), int(W), int(kernel_h), int(kernel_w), int(stride_h),
+                         int(stride_w), int(pad_h), int(pad_w), int(dilation_h), int(dilation_w),
+                         int(group), int(group_channels), float(offset_scale))
+
+
+def _check_inputs(input, offset, mask, geo, im2col_step):
+    """The reference's AT_ASSERTMs (dcnv3_cuda.cu:29-34,48-53) plus the shape algebra it left
+    to luck; raises the same exception types."""
+    for name, t in (("input", input), ("offset", offset), ("mask", mask)):
+        if not t.is_cuda:
+            # reference: AT_ERROR("Not implement on cpu"), src/cpu/dcnv3_cpu.cpp:25,36
+            raise NotImplementedError(f"Not implement on cpu ({name} is on {t.device}); "
+                                      "dcnv3_b200 has no CPU path")
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")
+    if input.dim() != 4 or offset.dim() != 4 or mask.dim() != 4:
+        raise RuntimeError("input, offset and mask must be 4-D channel-last tensors")
+    if not (input.dtype == offset.dtype == mask.dtype):
+        raise RuntimeError(f"input/offset/mask dtypes differ: {input.dtype}, {offset.dtype}, {mask.dtype}")
+    if input.dtype not in _DTYPES:
+        raise RuntimeError(f"unsupported dtype {input.dtype}")
+    if not (input.device == offset.device == mask.device):
+        raise RuntimeError("input, offset and mask must live on the same device")
+    N, H, W, C = input.shape
+    if C != geo.group * geo.group_channels:
+        raise RuntimeError(f"Input channels and group times group channels wont match: "
+                           f"({C} vs {geo.group * geo.group_channels}).")
+    step = min(N, int(im2col_step)) if N else 1
+    if step <= 0 or N % step != 0:
+        raise RuntimeError(f"batch({N}) must divide im2col_step({step})")
+    lib = _lib.load()
+    ho, wo = ctypes.c_int(), ctypes.c_int()
+    _lib.check(lib.dcnv3_b200_output_size(ctypes.byref(geo), ctypes.byref(ho), ctypes.byref(wo)),
+               "dcnv3_b200_output_size")
+    P = geo.kernel_h * geo.kernel_w
+    want_off = (N, ho.value, wo.value, geo.group * P * 2)
+    want_mask = (N, ho.value, wo.value, geo.group * P)
+    if tuple(offset.shape) != want_off:
+        raise RuntimeError(f"offset shape {tuple(offset.shape)} != {want_off}")
+    if tuple(mask.shape) != want_mask:
+        raise RuntimeError(f"mask shape {tuple(mask.shape)} != {want_mask}")
+    return ho.value, wo.value
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _forward(ctx, logits, input, offset, mask, kernel_h, kernel_w, stride_h, stride_w, pad_h,
+             pad_w, dilation_h, dilation_w, group, group_channels, offset_scale, im2col_step):
+    ctx.kernel_h, ctx.kernel_w = kernel_h, kernel_w
+    ctx.stride_h, ctx.stride_w = stride_h, stride_w
+    ctx.pad_h, ctx.pad_w = pad_h, pad_w
+    ctx.dilation_h, ctx.dilation_w = dilation_h, dilation_w
+    ctx.group, ctx.group_channels = group, group_channels
+    ctx.offset_scale, ctx.im2col_step = offset_scale, im2col_step
+    geo = _geometry(input, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h,
+                    dilation_w, group, group_channels, offset_scale)
+    Ho, Wo = _check_inputs(input, offset, mask, geo, im2col_step)
+    lib = _lib.load()
+    with torch.cuda.device_of(input):
+        output = torch.empty((input.shape[0], Ho, Wo, input.shape[3]), dtype=input.dtype,
+                             device=input.device)
+        rc = lib.dcnv3_b200_forward(input.data_ptr(), offset.data_ptr(), mask.data_ptr(),
+                                    output.data_ptr(), _DTYPES[input.dtype], ctypes.byref(geo),
+                                    int(logits), _stream(input.device))
+    _lib.check(rc, "dcnv3_b200_forward")
+    ctx.save_for_backward(input, offset, mask)
+    return output
+
+
+def _backward(ctx, logits, grad_output):
+    input, offset, mask = ctx.saved_tensors
+    grad_output = grad_output.contiguous()  # dcnv3_func.py:58
+    if grad_output.dtype != input.dtype:
+        grad_output = grad_output.to(input.dtype)
+    geo = _geometry(input, ctx.kernel_h, ctx.kernel_w, ctx.stride_h, ctx.stride_w, ctx.pad_h,
+                    ctx.pad_w, ctx.dilation_h, ctx.dilation_w, ctx.group, ctx.group_channels,
+                    ctx.offset_scale)
+    lib = _lib.load()
+    dt = _DTYPES[input.dtype]
+    with torch.cuda.device_of(input):
+        grad_input = torch.empty_like(input)
+        grad_offset = torch.empty_like(offset)
+        grad_mask = torch.empty_like(mask)
+        ws_bytes = lib.dcnv3_b200_backward_workspace_bytes(dt, ctypes.byref(geo), _grad_accum)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=input.device) if ws_bytes else None
+        rc = lib.dcnv3_b200_backward(
+            input.data_ptr(), offset.data_ptr(), mask.data_ptr(), grad_output.data_ptr(),
+            grad_input.data_ptr(), grad_offset.data_ptr(), grad_mask.data_ptr(),
+            ws.data_ptr() if ws is not None else None, ws_bytes, dt, ctypes.byref(geo),
+            int(logits), _grad_accum, _stream(input.device))
+    _lib.check(rc, "dcnv3_b200_backward")
+    return (grad_input, grad_offset, grad_mask,
+            None, None, None, None, None, None, None, None, None, None, None, None)
+
+
+def _symbolic(g, input, offset, mask, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
+              dilation_h, dilation_w, group, group_channels, offset_scale, im2col_step):
+    """ONNX node of the reference (dcnv3_func.py:63-89): mmdeploy::TRTDCNv3."""
+    return g.op(
+        "mmdeploy::TRTDCNv3", input, offset, mask,
+        kernel_h_i=int(kernel_h), kernel_w_i=int(kernel_w),
+        stride_h_i=int(stride_h), stride_w_i=int(stride_w),
+        pad_h_i=int(pad_h), pad_w_i=int(pad_w),
+        dilation_h_i=int(dilation_h), dilation_w_i=int(dilation_w),
+        group_i=int(group), group_channels_i=int(group_channels),
+        offset_scale_f=float(offset_scale), im2col_step_i=int(im2col_step))
+
+
+class DCNv3Function(Function):
+    """``DCNv3Function.apply(input, offset, mask, kernel_h, kernel_w, stride_h, stride_w, pad_h,
+    pad_w, dilation_h, dilation_w, group, group_channels, offset_scale, im2col_step)``"""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, input, offset, mask, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
+                dilation_h, dilation_w, group, group_channels, offset_scale, im2col_step):
+        return _forward(ctx, False, input, offset, mask, kernel_h, kernel_w, stride_h, stride_w,
+                        pad_h, pad_w, dilation_h, dilation_w, group, group_channels, offset_scale,
+                        im2col_step)
+
+    @staticmethod
+    @once_differentiable
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_output):
+        return _backward(ctx, False, grad_output)
+
+    symbolic = staticmethod(_symbolic)
+
+
+class DCNv3SoftmaxFunction(Function):
+    """Same signature; ``mask`` holds the pre-softmax logits and the softmax over the
+    kernel_h*kernel_w sampling points of each group (modules/dcnv3.py:122-123 in the reference)
+    runs inside the kernels.  ``backward`` returns the gradient w.r.t. the logits."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, input, offset, mask, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
+                dilation_h, dilation_w, group, group_channels, offset_scale, im2col_step):
+        return _forward(ctx, True, input, offset, mask, kernel_h, kernel_w, stride_h, stride_w,
+                        pad_h, pad_w, dilation_h, dilation_w, group, group_channels, offset_scale,
+                        im2col_step)
+
+    @staticmethod
+    @once_differentiable
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_output):
+        return _backward(ctx, True, grad_output)
+
+
+def dcnv3_debug_indices(offset, H, W, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
+                        dilation_h, dilation_w, group, offset_scale):
+    """The integer contract of the kernels: (hw_low int32 [N,Ho,Wo,G,P,2], bounds uint8
+    [N,Ho,Wo,G,P]) for a CUDA ``offset`` tensor.  See include/dcnv3_b200.h."""
+    if not offset.is_cuda:
+        raise NotImplementedError("Not implement on cpu")
+    offset = offset.contiguous()
+    N, Ho, Wo, _ = offset.shape
+    P = kernel_h * kernel_w
+    geo = _lib.Geometry(int(N), int(H), int(W), int(kernel_h), int(kernel_w), int(stride_h),
+                        int(stride_w), int(pad_h), int(pad_w), int(dilation_h), int(dilation_w),
+                        int(group), 1, float(offset_scale))
+    lib = _lib.load()
+    with torch.cuda.device_of(offset):
+        hw = torch.empty((N, Ho, Wo, group, P, 2), dtype=torch.int32, device=offset.device)
+        bd = torch.empty((N, Ho, Wo, group, P), dtype=torch.uint8, device=offset.device)
+        rc = lib.dcnv3_b200_debug_indices(offset.data_ptr(), hw.data_ptr(), bd.data_ptr(),
+                                          _DTYPES[offset.dtype], ctypes.byref(geo),
+                                          _stream(offset.device))
+    _lib.check(rc, "dcnv3_b200_debug_indices")
+    return hw, bd
