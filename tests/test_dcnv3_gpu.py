@@ -306,15 +306,30 @@ def test_full_size_properties(site, dtype, fn):
     want = F.avg_pool2d(x.float().permute(0, 3, 1, 2), 3, 1, 1, count_include_pad=True).permute(0, 2, 3, 1)
     want = want * 9 * float(u.flatten()[0])
     torch.testing.assert_close(ya.float(), want.contiguous(), **(dict(rtol=1e-2, atol=1e-2) if lowp else dict(rtol=1e-5, atol=1e-5)))
-    # (e) grad_offset against a central finite difference of <go, f> along a random direction (fp32 only)
+    # (e) closed form for grad_offset: on a linear ramp input[h, w, c] = a_c*w + b_c*h + d_c bilinear
+    #     sampling is exact, so wherever all four corners are valid
+    #         d/d(off_x[p]) = offset_scale * m_p * sum_c go_c a_c,   d/d(off_y[p]) = ... b_c
     if not lowp:
-        d = torch.randn_like(off)
-        h = 1e-2
-        fp = (go.double() * fn.apply(x, off + h * d, m, *args).double()).sum()
-        fm = (go.double() * fn.apply(x, off - h * d, m, *args).double()).sum()
-        fd = float(fp - fm) / (2 * h)
-        an = float((og.grad.double() * d.double()).sum())
-        assert abs(fd - an) <= 2e-2 * max(1.0, abs(an)), (fd, an)
+        from yolo_dual_b200.ops_dcnv3.functions import dcnv3_debug_indices
+        a_c = torch.randn(C, device=DEV, generator=gen) * 0.1
+        b_c = torch.randn(C, device=DEV, generator=gen) * 0.1
+        d_c = torch.randn(C, device=DEV, generator=gen)
+        ww = torch.arange(W, device=DEV, dtype=torch.float32).view(1, 1, W, 1)
+        hh = torch.arange(H, device=DEV, dtype=torch.float32).view(1, H, 1, 1)
+        ramp = (a_c * ww + b_c * hh + d_c).expand(N, H, W, C).contiguous().requires_grad_(True)
+        o2 = off.clone().requires_grad_(True)
+        scale = 1.5
+        args2 = (3, 3, 1, 1, 1, 1, 1, 1, G, gc, scale, 256)
+        fn.apply(ramp, o2, m, *args2).backward(go)
+        _, bd = dcnv3_debug_indices(off, H, W, 3, 3, 1, 1, 1, 1, 1, 1, G, scale)
+        full = (bd == 31).unsqueeze(-1)                                    # [N,H,W,G,P,1]
+        gog = go.view(N, H, W, G, gc)
+        sa = (gog * a_c.view(G, gc)).sum(-1)                               # [N,H,W,G]
+        sb = (gog * b_c.view(G, gc)).sum(-1)
+        want_o = scale * m.view(N, H, W, G, P, 1) * torch.stack((sa, sb), -1).unsqueeze(-2)
+        got_o = o2.grad.view(N, H, W, G, P, 2)
+        assert float(full.float().mean()) > 0.5
+        torch.testing.assert_close(got_o * full, want_o * full, rtol=1e-3, atol=1e-3)
 
 
 # ------------------------------------------------------------------------------------------
