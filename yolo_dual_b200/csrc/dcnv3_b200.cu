@@ -8,7 +8,9 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 
 #include "dcnv3_kernels.cuh"
 
@@ -105,30 +107,56 @@ bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 struct Plan {
     bool vec;
+    int bpl;  // bytes of channels per lane: 16 (LDG.128) or 32 (LDG.256)
     int vec_per_pix, lanes_per_group;
     unsigned total_vec;
 };
 
-// Can this call take the 16-byte-vector kernels?
+bool aligned_to(const void *p, int a) { return (reinterpret_cast<uintptr_t>(p) & (uintptr_t)(a - 1)) == 0; }
+
+// Tuning knob (read once): DCNV3_B200_BPL=16|32 forces the bytes-per-lane of the vector path.
+int forced_bpl() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("DCNV3_B200_BPL");
+        v = e ? atoi(e) : 0;
+        if (v != 16 && v != 32) v = 0;
+    }
+    return v;
+}
+
+// Can this call take the vector kernels, and with how many bytes per lane?
+// `ptrs` are the channel-vector tensors (input, output / grad_output): they must be aligned to
+// the lane width.  `off` only needs the alignment of one (x, y) pair.
 template <typename T>
 Plan plan_vec(const Geo &q, size_t n_pix, bool logits, std::initializer_list<const void *> ptrs,
-              const void *off) {
-    Plan pl{false, 0, 0, 0};
+              const void *off, size_t acc_elem) {
+    Plan pl{false, 0, 0, 0, 0};
     if (sizeof(T) > 4) return pl;  // f64 always generic
-    constexpr int VEC = 16 / (int)sizeof(T);
-    if (q.gc % VEC) return pl;
-    const int L = q.gc / VEC;
-    if (!is_pow2(L) || L > 32) return pl;
     if (logits && !(q.kh == 3 && q.kw == 3)) return pl;
-    for (const void *p : ptrs)
-        if (!aligned16(p)) return pl;
     if (reinterpret_cast<uintptr_t>(off) & (2 * sizeof(T) - 1)) return pl;
-    const unsigned long long tv = (unsigned long long)n_pix * (q.C / VEC);
-    if (tv >= (1ull << 31)) return pl;
-    pl.vec = true;
-    pl.vec_per_pix = q.C / VEC;
-    pl.lanes_per_group = L;
-    pl.total_vec = (unsigned)tv;
+    // byte offsets inside one image are 32-bit ints in the kernels
+    if ((unsigned long long)q.H * q.W * q.C * (acc_elem > sizeof(T) ? acc_elem : sizeof(T)) >= (1ull << 31)) return pl;
+    const int want = forced_bpl();
+    for (int bpl : {32, 16}) {
+        if (want && bpl != want) continue;
+        if (!want && bpl == 32) continue;  // default: 16 bytes per lane (kernel table)
+        const int ch = bpl / (int)sizeof(T);
+        if (q.gc % ch) continue;
+        const int L = q.gc / ch;
+        if (!is_pow2(L) || L > 32) continue;
+        bool ok = true;
+        for (const void *p : ptrs) ok = ok && aligned_to(p, bpl);
+        if (!ok) continue;
+        const unsigned long long tv = (unsigned long long)n_pix * (q.C / ch);
+        if (tv >= (1ull << 31)) continue;
+        pl.vec = true;
+        pl.bpl = bpl;
+        pl.vec_per_pix = q.C / ch;
+        pl.lanes_per_group = L;
+        pl.total_vec = (unsigned)tv;
+        return pl;
+    }
     return pl;
 }
 
@@ -142,18 +170,21 @@ int forward_t(const void *in_, const void *off_, const void *mask_, void *out_, 
     T *out = (T *)out_;
     const size_t n_pix = (size_t)q.N * q.Ho * q.Wo;
     if (n_pix == 0) return 0;
-    const Plan pl = plan_vec<T>(q, n_pix, logits, {in_, out_}, off_);
+    const Plan pl = plan_vec<T>(q, n_pix, logits, {in_, out_}, off_, sizeof(T));
     if constexpr (sizeof(T) <= 4) {
         if (pl.vec) {
             const unsigned grid = blocks_for(pl.total_vec);
             const bool k9 = (q.kh == 3 && q.kw == 3);
-#define LAUNCH_FWD(KP, LG)                                                               \
-    fwd_vec_kernel<T, KP, LG><<<grid, kThreads, 0, st>>>(in, off, mask, out, q,          \
-                                                         pl.vec_per_pix, pl.lanes_per_group, \
-                                                         pl.total_vec)
-            if (k9 && logits) LAUNCH_FWD(9, true);
-            else if (k9) LAUNCH_FWD(9, false);
-            else LAUNCH_FWD(0, false);
+#define LAUNCH_FWD(BPL, KP, LG)                                                               \
+    fwd_vec_kernel<T, BPL, KP, LG><<<grid, kThreads, 0, st>>>(in, off, mask, out, q,          \
+                                                              pl.vec_per_pix, pl.lanes_per_group, \
+                                                              pl.total_vec)
+#define LAUNCH_FWD_B(BPL)                      \
+    if (k9 && logits) LAUNCH_FWD(BPL, 9, true); \
+    else if (k9) LAUNCH_FWD(BPL, 9, false);     \
+    else LAUNCH_FWD(BPL, 0, false)
+            if (pl.bpl == 32) { LAUNCH_FWD_B(32); } else { LAUNCH_FWD_B(16); }
+#undef LAUNCH_FWD_B
 #undef LAUNCH_FWD
             return 0;
         }
@@ -175,13 +206,16 @@ int backward_launch(const T *in, const T *off, const T *mask, const T *gout, A *
         if (pl.vec) {
             const unsigned grid = blocks_for(pl.total_vec);
             const bool k9 = (q.kh == 3 && q.kw == 3);
-#define LAUNCH_BWD(KP, LG)                                                                  \
-    bwd_vec_kernel<T, A, KP, LG><<<grid, kThreads, 0, st>>>(in, off, mask, gout, acc, goff, \
-                                                            gmask, q, pl.vec_per_pix,       \
-                                                            pl.lanes_per_group, pl.total_vec)
-            if (k9 && logits) LAUNCH_BWD(9, true);
-            else if (k9) LAUNCH_BWD(9, false);
-            else LAUNCH_BWD(0, false);
+#define LAUNCH_BWD(BPL, KP, LG)                                                                  \
+    bwd_vec_kernel<T, A, BPL, KP, LG><<<grid, kThreads, 0, st>>>(in, off, mask, gout, acc, goff, \
+                                                                 gmask, q, pl.vec_per_pix,       \
+                                                                 pl.lanes_per_group, pl.total_vec)
+#define LAUNCH_BWD_B(BPL)                      \
+    if (k9 && logits) LAUNCH_BWD(BPL, 9, true); \
+    else if (k9) LAUNCH_BWD(BPL, 9, false);     \
+    else LAUNCH_BWD(BPL, 0, false)
+            if (pl.bpl == 32) { LAUNCH_BWD_B(32); } else { LAUNCH_BWD_B(16); }
+#undef LAUNCH_BWD_B
 #undef LAUNCH_BWD
             return 0;
         }
@@ -223,7 +257,7 @@ int backward_t(const void *in_, const void *off_, const void *mask_, const void 
         float *acc = (float *)ws;
         if ((e = cudaMemsetAsync(acc, 0, need, st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
         if (n_pix) {
-            const Plan pl = plan_vec<T>(q, n_pix, logits, {in_, gout_, ws}, off_);
+            const Plan pl = plan_vec<T>(q, n_pix, logits, {in_, gout_}, off_, sizeof(float));
             int rc = backward_launch<T, float>(in, off, mask, gout, acc, goff, gmask, q, logits, pl, n_pix, st);
             if (rc) return rc;
         }
@@ -237,7 +271,7 @@ int backward_t(const void *in_, const void *off_, const void *mask_, const void 
     // accumulate straight into grad_input (f32/f64 storage, or 16-bit ACC_STORAGE)
     if ((e = cudaMemsetAsync(gin, 0, n_in * sizeof(T), st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_input)");
     if (n_pix == 0) return 0;
-    const Plan pl = plan_vec<T>(q, n_pix, logits, {in_, gout_, gin_}, off_);
+    const Plan pl = aligned16(gin_) ? plan_vec<T>(q, n_pix, logits, {in_, gout_}, off_, sizeof(T)) : Plan{false, 0, 0, 0, 0};
     if constexpr (lowp) return backward_launch<T, T>(in, off, mask, gout, gin, goff, gmask, q, logits, pl, n_pix, st);
     else return backward_launch<T, M>(in, off, mask, gout, (M *)gin, goff, gmask, q, logits, pl, n_pix, st);
 }

@@ -60,9 +60,14 @@ __device__ __forceinline__ int floor_to_int(double v) { return __double2int_rd(v
 enum : unsigned { B_INSIDE = 1u, B_C1 = 2u, B_C2 = 4u, B_C3 = 8u, B_C4 = 16u };
 
 template <typename M> struct Point {
-    int h_low, w_low;
-    M lh, lw, hh, hw;
-    unsigned bits;  // B_INSIDE | corner validity, 0 when the gate is closed
+    int h_low, w_low;        // (0, 0) when the gate is closed
+    M lh, lw, hh, hw;        // all 0 when the gate is closed: every corner weight is then 0
+    bool inside;             // gate, cuh:262-263
+    bool ok1, ok2, ok3, ok4; // corner validity (false when the gate is closed)
+    __device__ __forceinline__ unsigned bits() const {  // the bounds byte of the integer contract
+        return (inside ? B_INSIDE : 0u) | (ok1 ? B_C1 : 0u) | (ok2 ? B_C2 : 0u) |
+               (ok3 ? B_C3 : 0u) | (ok4 ? B_C4 : 0u);
+    }
 };
 
 // Top-left of the kernel window in op-math, cuh:232-236 and :249-252.
@@ -76,6 +81,9 @@ __device__ __forceinline__ void window_origin(const Geo &q, int ho, int wo, M &p
 }
 
 // i indexes kernel_w (outer loop), j kernel_h (inner): p = i*kh + j, cuh:253-254.
+// Branch-free on purpose: with no divergent region per point the compiler can hoist the
+// corner loads of several points ahead of their use (memory-level parallelism per thread).
+// A closed gate yields zero weights and false validity, so nothing is read and 0 is added.
 template <typename M>
 __device__ __forceinline__ void locate(const Geo &q, M p0h_, M p0w_, int i, int j, M off_w,
                                        M off_h, Point<M> &t) {
@@ -83,24 +91,24 @@ __device__ __forceinline__ void locate(const Geo &q, M p0h_, M p0w_, int i, int 
     const M loc_w = add_rn(p0w_, mul_rn(add_rn((M)(i * q.dw), off_w), s));
     const M loc_h = add_rn(p0h_, mul_rn(add_rn((M)(j * q.dh), off_h), s));
     const bool inside = loc_h > (M)-1 && loc_w > (M)-1 && loc_h < (M)q.H && loc_w < (M)q.W;
-    t.bits = 0u;
-    t.h_low = 0;
-    t.w_low = 0;
-    t.lh = t.lw = t.hh = t.hw = (M)0;
-    if (inside) {
-        const int h_low = floor_to_int(loc_h);
-        const int w_low = floor_to_int(loc_w);
-        t.h_low = h_low;
-        t.w_low = w_low;
-        t.lh = sub_rn(loc_h, (M)h_low);
-        t.lw = sub_rn(loc_w, (M)w_low);
-        t.hh = sub_rn((M)1, t.lh);
-        t.hw = sub_rn((M)1, t.lw);
-        const bool h0 = h_low >= 0, w0 = w_low >= 0;
-        const bool h1 = h_low + 1 <= q.H - 1, w1 = w_low + 1 <= q.W - 1;
-        t.bits = B_INSIDE | (h0 && w0 ? B_C1 : 0u) | (h0 && w1 ? B_C2 : 0u) |
-                 (h1 && w0 ? B_C3 : 0u) | (h1 && w1 ? B_C4 : 0u);
-    }
+    // float -> int saturates for out-of-range / NaN inputs; the results are discarded then
+    const int h_low = floor_to_int(loc_h);
+    const int w_low = floor_to_int(loc_w);
+    const M lh = sub_rn(loc_h, (M)h_low);
+    const M lw = sub_rn(loc_w, (M)w_low);
+    t.inside = inside;
+    t.h_low = inside ? h_low : 0;
+    t.w_low = inside ? w_low : 0;
+    t.lh = inside ? lh : (M)0;
+    t.lw = inside ? lw : (M)0;
+    t.hh = inside ? sub_rn((M)1, lh) : (M)0;
+    t.hw = inside ? sub_rn((M)1, lw) : (M)0;
+    const bool h0 = h_low >= 0, w0 = w_low >= 0;
+    const bool h1 = h_low + 1 <= q.H - 1, w1 = w_low + 1 <= q.W - 1;
+    t.ok1 = inside && h0 && w0;
+    t.ok2 = inside && h0 && w1;
+    t.ok3 = inside && h1 && w0;
+    t.ok4 = inside && h1 && w1;
 }
 
 // ---------------------------------------------------------------------------
@@ -174,48 +182,27 @@ __device__ __forceinline__ float2 load_offset_pair(const __nv_bfloat16 *p) {
 // ---------------------------------------------------------------------------
 // vector reductions into global memory (sm_90+ PTX; REDG.E.ADD.{F32x4,F16x8,BF16x8})
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void red_add_v4_f32(float *p, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b),
-                 "f"(c), "f"(d)
+// The predicate lives inside the asm so each reduction is ONE predicated REDG (inline asm
+// under a C++ `if` becomes a branch + reconvergence region per reduction).
+__device__ __forceinline__ void red_add_v4_f32(float *p, float a, float b, float c, float d,
+                                               bool pred = true) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p), "f"(a), "f"(b),
+                 "f"(c), "f"(d), "r"((int)pred)
                  : "memory");
 }
-__device__ __forceinline__ void red_add_v4_f16x2(__half *p, const uint4 &v) {
-    asm volatile("red.global.add.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x),
-                 "r"(v.y), "r"(v.z), "r"(v.w)
+__device__ __forceinline__ void red_add_v4_f16x2(__half *p, const uint4 &v, bool pred = true) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q red.global.add.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w), "r"((int)pred)
                  : "memory");
 }
-__device__ __forceinline__ void red_add_v4_bf16x2(__nv_bfloat16 *p, const uint4 &v) {
-    asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x),
-                 "r"(v.y), "r"(v.z), "r"(v.w)
+__device__ __forceinline__ void red_add_v4_bf16x2(__nv_bfloat16 *p, const uint4 &v, bool pred = true) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w), "r"((int)pred)
                  : "memory");
 }
-
-// grad_input[corner] += w * tg[0..VEC) for one corner, in the accumulation type A
-template <int VEC> struct RedAdd;
-template <> struct RedAdd<4> {
-    __device__ static __forceinline__ void run(float *dst, const float (&tg)[4], float w) {
-        red_add_v4_f32(dst, w * tg[0], w * tg[1], w * tg[2], w * tg[3]);
-    }
-};
-template <> struct RedAdd<8> {
-    // fp32 accumulation buffer (workspace), 8 channels = two v4.f32 reductions
-    __device__ static __forceinline__ void run(float *dst, const float (&tg)[8], float w) {
-        red_add_v4_f32(dst, w * tg[0], w * tg[1], w * tg[2], w * tg[3]);
-        red_add_v4_f32(dst + 4, w * tg[4], w * tg[5], w * tg[6], w * tg[7]);
-    }
-    __device__ static __forceinline__ void run(__half *dst, const float (&tg)[8], float w) {
-        float t[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) t[k] = w * tg[k];
-        red_add_v4_f16x2(dst, pack(t, (const __half *)nullptr));
-    }
-    __device__ static __forceinline__ void run(__nv_bfloat16 *dst, const float (&tg)[8], float w) {
-        float t[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) t[k] = w * tg[k];
-        red_add_v4_bf16x2(dst, pack(t, (const __nv_bfloat16 *)nullptr));
-    }
-};
 
 // scalar atomics for the generic path
 __device__ __forceinline__ void atomic_add(float *p, float v) { atomicAdd(p, v); }

@@ -22,7 +22,81 @@ namespace dcnv3 {
 constexpr int kThreads = 256;
 constexpr int kMaxSoftmaxP = 49;  // runtime-sized fused softmax keeps P values in registers/local
 
-// Decode a flat vector index into (pixel, vector-in-pixel, group, n, ho, wo).
+// ---------------------------------------------------------------------------
+// lane chunks: BPL bytes of channels per lane (16 -> LDG.128, 32 -> LDG.256)
+// ---------------------------------------------------------------------------
+template <int BPL> struct Words { unsigned w[BPL / 4]; };
+
+// predicated read-only load: zeros when !pred (an invalid corner contributes exactly 0,
+// and its address is never dereferenced — same as the reference's `if (valid)` reads)
+template <int BPL> __device__ __forceinline__ Words<BPL> ldg_pred(const void *p, bool pred);
+template <> __device__ __forceinline__ Words<16> ldg_pred<16>(const void *p, bool pred) {
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    if (pred) r = __ldg(reinterpret_cast<const uint4 *>(p));
+    Words<16> o;
+    o.w[0] = r.x; o.w[1] = r.y; o.w[2] = r.z; o.w[3] = r.w;
+    return o;
+}
+template <> __device__ __forceinline__ Words<32> ldg_pred<32>(const void *p, bool pred) {
+    Words<32> o;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %9, 0;\n\t"
+        "mov.b32 %0, 0; mov.b32 %1, 0; mov.b32 %2, 0; mov.b32 %3, 0;\n\t"
+        "mov.b32 %4, 0; mov.b32 %5, 0; mov.b32 %6, 0; mov.b32 %7, 0;\n\t"
+        "@q ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t}"
+        : "=r"(o.w[0]), "=r"(o.w[1]), "=r"(o.w[2]), "=r"(o.w[3]), "=r"(o.w[4]), "=r"(o.w[5]),
+          "=r"(o.w[6]), "=r"(o.w[7])
+        : "l"(p), "r"((int)pred));
+    return o;
+}
+
+template <typename T, int BPL> struct Lane {
+    static constexpr int CH = BPL / (int)sizeof(T);  // channels per lane
+    static constexpr int NP = CH / 2;                // float2 pairs per lane
+};
+
+// storage words -> op-math float2 pairs (channel 2k, 2k+1)
+template <int BPL>
+__device__ __forceinline__ void to_pairs(const Words<BPL> &r, float2 (&v)[BPL / 8], const float *) {
+#pragma unroll
+    for (int k = 0; k < BPL / 8; ++k)
+        v[k] = make_float2(__uint_as_float(r.w[2 * k]), __uint_as_float(r.w[2 * k + 1]));
+}
+template <int BPL>
+__device__ __forceinline__ void to_pairs(const Words<BPL> &r, float2 (&v)[BPL / 4], const __half *) {
+#pragma unroll
+    for (int k = 0; k < BPL / 4; ++k) v[k] = __half22float2(*reinterpret_cast<const __half2 *>(&r.w[k]));
+}
+template <int BPL>
+__device__ __forceinline__ void to_pairs(const Words<BPL> &r, float2 (&v)[BPL / 4], const __nv_bfloat16 *) {
+#pragma unroll
+    for (int k = 0; k < BPL / 4; ++k)  // bf16 -> f32 is a 16-bit shift / mask
+        v[k] = make_float2(__uint_as_float(r.w[k] << 16), __uint_as_float(r.w[k] & 0xffff0000u));
+}
+
+// op-math pairs -> storage words (round to nearest even)
+template <int BPL>
+__device__ __forceinline__ void from_pairs(const float2 (&v)[BPL / 8], Words<BPL> &r, const float *) {
+#pragma unroll
+    for (int k = 0; k < BPL / 8; ++k) { r.w[2 * k] = __float_as_uint(v[k].x); r.w[2 * k + 1] = __float_as_uint(v[k].y); }
+}
+template <int BPL>
+__device__ __forceinline__ void from_pairs(const float2 (&v)[BPL / 4], Words<BPL> &r, const __half *) {
+#pragma unroll
+    for (int k = 0; k < BPL / 4; ++k) { const __half2 h = __float22half2_rn(v[k]); r.w[k] = *reinterpret_cast<const unsigned *>(&h); }
+}
+template <int BPL>
+__device__ __forceinline__ void from_pairs(const float2 (&v)[BPL / 4], Words<BPL> &r, const __nv_bfloat16 *) {
+#pragma unroll
+    for (int k = 0; k < BPL / 4; ++k) { const __nv_bfloat162 h = __float22bfloat162_rn(v[k]); r.w[k] = *reinterpret_cast<const unsigned *>(&h); }
+}
+
+template <int BPL> __device__ __forceinline__ void st_words(void *p, const Words<BPL> &r) {
+#pragma unroll
+    for (int k = 0; k < BPL / 16; ++k)
+        reinterpret_cast<uint4 *>(p)[k] = make_uint4(r.w[4 * k], r.w[4 * k + 1], r.w[4 * k + 2], r.w[4 * k + 3]);
+}
+
+// Decode a flat lane index into (pixel, lane-in-pixel, group, n, ho, wo).
 struct VecCoord {
     unsigned pix;
     int v, g, n, ho, wo;
@@ -54,21 +128,23 @@ __device__ __forceinline__ void softmax_stats(const T *pm, int P, float &mx, flo
 }
 
 // ===========================================================================
-// forward, vector path
+// forward, vector path: one lane owns BPL bytes of channels of one (n, ho, wo, g)
 // ===========================================================================
-template <typename T, int KP, bool LOGITS>
+template <typename T, int BPL, int KP, bool LOGITS>
 __global__ void __launch_bounds__(kThreads)
 fwd_vec_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
                T *__restrict__ out, const Geo q, const int vec_per_pix,
                const int lanes_per_group, const unsigned total) {
-    constexpr int VEC = Vec<T>::N;
+    constexpr int CH = Lane<T, BPL>::CH, NP = Lane<T, BPL>::NP;
     const unsigned idx = blockIdx.x * (unsigned)kThreads + threadIdx.x;
     if (idx >= total) return;
     const VecCoord c = decode_vec(idx, q, vec_per_pix, lanes_per_group);
 
     float p0h_, p0w_;
     window_origin<float>(q, c.ho, c.wo, p0h_, p0w_);
-    const T *im = in + (size_t)c.n * q.H * q.W * q.C + c.v * VEC;
+    const char *im = reinterpret_cast<const char *>(in + (size_t)c.n * q.H * q.W * q.C + c.v * CH);
+    const int sC = q.C * (int)sizeof(T);  // byte strides of one pixel / one row
+    const int sW = q.W * sC;
     const size_t pg = (size_t)c.pix * q.G + c.g;
     const T *po = off + pg * q.P * 2;
     const T *pm = mask + pg * q.P;
@@ -76,9 +152,9 @@ fwd_vec_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     float mx = 0.f, inv = 1.f;
     if (LOGITS) softmax_stats<T, KP>(pm, q.P, mx, inv);
 
-    float acc[VEC];
+    float2 acc[NP];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+    for (int k = 0; k < NP; ++k) acc[k] = make_float2(0.f, 0.f);
 
     const int kw = KP ? 3 : q.kw, kh = KP ? 3 : q.kh;
     int p = 0;
@@ -91,41 +167,49 @@ fwd_vec_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
             locate<float>(q, p0h_, p0w_, i, j, o.x, o.y, t);
             float m = to_math(pm[p]);
             if (LOGITS) m = expf(m - mx) * inv;
-            if (t.bits) {
-                const float w1 = t.hh * t.hw * m, w2 = t.hh * t.lw * m;
-                const float w3 = t.lh * t.hw * m, w4 = t.lh * t.lw * m;
-                const T *r1 = im + (t.h_low * q.W + t.w_low) * q.C;
-                const T *r3 = r1 + q.W * q.C;
-                float v[VEC];
-                if (t.bits & B_C1) {
-                    unpack(ldg128(r1), v, (const T *)nullptr);
+            {
+                const float hm = t.hh * m, lm = t.lh * m;
+                const float w1 = hm * t.hw, w2 = hm * t.lw, w3 = lm * t.hw, w4 = lm * t.lw;
+                const char *r1 = im + (t.h_low * q.W + t.w_low) * sC;
+                const Words<BPL> c1 = ldg_pred<BPL>(r1, t.ok1);
+                const Words<BPL> c2 = ldg_pred<BPL>(r1 + sC, t.ok2);
+                const Words<BPL> c3 = ldg_pred<BPL>(r1 + sW, t.ok3);
+                const Words<BPL> c4 = ldg_pred<BPL>(r1 + sW + sC, t.ok4);
+                float2 v[NP];
+                to_pairs<BPL>(c1, v, (const T *)nullptr);
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) acc[k] = fmaf(w1, v[k], acc[k]);
-                }
-                if (t.bits & B_C2) {
-                    unpack(ldg128(r1 + q.C), v, (const T *)nullptr);
+                for (int k = 0; k < NP; ++k) acc[k] = __ffma2_rn(v[k], make_float2(w1, w1), acc[k]);
+                to_pairs<BPL>(c2, v, (const T *)nullptr);
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) acc[k] = fmaf(w2, v[k], acc[k]);
-                }
-                if (t.bits & B_C3) {
-                    unpack(ldg128(r3), v, (const T *)nullptr);
+                for (int k = 0; k < NP; ++k) acc[k] = __ffma2_rn(v[k], make_float2(w2, w2), acc[k]);
+                to_pairs<BPL>(c3, v, (const T *)nullptr);
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) acc[k] = fmaf(w3, v[k], acc[k]);
-                }
-                if (t.bits & B_C4) {
-                    unpack(ldg128(r3 + q.C), v, (const T *)nullptr);
+                for (int k = 0; k < NP; ++k) acc[k] = __ffma2_rn(v[k], make_float2(w3, w3), acc[k]);
+                to_pairs<BPL>(c4, v, (const T *)nullptr);
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) acc[k] = fmaf(w4, v[k], acc[k]);
-                }
+                for (int k = 0; k < NP; ++k) acc[k] = __ffma2_rn(v[k], make_float2(w4, w4), acc[k]);
             }
         }
     }
-    *reinterpret_cast<uint4 *>(out + (size_t)c.pix * q.C + c.v * VEC) = pack(acc, (const T *)nullptr);
+    Words<BPL> r;
+    from_pairs<BPL>(acc, r, (const T *)nullptr);
+    st_words<BPL>(out + (size_t)c.pix * q.C + c.v * CH, r);
 }
 
 // ===========================================================================
-// backward, vector path.  A = accumulation type of grad_input (float: gin itself
-// for f32 storage or the fp32 workspace for 16-bit storage; T: packed 16-bit reds).
+// backward, vector path.  A = accumulation type of grad_input (float: gin itself for f32
+// storage or the fp32 workspace for 16-bit storage; T: packed 16-bit reductions).
+//
+// Per sampling point only the four corner dot products d_k = sum_c go[c] * v_k[c] are needed:
+//   grad_mask          = w1 d1 + w2 d2 + w3 d3 + w4 d4                      (cuh:144)
+//   sum_c go*grad_w_w  = hh (d2 - d1) + lh (d4 - d3)                        (cuh:114-139,145)
+//   sum_c go*grad_h_w  = hw (d3 - d1) + lw (d4 - d2)                        (cuh:114-139,146)
+// and the lanes of a group reduce the three sums with __shfl_xor.
+//
+// grad_input reductions are issued so that the L lanes of a group cover one contiguous
+// L*16-byte range per instruction (whole 32-byte sectors): instruction j of lane l carries
+// 16-byte chunk j*L + l of the group's slab, with the matching grad_output values re-read
+// from global memory once per thread (L1 hits).
 // ===========================================================================
 template <typename T> __device__ __forceinline__ void store_pair(T *p, float x, float y);
 template <> __device__ __forceinline__ void store_pair<float>(float *p, float x, float y) {
@@ -138,33 +222,108 @@ template <> __device__ __forceinline__ void store_pair<__nv_bfloat16>(__nv_bfloa
     *reinterpret_cast<__nv_bfloat162 *>(p) = __floats2bfloat162_rn(x, y);
 }
 
-template <typename T, typename A, int KP, bool LOGITS>
+// one 16-byte reduction chunk: CPQ channels of accumulation type A
+template <typename A> struct RedChunk;
+template <> struct RedChunk<float> {
+    static constexpr int CPQ = 4;
+    __device__ static __forceinline__ void run(char *dst, const float (&g)[4], float w, bool pred) {
+        const float2 a = __fmul2_rn(make_float2(g[0], g[1]), make_float2(w, w));
+        const float2 b = __fmul2_rn(make_float2(g[2], g[3]), make_float2(w, w));
+        red_add_v4_f32(reinterpret_cast<float *>(dst), a.x, a.y, b.x, b.y, pred);
+    }
+};
+template <> struct RedChunk<__half> {
+    static constexpr int CPQ = 8;
+    __device__ static __forceinline__ void run(char *dst, const float (&g)[8], float w, bool pred) {
+        float t[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[k] = w * g[k];
+        const uint4 v = pack(t, (const __half *)nullptr);
+        red_add_v4_f16x2(reinterpret_cast<__half *>(dst), v, pred);
+    }
+};
+template <> struct RedChunk<__nv_bfloat16> {
+    static constexpr int CPQ = 8;
+    __device__ static __forceinline__ void run(char *dst, const float (&g)[8], float w, bool pred) {
+        float t[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t[k] = w * g[k];
+        const uint4 v = pack(t, (const __nv_bfloat16 *)nullptr);
+        red_add_v4_bf16x2(reinterpret_cast<__nv_bfloat16 *>(dst), v, pred);
+    }
+};
+
+// CPQ consecutive channels of grad_output as op-math floats
+template <typename T, int CPQ>
+__device__ __forceinline__ void load_go_chunk(const T *p, float (&g)[CPQ]) {
+    if constexpr (sizeof(T) == 4) {
+        static_assert(CPQ == 4, "");
+        const float4 r = __ldg(reinterpret_cast<const float4 *>(p));
+        g[0] = r.x; g[1] = r.y; g[2] = r.z; g[3] = r.w;
+    } else if constexpr (CPQ == 4) {
+        const uint2 r = __ldg(reinterpret_cast<const uint2 *>(p));
+        Words<8> w; w.w[0] = r.x; w.w[1] = r.y;
+        float2 v[2];
+        to_pairs<8>(w, v, (const T *)nullptr);
+        g[0] = v[0].x; g[1] = v[0].y; g[2] = v[1].x; g[3] = v[1].y;
+    } else {
+        static_assert(CPQ == 8, "");
+        const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+        Words<16> w; w.w[0] = r.x; w.w[1] = r.y; w.w[2] = r.z; w.w[3] = r.w;
+        float2 v[4];
+        to_pairs<16>(w, v, (const T *)nullptr);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { g[2 * k] = v[k].x; g[2 * k + 1] = v[k].y; }
+    }
+}
+
+template <typename T, typename A, int BPL, int KP, bool LOGITS>
 __global__ void __launch_bounds__(kThreads)
 bwd_vec_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
                const T *__restrict__ gout, A *__restrict__ gin, T *__restrict__ goff,
                T *__restrict__ gmask, const Geo q, const int vec_per_pix,
                const int lanes_per_group, const unsigned total) {
     static_assert(!LOGITS || KP > 0, "fused softmax in the vector path needs a compile-time P");
-    constexpr int VEC = Vec<T>::N;
+    constexpr int CH = Lane<T, BPL>::CH, NP = Lane<T, BPL>::NP;
+    constexpr int CPQ = RedChunk<A>::CPQ;                 // channels per 16-byte reduction
+    constexpr int R = CH * (int)sizeof(A) / 16;           // reductions per corner per lane
     unsigned idx = blockIdx.x * (unsigned)kThreads + threadIdx.x;
     const bool active = idx < total;  // tail lanes stay for the shuffles
     if (!active) idx = total - 1;
     const VecCoord c = decode_vec(idx, q, vec_per_pix, lanes_per_group);
+    const int lane_in_group = c.v - c.g * lanes_per_group;
 
     float p0h_, p0w_;
     window_origin<float>(q, c.ho, c.wo, p0h_, p0w_);
-    const size_t img = (size_t)c.n * q.H * q.W * q.C + c.v * VEC;
-    const T *im = in + img;
-    A *gim = gin + img;
+    const size_t img = (size_t)c.n * q.H * q.W * q.C;
+    const char *im = reinterpret_cast<const char *>(in + img + c.v * CH);
+    char *gim = reinterpret_cast<char *>(gin + img + c.g * q.gc);  // group slab start, A units
+    const int sC = q.C * (int)sizeof(T), sW = q.W * sC;
+    constexpr int ARATIO = (int)sizeof(A) / (int)sizeof(T) > 0 ? (int)sizeof(A) / (int)sizeof(T) : 1;
+    static_assert(sizeof(A) >= sizeof(T), "");
     const size_t pg = (size_t)c.pix * q.G + c.g;
     const T *po = off + pg * q.P * 2;
     const T *pm = mask + pg * q.P;
     T *d_o = goff + pg * q.P * 2;
     T *d_m = gmask + pg * q.P;
-    const bool writer = active && (c.v % lanes_per_group) == 0;
+    const bool writer = active && lane_in_group == 0;
 
-    float go[VEC];
-    unpack(ldg128(gout + (size_t)c.pix * q.C + c.v * VEC), go, (const T *)nullptr);
+    // grad_output: this lane's channels (for the dots) ...
+    const T *gop = gout + (size_t)c.pix * q.C;
+    float2 gp[NP];
+    {
+        const Words<BPL> gw = ldg_pred<BPL>(gop + c.v * CH, true);
+        to_pairs<BPL>(gw, gp, (const T *)nullptr);
+    }
+    // ... and the channels of the reduction chunks this lane issues (chunk j*L + l)
+    float gr[R][CPQ];
+    int red_off[R];  // byte offset of the chunk inside the group's slab (A units)
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const int chunk = j * lanes_per_group + lane_in_group;
+        load_go_chunk<T, CPQ>(gop + c.g * q.gc + chunk * CPQ, gr[j]);
+        red_off[j] = chunk * 16;
+    }
 
     float mx = 0.f, inv = 1.f;
     if (LOGITS) softmax_stats<T, KP>(pm, q.P, mx, inv);
@@ -182,41 +341,50 @@ bwd_vec_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
             float m = to_math(pm[p]);
             if (LOGITS) m = expf(m - mx) * inv;
 
-            float s_m = 0.f, s_w = 0.f, s_h = 0.f;
-            if (t.bits) {
-                const int base = (t.h_low * q.W + t.w_low) * q.C;
-                const int row = q.W * q.C;
-                float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) v1[k] = v2[k] = v3[k] = v4[k] = 0.f;
-                if (t.bits & B_C1) unpack(ldg128(im + base), v1, (const T *)nullptr);
-                if (t.bits & B_C2) unpack(ldg128(im + base + q.C), v2, (const T *)nullptr);
-                if (t.bits & B_C3) unpack(ldg128(im + base + row), v3, (const T *)nullptr);
-                if (t.bits & B_C4) unpack(ldg128(im + base + row + q.C), v4, (const T *)nullptr);
-                const float w1 = t.hh * t.hw, w2 = t.hh * t.lw, w3 = t.lh * t.hw, w4 = t.lh * t.lw;
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) {
-                    // cuh:114-139: grad_w_weight = hh*(v2-v1) + lh*(v4-v3),
-                    //              grad_h_weight = hw*(v3-v1) + lw*(v4-v2)
-                    const float val = w1 * v1[k] + w2 * v2[k] + w3 * v3[k] + w4 * v4[k];
-                    const float gw = t.hh * (v2[k] - v1[k]) + t.lh * (v4[k] - v3[k]);
-                    const float gh = t.hw * (v3[k] - v1[k]) + t.lw * (v4[k] - v2[k]);
-                    s_m = fmaf(go[k], val, s_m);
-                    s_w = fmaf(go[k], gw, s_w);
-                    s_h = fmaf(go[k], gh, s_h);
+            float s_m, s_w, s_h;
+            {
+                const int e0 = (t.h_low * q.W + t.w_low) * sC;  // byte offset of corner 1 (T units)
+                const char *r1 = im + e0;
+                const Words<BPL> c1 = ldg_pred<BPL>(r1, t.ok1);
+                const Words<BPL> c2 = ldg_pred<BPL>(r1 + sC, t.ok2);
+                const Words<BPL> c3 = ldg_pred<BPL>(r1 + sW, t.ok3);
+                const Words<BPL> c4 = ldg_pred<BPL>(r1 + sW + sC, t.ok4);
+                float d[4];
+                {
+                    float2 v[NP];
+                    float2 a;
+#define DCNV3_DOT(CW, K)                                                          \
+    to_pairs<BPL>(CW, v, (const T *)nullptr);                                     \
+    a = make_float2(0.f, 0.f);                                                    \
+    _Pragma("unroll") for (int k = 0; k < NP; ++k) a = __ffma2_rn(gp[k], v[k], a); \
+    d[K] = a.x + a.y;
+                    DCNV3_DOT(c1, 0)
+                    DCNV3_DOT(c2, 1)
+                    DCNV3_DOT(c3, 2)
+                    DCNV3_DOT(c4, 3)
+#undef DCNV3_DOT
                 }
-                if (active) {  // cuh:116,124,132,140: grad_im[corner] += w_k * top_grad * mask
-                    if (t.bits & B_C1) RedAdd<VEC>::run(gim + base, go, w1 * m);
-                    if (t.bits & B_C2) RedAdd<VEC>::run(gim + base + q.C, go, w2 * m);
-                    if (t.bits & B_C3) RedAdd<VEC>::run(gim + base + row, go, w3 * m);
-                    if (t.bits & B_C4) RedAdd<VEC>::run(gim + base + row + q.C, go, w4 * m);
+                const float w1 = t.hh * t.hw, w2 = t.hh * t.lw, w3 = t.lh * t.hw, w4 = t.lh * t.lw;
+                s_m = w1 * d[0] + w2 * d[1] + w3 * d[2] + w4 * d[3];
+                s_w = t.hh * (d[1] - d[0]) + t.lh * (d[3] - d[2]);
+                s_h = t.hw * (d[2] - d[0]) + t.lw * (d[3] - d[1]);
+                {  // cuh:116,124,132,140: grad_im[corner] += w_k * top_grad * mask
+                    char *g1 = gim + (size_t)e0 * ARATIO;
+                    const int aC = sC * ARATIO, aW = sW * ARATIO;
+#pragma unroll
+                    for (int jj = 0; jj < R; ++jj) {
+                        RedChunk<A>::run(g1 + red_off[jj], gr[jj], w1 * m, active && t.ok1);
+                        RedChunk<A>::run(g1 + aC + red_off[jj], gr[jj], w2 * m, active && t.ok2);
+                        RedChunk<A>::run(g1 + aW + red_off[jj], gr[jj], w3 * m, active && t.ok3);
+                        RedChunk<A>::run(g1 + aW + aC + red_off[jj], gr[jj], w4 * m, active && t.ok4);
+                    }
                 }
             }
-            // sum over the channels of the group: lanes of one group are an aligned segment
-            for (int d = lanes_per_group >> 1; d > 0; d >>= 1) {
-                s_m += shfl_xor(s_m, d);
-                s_w += shfl_xor(s_w, d);
-                s_h += shfl_xor(s_h, d);
+            // sum over the channels of the group: its lanes are an aligned warp segment
+            for (int dlt = lanes_per_group >> 1; dlt > 0; dlt >>= 1) {
+                s_m += shfl_xor(s_m, dlt);
+                s_w += shfl_xor(s_w, dlt);
+                s_h += shfl_xor(s_h, dlt);
             }
             const float sm = q.scale * m;  // cuh:145-146
             if (writer) store_pair<T>(d_o + 2 * p, sm * s_w, sm * s_h);
@@ -292,15 +460,15 @@ fwd_any_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         for (int j = 0; j < q.kh; ++j, ++p) {
             Point<M> t;
             locate<M>(q, p0h_, p0w_, i, j, (M)to_math(po[2 * p]), (M)to_math(po[2 * p + 1]), t);
-            if (!t.bits) continue;
+            if (!t.inside) continue;
             M m = to_math(pm[p]);
             if (LOGITS) m = exp(m - mx) * inv;
             const size_t base = ((size_t)t.h_low * q.W + t.w_low) * q.C;
             const size_t rw = (size_t)q.W * q.C;
-            const M v1 = (t.bits & B_C1) ? (M)to_math(im[base]) : (M)0;
-            const M v2 = (t.bits & B_C2) ? (M)to_math(im[base + q.C]) : (M)0;
-            const M v3 = (t.bits & B_C3) ? (M)to_math(im[base + rw]) : (M)0;
-            const M v4 = (t.bits & B_C4) ? (M)to_math(im[base + rw + q.C]) : (M)0;
+            const M v1 = t.ok1 ? (M)to_math(im[base]) : (M)0;
+            const M v2 = t.ok2 ? (M)to_math(im[base + q.C]) : (M)0;
+            const M v3 = t.ok3 ? (M)to_math(im[base + rw]) : (M)0;
+            const M v4 = t.ok4 ? (M)to_math(im[base + rw + q.C]) : (M)0;
             acc += (t.hh * t.hw * v1 + t.hh * t.lw * v2 + t.lh * t.hw * v3 + t.lh * t.lw * v4) * m;
         }
     out[idx] = from_math<T>(acc);
@@ -351,7 +519,7 @@ bwd_any_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
             M m = to_math(pm[p]);
             if (LOGITS) m = exp(m - mx) * inv;
             M s_m = 0, s_w = 0, s_h = 0;
-            if (t.bits) {  // warp-uniform: every lane sees the same point
+            if (t.inside) {  // warp-uniform: every lane sees the same point
                 const size_t base = ((size_t)t.h_low * q.W + t.w_low) * q.C;
                 const size_t rw = (size_t)q.W * q.C;
                 const M w1 = t.hh * t.hw, w2 = t.hh * t.lw, w3 = t.lh * t.hw, w4 = t.lh * t.lw;
@@ -359,10 +527,10 @@ bwd_any_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                     const M top = to_math(go[ch]);
                     const M tg = top * m;
                     M v1 = 0, v2 = 0, v3 = 0, v4 = 0;
-                    if (t.bits & B_C1) { v1 = to_math(im[base + ch]); atomic_add(gim + base + ch, w1 * tg); }
-                    if (t.bits & B_C2) { v2 = to_math(im[base + q.C + ch]); atomic_add(gim + base + q.C + ch, w2 * tg); }
-                    if (t.bits & B_C3) { v3 = to_math(im[base + rw + ch]); atomic_add(gim + base + rw + ch, w3 * tg); }
-                    if (t.bits & B_C4) { v4 = to_math(im[base + rw + q.C + ch]); atomic_add(gim + base + rw + q.C + ch, w4 * tg); }
+                    if (t.ok1) { v1 = to_math(im[base + ch]); atomic_add(gim + base + ch, w1 * tg); }
+                    if (t.ok2) { v2 = to_math(im[base + q.C + ch]); atomic_add(gim + base + q.C + ch, w2 * tg); }
+                    if (t.ok3) { v3 = to_math(im[base + rw + ch]); atomic_add(gim + base + rw + ch, w3 * tg); }
+                    if (t.ok4) { v4 = to_math(im[base + rw + q.C + ch]); atomic_add(gim + base + rw + q.C + ch, w4 * tg); }
                     const M val = w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
                     s_m += top * val;
                     s_w += top * (t.hh * (v2 - v1) + t.lh * (v4 - v3));
@@ -412,7 +580,7 @@ indices_kernel(const T *__restrict__ off, int32_t *__restrict__ hw_low,
     locate<M>(q, p0h_, p0w_, i, j, (M)to_math(off[2 * idx]), (M)to_math(off[2 * idx + 1]), t);
     hw_low[2 * idx] = t.h_low;
     hw_low[2 * idx + 1] = t.w_low;
-    bounds[idx] = (uint8_t)t.bits;
+    bounds[idx] = (uint8_t)t.bits();
 }
 
 }  // namespace dcnv3
