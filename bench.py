@@ -57,6 +57,18 @@ def algo_bytes(site, e, N=None):
     return fwd, bwd
 
 
+def ncu_traffic(op):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the op's main kernel, per launch, from the
+    committed ncu capture (profiles/r01_ncu_traffic.json); None when that op was not captured."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f).get(op)
+        return None if t is None else t["dram_bytes_read"] + t["dram_bytes_write"]
+    except OSError:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -281,6 +293,100 @@ def time_e2e(wl, steps, warmup, dist):
 
 
 # ----------------------------------------------------------------------------------------------
+# The caller of the hot path: C3-DCN seg training step (BASELINE configs[1]/[3]) — imgs/s.
+# YOLOv5-style seg model with C3_DCNV3 in the three C3_DCN slots, 640x640, batch 16 per GPU,
+# bf16 autocast, CE + 0.5 Dice, SGD-nesterov; DDP (NCCL) gradient all-reduce when world > 1.
+# Every step copies its images/labels from pinned host memory and reads the loss back.
+# ----------------------------------------------------------------------------------------------
+def time_seg(dev, dist, world, steps, warmup, batch, model_name):
+    from yolo_dual_b200 import seg
+    torch.manual_seed(0)
+    cfg = {"yolov5seg": seg.YOLOV5_SEG, "yolov8seg": seg.YOLOV8_SEG}[model_name]
+    model = seg.SegModel(cfg, dcn="dcnv3").to(dev)
+    crit = seg.SegmentationLoss(12, class_weights=seg.CAMVID_CLASS_WEIGHTS).to(dev)
+    ddp = seg.wrap_ddp(model, dev)
+    opt = seg.smart_optimizer(ddp)
+    ddp.train()
+    g = torch.Generator().manual_seed(1 + (dist.get_rank() if dist is not None else 0))
+    imgs_h = torch.randn(batch, 3, 640, 640, generator=g).pin_memory()
+    lab_h = torch.randint(0, 12, (batch, 640, 640), generator=g).pin_memory()
+
+    def one():
+        imgs = imgs_h.to(dev, non_blocking=True)
+        lab = lab_h.to(dev, non_blocking=True)
+        loss, _ = seg.train_step(ddp, crit, opt, imgs, lab, autocast_dtype=torch.bfloat16)
+        return float(loss)  # D2H: the step's result
+
+    for _ in range(warmup):
+        last = one()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        last = one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        dist.barrier()
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    n_params = sum(p.numel() for p in model.parameters())
+    return {"model": f"{model_name} with C3_DCNV3 at P3/P4/P5 (DCNv3 C=128/256/512, group_channels 16)",
+            "imgs_per_s": batch * world * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps,
+            "batch_per_gpu": batch, "global_batch": batch * world, "image": "640x640", "autocast": "bf16",
+            "optimizer": "SGD nesterov 3 groups", "params": n_params, "loss_last": last,
+            "h2d_bytes_per_step": imgs_h.numel() * 4 + lab_h.numel() * 8, "d2h_bytes_per_step": 4,
+            "data_parallel": f"DDP x{world} (NCCL all-reduce of {n_params * 4 / 1e6:.1f} MB fp32 grads)" if world > 1 else "single GPU"}
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU baseline: the reference's OWN CUDA kernels rebuilt for sm_100a (oracle/_ref, test
+# infrastructure, built by oracle/build_ref_cuda.py where /root/reference is mounted).  They have no
+# bf16 path (dcnv3_cuda.cu:69,147), so the comparison runs in fp16 on both sides.
+# ----------------------------------------------------------------------------------------------
+def time_reference_cuda(dev, sites, steps, warmup):
+    from oracle.build_ref_cuda import load_module
+    ref = load_module()
+    if ref is None:
+        return None
+    dt = torch.float16
+    sets = []
+    for r in range(N_BUFFER_SETS):
+        sets.append([SiteBuffers(s, dt, dev, 1000 * r + i, False) for i, s in enumerate(sites)])
+
+    def step(k):
+        bufs = sets[k % N_BUFFER_SETS]
+        for b in bufs:
+            N, H, W, G, gc = SITES[b.name]
+            ref.dcnv3_forward(b.input, b.offset, b.mask, 3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0, 256)
+        for b in reversed(bufs):
+            N, H, W, G, gc = SITES[b.name]
+            ref.dcnv3_backward(b.input, b.offset, b.mask, 3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0, b.grad_out, 256)
+
+    for k in range(warmup):
+        step(k)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(steps):
+        step(warmup + k)
+    e1.record()
+    torch.cuda.synchronize()
+    ref_ms = e0.elapsed_time(e1) / steps
+    del sets
+    wl = Workload(dev, dt, sites, "opmath", False)
+    ours_ms = time_steps(wl, steps, warmup, None) / steps
+    return {"what": "the reference's own CUDA kernels (dcnv3_im2col_cuda.cuh) rebuilt for sm_100a, same step, "
+                    "fp16 (the reference has no bf16), outputs allocated inside as it does",
+            "dtype": "fp16", "steps": steps, "reference_ms_per_step": ref_ms, "ours_fp16_ms_per_step": ours_ms,
+            "speedup": ref_ms / ours_ms}
+
+
+# ----------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the reference's own CPU algorithm for this path is the pure-PyTorch
 # dcnv3_core_pytorch; /root/reference is not on the GPU box, so its restatement in oracle/ is timed
 # (kind "port").  This is the only place bench.py executes oracle/.
@@ -333,6 +439,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--no-seg", action="store_true")
+    ap.add_argument("--seg-steps", type=int, default=10)
+    ap.add_argument("--seg-batch", type=int, default=16)
+    ap.add_argument("--seg-model", default="yolov5seg", choices=["yolov5seg", "yolov8seg"])
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3
@@ -379,6 +490,7 @@ def main():
     clocks = Clocks(local) if rank == 0 else None
 
     wl = Workload(dev, dtype, sites, a.grad_accum, a.fused_softmax)
+    launches = wl.launches_per_step * a.steps
     ms = time_steps(wl, a.steps, a.warmup, dist)
     ops = time_ops(wl, min(a.steps, 100), a.warmup)
     e2e = None
@@ -388,6 +500,23 @@ def main():
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.e2e_steps,
                "steps": a.e2e_steps,
                "api": "DCNv3Function.apply + autograd backward on pinned host tensors (H2D in, D2H out every step)"}
+    seg_res = None
+    if not a.no_seg:
+        del wl
+        torch.cuda.empty_cache()
+        try:
+            seg_res = time_seg(dev, dist, world, a.seg_steps, 3, a.seg_batch, a.seg_model)
+        except Exception as ex:
+            if world > 1:
+                raise  # a rank must not leave a collective half-done
+            seg_res = {"error": repr(ex)[:300]}
+        wl = None
+    ref_cuda = None
+    if rank == 0 and not a.no_ref_cuda:
+        try:
+            ref_cuda = time_reference_cuda(dev, sites, 20, 3)
+        except Exception as ex:  # the baseline must never take the bench down
+            ref_cuda = {"error": repr(ex)[:300]}
     clk = clocks.stop() if clocks else None
     if rank != 0:
         if dist is not None:
@@ -407,13 +536,13 @@ def main():
     dom = max(table, key=lambda k: table[k]["us_mean"])
     roofline = {"bound": "hbm", "kernel": dom + (" (memset + bwd_vec_kernel + cast_ws_kernel)" if dom.startswith("bwd") and e == 2 and a.grad_accum == "opmath" else ""),
                 "achieved": table[dom]["GBps"], "peak": peak, "unit": "GB/s", "frac": table[dom]["GBps"] / peak,
-                "peak_source": peak_src, "traffic": None,
+                "peak_source": peak_src, "traffic": ncu_traffic(dom),
                 "step_frac": value / world / peak}
     out = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": a.steps,
            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": a.dtype if a.dtype != "fp32" else "f32", "data": "synthetic",
            "config": config, "pct_hbm_peak": 100.0 * value / world / peak, "roofline": roofline,
-           "ops": table, "e2e": e2e, "gpu_launches": wl.launches_per_step * a.steps, "clocks": clk}
+           "ops": table, "seg_train": seg_res, "reference_cuda": ref_cuda, "e2e": e2e, "gpu_launches": launches, "clocks": clk}
     if not a.no_cpu_baseline:
         gbps, cms, cores, sample, _ = cpu_run(sites, e, 3, 1, budget_s=30.0)
         out["cpu_baseline"] = {"value": gbps, "unit": "GB/s", "cores": cores, "kind": "port",

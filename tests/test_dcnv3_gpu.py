@@ -130,6 +130,66 @@ def test_vs_pixel_oracle(shape, dtype, dist, fn, pixel_oracle):
     assert_close_scaled(go_, want_go, what="grad_offset", **tol)
 
 
+@pytest.mark.parametrize("env", [{"DCNV3_B200_BPL": "32"}, {"DCNV3_B200_BWD": "tile"},
+                                 {"DCNV3_B200_BWD": "tile", "DCNV3_B200_TILE": "8,8,2,4"},
+                                 {"DCNV3_B200_BWD": "tile", "DCNV3_B200_TILE": "2,4,0,1"}],
+                         ids=["bpl32", "tile", "tile882", "tile_tiny_halo0"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16], ids=["f32", "f16", "bf16"])
+@pytest.mark.parametrize("shape", ["cfg1", "D16", "stride2", "G32gc8", "k5dil2_gc16"])
+def test_alternative_kernel_families(shape, dtype, env, fn, pixel_oracle, monkeypatch):
+    """The 32-byte-per-lane mapping and the experimental privatised (tile) backward are selected by
+    environment knobs read on every call; both must meet the same bar as the default kernels.
+    'tile_tiny_halo0' forces most corners through the outside-the-window fallback and the
+    conflict-serialisation path."""
+    from oracle.dcnv3_oracle import make_inputs
+    for k_, v_ in env.items():
+        monkeypatch.setenv(k_, v_)
+    shapes = dict(SHAPES, k5dil2_gc16=_case(1, 20, 18, 2, 16, k=5, pad=4, dil=2))
+    (N, H, W, G, gc), args = shapes[shape]
+    kh, kw, sh, sw, ph, pw, dh, dw = args[:8]
+    x, off, m, go = make_inputs(N, H, W, G, gc, kh, kw, sh, sw, ph, pw, dh, dw, dist="unit", seed=17)
+    xr, offr, mr, gor = (t.to(dtype).float() for t in (x, off, m, go))
+    want_out = pixel_oracle.forward(xr, offr, mr, *args)
+    want = pixel_oracle.backward(xr, offr, mr, gor, *args)
+    out, gi, go_, gm = run_cuda(fn, x, off, m, go, args, dtype=dtype)
+    tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=1e-2, atol=2e-3)
+    assert_close_scaled(out, want_out, what="output", **tol)
+    for got, w_, name in zip((gi, go_, gm), want, ("grad_input", "grad_offset", "grad_mask")):
+        assert_close_scaled(got, w_, what=name, **tol)
+
+
+# ------------------------------------------------------------------------------------------
+# 2b. CUDA vs the reference's own CUDA kernels rebuilt for sm_100a (oracle/_ref, second oracle)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16], ids=["f32", "f16"])
+@pytest.mark.parametrize("shape", ["cfg1", "D16", "D30", "D71", "stride2", "k5dil2", "pad0"])
+def test_vs_reference_cuda_kernels(shape, dtype, fn):
+    """Same inputs through the reference's dcnv3_cuda_forward/backward (dcnv3_cuda.cu:21-173) and
+    through ours.  Skipped when oracle/_ref was never built (it needs /root/reference at build time)."""
+    from oracle.build_ref_cuda import load_module
+    from oracle.dcnv3_oracle import make_inputs
+    ref = load_module()
+    if ref is None:
+        pytest.skip("oracle/_ref/dcnv3_ref_cuda.so not built")
+    (N, H, W, G, gc), args = SHAPES[shape]
+    kh, kw, sh, sw, ph, pw, dh, dw = args[:8]
+    x, off, m, go = make_inputs(N, H, W, G, gc, kh, kw, sh, sw, ph, pw, dh, dw, dist="unit", seed=23)
+    xs, os_, ms, gs = (t.to(DEV, dtype).contiguous() for t in (x, off, m, go))
+    want_out = ref.dcnv3_forward(xs, os_, ms, *args, 256)
+    want = ref.dcnv3_backward(xs, os_, ms, *args, gs, 256)
+    out, gi, go_, gm = run_cuda(fn, x, off, m, go, args, dtype=dtype)
+    tol = dict(rtol=1e-5, atol=1e-4) if dtype == torch.float32 else dict(rtol=1e-2, atol=2e-3)
+    assert_close_scaled(out, want_out.cpu(), what="output", **tol)
+    assert_close_scaled(gi, want[0].cpu(), what="grad_input", **tol)
+    assert_close_scaled(gm, want[2].cpu(), what="grad_mask", **tol)
+    # the reference build contracts the location arithmetic into FMAs, ours does not (integer
+    # contract): floor() may differ on a cell border, where grad_offset is discontinuous
+    c = dict(G=G, kh=kh, kw=kw, sh=sh, sw=sw, ph=ph, pw=pw, dh=dh, dw=dw, offset_scale=args[10])
+    near, keep = near_cell_border(off.to(dtype).float(), c, 1e-4)
+    assert near.float().mean() < 0.01
+    assert_close_scaled(go_ * keep, want[1].cpu() * keep, what="grad_offset", **tol)
+
+
 # ------------------------------------------------------------------------------------------
 # 3. integer contract: bit-exact corner indices and bounds bytes
 # ------------------------------------------------------------------------------------------
@@ -422,3 +482,28 @@ def test_module_matches_oracle_composition(fused):
     want = [yc.detach(), xc.grad, ref.offset.weight.grad, ref.mask.weight.grad, ref.input_proj.weight.grad]
     for a, b, name in zip(got, want, ("y", "dx", "dW_offset", "dW_mask", "dW_in")):
         assert_close_scaled(a, b, rtol=1e-3, atol=1e-4, what=name)
+
+
+# ------------------------------------------------------------------------------------------
+# 10. the callers: C3_DCNV3 blocks inside the seg model, one training step on the GPU
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg_name", ["yolov5seg", "yolov8seg"])
+def test_seg_model_train_step(cfg_name):
+    from yolo_dual_b200 import seg
+    torch.manual_seed(0)
+    cfg = {"yolov5seg": seg.YOLOV5_SEG, "yolov8seg": seg.YOLOV8_SEG}[cfg_name]
+    model = seg.SegModel(cfg, dcn="dcnv3", img_size=(128, 128)).to(DEV).train()
+    crit = seg.SegmentationLoss(12, class_weights=seg.CAMVID_CLASS_WEIGHTS).to(DEV)
+    opt = seg.smart_optimizer(model, lr=0.01)
+    imgs = torch.randn(2, 3, 128, 128, device=DEV)
+    labels = torch.randint(0, 12, (2, 128, 128), device=DEV)
+    before = {n: p.detach().clone() for n, p in model.named_parameters() if "dcnv3.offset.bias" in n}
+    losses = []
+    for _ in range(3):
+        loss, _ = seg.train_step(model, crit, opt, imgs, labels, autocast_dtype=torch.bfloat16)
+        losses.append(float(loss))
+    assert all(torch.isfinite(torch.tensor(losses)))
+    assert losses[-1] < losses[0]  # same batch three times: the loss must go down
+    # gradients reached the DCNv3 offset heads through the CUDA backward (they start at zero)
+    moved = [float((p.detach() - before[n]).abs().max()) for n, p in model.named_parameters() if n in before]
+    assert len(moved) == 3 and all(v > 0 for v in moved)

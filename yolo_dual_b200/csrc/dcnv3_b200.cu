@@ -9,10 +9,12 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <initializer_list>
 
 #include "dcnv3_kernels.cuh"
+#include "dcnv3_bwd_tile.cuh"
 
 using namespace dcnv3;
 
@@ -114,15 +116,11 @@ struct Plan {
 
 bool aligned_to(const void *p, int a) { return (reinterpret_cast<uintptr_t>(p) & (uintptr_t)(a - 1)) == 0; }
 
-// Tuning knob (read once): DCNV3_B200_BPL=16|32 forces the bytes-per-lane of the vector path.
+// Tuning knob: DCNV3_B200_BPL=16|32 forces the bytes-per-lane of the vector path.
 int forced_bpl() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("DCNV3_B200_BPL");
-        v = e ? atoi(e) : 0;
-        if (v != 16 && v != 32) v = 0;
-    }
-    return v;
+    const char *e = getenv("DCNV3_B200_BPL");
+    const int v = e ? atoi(e) : 0;
+    return (v == 16 || v == 32) ? v : 0;
 }
 
 // Can this call take the vector kernels, and with how many bytes per lane?
@@ -197,6 +195,83 @@ int forward_t(const void *in_, const void *off_, const void *mask_, void *out_, 
     return 0;
 }
 
+// ------------------------------------------------ privatised backward (tile)
+// Knobs: DCNV3_B200_BWD=tile selects this family, DCNV3_B200_TILE="TH,TW,R,warps" its tile shape.
+struct TileKnobs { int force; int TH, TW, R, warps; };
+TileKnobs tile_knobs() {  // read per call (getenv is ~100 ns) so tests can switch paths in-process
+    TileKnobs t{0, 4, 8, 1, 4};
+    if (const char *e = getenv("DCNV3_B200_BWD")) t.force = !strcmp(e, "vec") ? 1 : (!strcmp(e, "tile") ? 2 : 0);
+    if (const char *e = getenv("DCNV3_B200_TILE")) {
+        int a, b, c, d;
+        if (sscanf(e, "%d,%d,%d,%d", &a, &b, &c, &d) == 4 && a >= 2 && b >= 2 && is_pow2(a) && is_pow2(b) &&
+            c >= 0 && d >= 1 && d <= 4) { t.TH = a; t.TW = b; t.R = c; t.warps = d; }
+    }
+    return t;
+}
+
+template <typename T>
+bool plan_tile(const Geo &q, bool logits, const void *in, const void *gout, const void *off,
+               const void *acc, TileCfg &tc) {
+    // Experimental (round 1): correct, but not faster than the vector kernel yet, so it
+    // only runs when asked for with DCNV3_B200_BWD=tile.
+    const TileKnobs kn = tile_knobs();
+    if (kn.force != 2) return false;
+    if (sizeof(T) > 4 || q.gc != kTileGC) return false;
+    if (!aligned_to(in, 8 * (int)sizeof(T)) || !aligned_to(gout, 8 * (int)sizeof(T)) || !aligned16(acc)) return false;
+    if (reinterpret_cast<uintptr_t>(off) & (2 * sizeof(T) - 1)) return false;
+    if ((unsigned long long)q.H * q.W * q.C * 4ull >= (1ull << 31)) return false;
+    const float s = fabsf(q.scale);
+    if (!(s < 64.f)) return false;
+    tc.TH = kn.TH; tc.TW = kn.TW; tc.R = kn.R;
+    tc.lth = 0; while ((2 << tc.lth) < tc.TH) ++tc.lth;
+    tc.ltw = 0; while ((2 << tc.ltw) < tc.TW) ++tc.ltw;
+    // footprint of the un-offset taps around (ho*stride - pad): [half - s*half, half + s*(dil*(k-1) - half)]
+    const int lo_h = (int)ceilf(s * q.half_h), hi_h = (int)ceilf(s * (q.dh * (q.kh - 1) - q.half_h));
+    const int lo_w = (int)ceilf(s * q.half_w), hi_w = (int)ceilf(s * (q.dw * (q.kw - 1) - q.half_w));
+    tc.oy = q.half_h - q.ph - lo_h - tc.R;
+    tc.ox = q.half_w - q.pw - lo_w - tc.R;
+    tc.WH = (tc.TH - 1) * q.sh + lo_h + hi_h + 2 + 2 * tc.R;
+    tc.WW = (tc.TW - 1) * q.sw + lo_w + hi_w + 2 + 2 * tc.R;
+    tc.tiles_y = (q.Ho + tc.TH - 1) / tc.TH;
+    tc.tiles_x = (q.Wo + tc.TW - 1) / tc.TW;
+    tc.warps = q.G < kn.warps ? q.G : kn.warps;
+    // staged input rows: 32-byte slabs need a pitch == 2 (mod 4) pixels so the two corner rows of an
+    // entry fall into different 16-byte bank groups; 64-byte (fp32) slabs use the half-swap instead
+    tc.WWi = tc.WW;
+    if (sizeof(T) == 2) while ((tc.WWi & 3) != 2) ++tc.WWi;
+    size_t per = (size_t)tc.WH * tc.WW * 64 + (size_t)tc.WH * tc.WWi * kTileGC * sizeof(T) +
+                 32 * 8 + 32 * 16 + 32 * 8 * 4;
+    if (logits) per += (size_t)2 * tc.TH * tc.TW * q.P * 4;
+    per = (per + 127) & ~(size_t)127;
+    if (per > 64 * 1024 || per * tc.warps > 220 * 1024) return false;
+    tc.smem_per_warp = (int)per;
+    const unsigned long long blocks = (unsigned long long)q.N * tc.tiles_y * tc.tiles_x * ((q.G + tc.warps - 1) / tc.warps);
+    if (blocks >= (1ull << 31)) return false;
+    return true;
+}
+
+template <typename T>
+int launch_tile(const T *in, const T *off, const T *mask, const T *gout, float *acc, T *goff, T *gmask,
+                const Geo &q, bool logits, const TileCfg &tc, cudaStream_t st) {
+    const unsigned grid = (unsigned)((size_t)q.N * tc.tiles_y * tc.tiles_x * ((q.G + tc.warps - 1) / tc.warps));
+    const size_t smem = (size_t)tc.smem_per_warp * tc.warps;
+    cudaError_t e;
+#define LAUNCH_TILE(KP, LG)                                                                              \
+    do {                                                                                                 \
+        if ((e = cudaFuncSetAttribute(bwd_tile_kernel<T, KP, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)smem)) != cudaSuccess)                                        \
+            return cuda_fail(e, "cudaFuncSetAttribute(bwd_tile_kernel)");                                \
+        bwd_tile_kernel<T, KP, LG><<<grid, 32 * tc.warps, smem, st>>>(in, off, mask, gout, acc, goff, gmask, q, tc); \
+    } while (0)
+    const bool k9 = (q.kh == 3 && q.kw == 3);
+    if (k9 && logits) LAUNCH_TILE(9, true);
+    else if (k9) LAUNCH_TILE(9, false);
+    else if (logits) LAUNCH_TILE(0, true);
+    else LAUNCH_TILE(0, false);
+#undef LAUNCH_TILE
+    return 0;
+}
+
 // ----------------------------------------------------------------- backward
 template <typename T, typename A>
 int backward_launch(const T *in, const T *off, const T *mask, const T *gout, A *acc, T *goff,
@@ -257,8 +332,19 @@ int backward_t(const void *in_, const void *off_, const void *mask_, const void 
         float *acc = (float *)ws;
         if ((e = cudaMemsetAsync(acc, 0, need, st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
         if (n_pix) {
-            const Plan pl = plan_vec<T>(q, n_pix, logits, {in_, gout_}, off_, sizeof(float));
-            int rc = backward_launch<T, float>(in, off, mask, gout, acc, goff, gmask, q, logits, pl, n_pix, st);
+            TileCfg tc;
+            int rc = 0;
+            bool tiled = false;
+            if constexpr (lowp) {
+                if (plan_tile<T>(q, logits, in_, gout_, off_, acc, tc)) {
+                    rc = launch_tile<T>(in, off, mask, gout, acc, goff, gmask, q, logits, tc, st);
+                    tiled = true;
+                }
+            }
+            if (!tiled) {
+                const Plan pl = plan_vec<T>(q, n_pix, logits, {in_, gout_}, off_, sizeof(float));
+                rc = backward_launch<T, float>(in, off, mask, gout, acc, goff, gmask, q, logits, pl, n_pix, st);
+            }
             if (rc) return rc;
         }
         if constexpr (lowp) {
@@ -272,8 +358,16 @@ int backward_t(const void *in_, const void *off_, const void *mask_, const void 
     if ((e = cudaMemsetAsync(gin, 0, n_in * sizeof(T), st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_input)");
     if (n_pix == 0) return 0;
     const Plan pl = aligned16(gin_) ? plan_vec<T>(q, n_pix, logits, {in_, gout_}, off_, sizeof(T)) : Plan{false, 0, 0, 0, 0};
-    if constexpr (lowp) return backward_launch<T, T>(in, off, mask, gout, gin, goff, gmask, q, logits, pl, n_pix, st);
-    else return backward_launch<T, M>(in, off, mask, gout, (M *)gin, goff, gmask, q, logits, pl, n_pix, st);
+    if constexpr (lowp) {
+        return backward_launch<T, T>(in, off, mask, gout, gin, goff, gmask, q, logits, pl, n_pix, st);
+    } else {
+        if constexpr (sizeof(T) == 4) {
+            TileCfg tc;
+            if (plan_tile<T>(q, logits, in_, gout_, off_, gin_, tc))
+                return launch_tile<T>(in, off, mask, gout, (float *)gin, goff, gmask, q, logits, tc, st);
+        }
+        return backward_launch<T, M>(in, off, mask, gout, (M *)gin, goff, gmask, q, logits, pl, n_pix, st);
+    }
 }
 
 int finish(cudaStream_t st, const char *what) {
