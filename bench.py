@@ -426,7 +426,17 @@ def cpu_run(sites, e_workload, steps, warmup, budget_s):
     return gbps, total / steps * 1e3, cores, sample, n_img
 
 
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    banner on init), so fd 1 is pointed at stderr for the whole run and the JSON goes to the saved fd."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
+    out_stream = claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=500)
@@ -467,13 +477,13 @@ def main():
         if rank != 0:
             return 0
         gbps, ms, cores, sample, n_img = cpu_run(sites, e, a.steps, a.warmup, budget_s=150.0)
-        print(json.dumps({
+        print(file=out_stream, flush=True, *[json.dumps({
             "impl": "reference", "metric": METRIC, "value": gbps, "unit": "GB/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "cpu_baseline": {"value": gbps, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": gbps, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
+            "gpu_launches": 0})])
         return 0
 
     if not torch.cuda.is_available():
@@ -547,7 +557,7 @@ def main():
         gbps, cms, cores, sample, _ = cpu_run(sites, e, 3, 1, budget_s=30.0)
         out["cpu_baseline"] = {"value": gbps, "unit": "GB/s", "cores": cores, "kind": "port",
                                "sample": sample, "ms_per_step_sample": cms}
-    print(json.dumps(out))
+    print(json.dumps(out), file=out_stream, flush=True)
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -196,15 +196,14 @@ int forward_t(const void *in_, const void *off_, const void *mask_, void *out_, 
 }
 
 // ------------------------------------------------ privatised backward (tile)
-// Knobs: DCNV3_B200_BWD=tile selects this family, DCNV3_B200_TILE="TH,TW,R,warps" its tile shape.
-struct TileKnobs { int force; int TH, TW, R, warps; };
+// Knobs: DCNV3_B200_BWD=tile selects this family, DCNV3_B200_TILE="R,warps" its halo / warps per CTA.
+struct TileKnobs { int force; int R, warps; };
 TileKnobs tile_knobs() {  // read per call (getenv is ~100 ns) so tests can switch paths in-process
-    TileKnobs t{0, 4, 8, 1, 4};
+    TileKnobs t{0, 2, 4};
     if (const char *e = getenv("DCNV3_B200_BWD")) t.force = !strcmp(e, "vec") ? 1 : (!strcmp(e, "tile") ? 2 : 0);
     if (const char *e = getenv("DCNV3_B200_TILE")) {
-        int a, b, c, d;
-        if (sscanf(e, "%d,%d,%d,%d", &a, &b, &c, &d) == 4 && a >= 2 && b >= 2 && is_pow2(a) && is_pow2(b) &&
-            c >= 0 && d >= 1 && d <= 4) { t.TH = a; t.TW = b; t.R = c; t.warps = d; }
+        int c, d;
+        if (sscanf(e, "%d,%d", &c, &d) == 2 && c >= 0 && c <= 8 && d >= 1 && d <= 4) { t.R = c; t.warps = d; }
     }
     return t;
 }
@@ -212,38 +211,30 @@ TileKnobs tile_knobs() {  // read per call (getenv is ~100 ns) so tests can swit
 template <typename T>
 bool plan_tile(const Geo &q, bool logits, const void *in, const void *gout, const void *off,
                const void *acc, TileCfg &tc) {
-    // Experimental (round 1): correct, but not faster than the vector kernel yet, so it
-    // only runs when asked for with DCNV3_B200_BWD=tile.
+    // Experimental (round 1): only runs when asked for with DCNV3_B200_BWD=tile.
     const TileKnobs kn = tile_knobs();
     if (kn.force != 2) return false;
     if (sizeof(T) > 4 || q.gc != kTileGC) return false;
+    if (logits && !(q.kh == 3 && q.kw == 3) && q.P > kMaxSoftmaxP) return false;
     if (!aligned_to(in, 8 * (int)sizeof(T)) || !aligned_to(gout, 8 * (int)sizeof(T)) || !aligned16(acc)) return false;
     if (reinterpret_cast<uintptr_t>(off) & (2 * sizeof(T) - 1)) return false;
     if ((unsigned long long)q.H * q.W * q.C * 4ull >= (1ull << 31)) return false;
     const float s = fabsf(q.scale);
     if (!(s < 64.f)) return false;
-    tc.TH = kn.TH; tc.TW = kn.TW; tc.R = kn.R;
-    tc.lth = 0; while ((2 << tc.lth) < tc.TH) ++tc.lth;
-    tc.ltw = 0; while ((2 << tc.ltw) < tc.TW) ++tc.ltw;
+    tc.R = kn.R;
     // footprint of the un-offset taps around (ho*stride - pad): [half - s*half, half + s*(dil*(k-1) - half)]
     const int lo_h = (int)ceilf(s * q.half_h), hi_h = (int)ceilf(s * (q.dh * (q.kh - 1) - q.half_h));
     const int lo_w = (int)ceilf(s * q.half_w), hi_w = (int)ceilf(s * (q.dw * (q.kw - 1) - q.half_w));
     tc.oy = q.half_h - q.ph - lo_h - tc.R;
     tc.ox = q.half_w - q.pw - lo_w - tc.R;
-    tc.WH = (tc.TH - 1) * q.sh + lo_h + hi_h + 2 + 2 * tc.R;
-    tc.WW = (tc.TW - 1) * q.sw + lo_w + hi_w + 2 + 2 * tc.R;
-    tc.tiles_y = (q.Ho + tc.TH - 1) / tc.TH;
-    tc.tiles_x = (q.Wo + tc.TW - 1) / tc.TW;
+    tc.WH = (kTileT - 1) * q.sh + lo_h + hi_h + 2 + 2 * tc.R;
+    tc.WW = (kTileT - 1) * q.sw + lo_w + hi_w + 2 + 2 * tc.R;
+    tc.tiles_y = (q.Ho + kTileT - 1) / kTileT;
+    tc.tiles_x = (q.Wo + kTileT - 1) / kTileT;
     tc.warps = q.G < kn.warps ? q.G : kn.warps;
-    // staged input rows: 32-byte slabs need a pitch == 2 (mod 4) pixels so the two corner rows of an
-    // entry fall into different 16-byte bank groups; 64-byte (fp32) slabs use the half-swap instead
-    tc.WWi = tc.WW;
-    if (sizeof(T) == 2) while ((tc.WWi & 3) != 2) ++tc.WWi;
-    size_t per = (size_t)tc.WH * tc.WW * 64 + (size_t)tc.WH * tc.WWi * kTileGC * sizeof(T) +
-                 32 * 8 + 32 * 16 + 32 * 8 * 4;
-    if (logits) per += (size_t)2 * tc.TH * tc.TW * q.P * 4;
+    size_t per = (size_t)tc.WH * tc.WW * (64 + 4);
     per = (per + 127) & ~(size_t)127;
-    if (per > 64 * 1024 || per * tc.warps > 220 * 1024) return false;
+    if (per > 56 * 1024 || per * tc.warps > 220 * 1024) return false;
     tc.smem_per_warp = (int)per;
     const unsigned long long blocks = (unsigned long long)q.N * tc.tiles_y * tc.tiles_x * ((q.G + tc.warps - 1) / tc.warps);
     if (blocks >= (1ull << 31)) return false;
