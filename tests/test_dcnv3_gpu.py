@@ -130,10 +130,10 @@ def test_vs_pixel_oracle(shape, dtype, dist, fn, pixel_oracle):
     assert_close_scaled(go_, want_go, what="grad_offset", **tol)
 
 
-@pytest.mark.parametrize("env", [{"DCNV3_B200_BPL": "32"}, {"DCNV3_B200_BWD": "tile"},
+@pytest.mark.parametrize("env", [{"DCNV3_B200_BPL": "32"}, {"DCNV3_B200_BPL": "8"}, {"DCNV3_B200_BWD": "tile"},
                                  {"DCNV3_B200_BWD": "tile", "DCNV3_B200_TILE": "3,2"},
                                  {"DCNV3_B200_BWD": "tile", "DCNV3_B200_TILE": "0,1"}],
-                         ids=["bpl32", "tile", "tile_r3", "tile_halo0"])
+                         ids=["bpl32", "bpl8", "tile", "tile_r3", "tile_halo0"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16], ids=["f32", "f16", "bf16"])
 @pytest.mark.parametrize("shape", ["cfg1", "D16", "stride2", "G32gc8", "k5dil2_gc16"])
 def test_alternative_kernel_families(shape, dtype, env, fn, pixel_oracle, monkeypatch):

@@ -120,7 +120,7 @@ bool aligned_to(const void *p, int a) { return (reinterpret_cast<uintptr_t>(p) &
 int forced_bpl() {
     const char *e = getenv("DCNV3_B200_BPL");
     const int v = e ? atoi(e) : 0;
-    return (v == 16 || v == 32) ? v : 0;
+    return (v == 8 || v == 16 || v == 32) ? v : 0;
 }
 
 // Can this call take the vector kernels, and with how many bytes per lane?
@@ -128,17 +128,25 @@ int forced_bpl() {
 // the lane width.  `off` only needs the alignment of one (x, y) pair.
 template <typename T>
 Plan plan_vec(const Geo &q, size_t n_pix, bool logits, std::initializer_list<const void *> ptrs,
-              const void *off, size_t acc_elem) {
+              const void *off, size_t acc_elem, bool allow8 = false) {
     Plan pl{false, 0, 0, 0, 0};
     if (sizeof(T) > 4) return pl;  // f64 always generic
     if (logits && !(q.kh == 3 && q.kw == 3)) return pl;
     if (reinterpret_cast<uintptr_t>(off) & (2 * sizeof(T) - 1)) return pl;
     // byte offsets inside one image are 32-bit ints in the kernels
     if ((unsigned long long)q.H * q.W * q.C * (acc_elem > sizeof(T) ? acc_elem : sizeof(T)) >= (1ull << 31)) return pl;
-    const int want = forced_bpl();
-    for (int bpl : {32, 16}) {
-        if (want && bpl != want) continue;
-        if (!want && bpl == 32) continue;  // default: 16 bytes per lane (kernel table)
+    // Candidate lane widths in order of preference.  8-byte lanes exist for the 16-bit backward with
+    // fp32 accumulation, where they are the default: the 4 lanes of a group then cover the whole
+    // 64-byte fp32 slab in ONE reduction instruction (one line-request on the SM->crossbar port
+    // instead of two).  Everything else defaults to 16; DCNV3_B200_BPL forces one.
+    const bool can8 = allow8 && sizeof(T) == 2;
+    int want = forced_bpl();
+    if (want == 8 && !can8) want = 0;
+    int cand[2] = {16, 0};
+    if (want) cand[0] = want;
+    else if (can8) { cand[0] = 8; cand[1] = 16; }
+    for (int bpl : cand) {
+        if (!bpl) continue;
         const int ch = bpl / (int)sizeof(T);
         if (q.gc % ch) continue;
         const int L = q.gc / ch;
@@ -280,23 +288,29 @@ int backward_launch(const T *in, const T *off, const T *mask, const T *gout, A *
     if (k9 && logits) LAUNCH_BWD(BPL, 9, true); \
     else if (k9) LAUNCH_BWD(BPL, 9, false);     \
     else LAUNCH_BWD(BPL, 0, false)
-            if (pl.bpl == 32) { LAUNCH_BWD_B(32); } else { LAUNCH_BWD_B(16); }
+            if (pl.bpl == 32) { LAUNCH_BWD_B(32); }
+            else if (pl.bpl == 8) {
+                if constexpr (sizeof(T) == 2 && sizeof(A) == 4) { LAUNCH_BWD_B(8); }
+                else return fail(DCNV3_B200_EINVAL, "8-byte lanes need 16-bit storage with fp32 accumulation");
+            } else { LAUNCH_BWD_B(16); }
 #undef LAUNCH_BWD_B
 #undef LAUNCH_BWD
             return 0;
         }
     }
     const size_t n_units = n_pix * q.G;
-    const size_t threads = n_units * 32;
+    int lpu = 1;  // lanes per (pixel, group): next power of two >= min(group_channels, 32)
+    while (lpu < q.gc && lpu < 32) lpu <<= 1;
+    const size_t threads = n_units * lpu;
     if (threads / kThreads >= (1ull << 31))
         return fail(DCNV3_B200_ERANGE, "too many (pixel, group) units for one launch");
     if (logits) {
         if (q.P > kMaxSoftmaxP)
             return fail(DCNV3_B200_EINVAL, "fused softmax supports at most %d sampling points (got %d)",
                         kMaxSoftmaxP, q.P);
-        bwd_any_kernel<T, A, true><<<blocks_for(threads), kThreads, 0, st>>>(in, off, mask, gout, acc, goff, gmask, q, n_units);
+        bwd_any_kernel<T, A, true><<<blocks_for(threads), kThreads, 0, st>>>(in, off, mask, gout, acc, goff, gmask, q, n_units, lpu);
     } else {
-        bwd_any_kernel<T, A, false><<<blocks_for(threads), kThreads, 0, st>>>(in, off, mask, gout, acc, goff, gmask, q, n_units);
+        bwd_any_kernel<T, A, false><<<blocks_for(threads), kThreads, 0, st>>>(in, off, mask, gout, acc, goff, gmask, q, n_units, lpu);
     }
     return 0;
 }
@@ -333,7 +347,7 @@ int backward_t(const void *in_, const void *off_, const void *mask_, const void 
                 }
             }
             if (!tiled) {
-                const Plan pl = plan_vec<T>(q, n_pix, logits, {in_, gout_}, off_, sizeof(float));
+                const Plan pl = plan_vec<T>(q, n_pix, logits, {in_, gout_}, off_, sizeof(float), true);
                 rc = backward_launch<T, float>(in, off, mask, gout, acc, goff, gmask, q, logits, pl, n_pix, st);
             }
             if (rc) return rc;

@@ -37,6 +37,13 @@ template <> __device__ __forceinline__ Words<16> ldg_pred<16>(const void *p, boo
     o.w[0] = r.x; o.w[1] = r.y; o.w[2] = r.z; o.w[3] = r.w;
     return o;
 }
+template <> __device__ __forceinline__ Words<8> ldg_pred<8>(const void *p, bool pred) {
+    uint2 r = make_uint2(0u, 0u);
+    if (pred) r = __ldg(reinterpret_cast<const uint2 *>(p));
+    Words<8> o;
+    o.w[0] = r.x; o.w[1] = r.y;
+    return o;
+}
 template <> __device__ __forceinline__ Words<32> ldg_pred<32>(const void *p, bool pred) {
     Words<32> o;
     asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %9, 0;\n\t"
@@ -91,9 +98,13 @@ __device__ __forceinline__ void from_pairs(const float2 (&v)[BPL / 4], Words<BPL
 }
 
 template <int BPL> __device__ __forceinline__ void st_words(void *p, const Words<BPL> &r) {
+    if constexpr (BPL == 8) {
+        *reinterpret_cast<uint2 *>(p) = make_uint2(r.w[0], r.w[1]);
+    } else {
 #pragma unroll
-    for (int k = 0; k < BPL / 16; ++k)
-        reinterpret_cast<uint4 *>(p)[k] = make_uint4(r.w[4 * k], r.w[4 * k + 1], r.w[4 * k + 2], r.w[4 * k + 3]);
+        for (int k = 0; k < BPL / 16; ++k)
+            reinterpret_cast<uint4 *>(p)[k] = make_uint4(r.w[4 * k], r.w[4 * k + 1], r.w[4 * k + 2], r.w[4 * k + 3]);
+    }
 }
 
 // Decode a flat lane index into (pixel, lane-in-pixel, group, n, ho, wo).
@@ -287,6 +298,7 @@ bwd_vec_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     constexpr int CH = Lane<T, BPL>::CH, NP = Lane<T, BPL>::NP;
     constexpr int CPQ = RedChunk<A>::CPQ;                 // channels per 16-byte reduction
     constexpr int R = CH * (int)sizeof(A) / 16;           // reductions per corner per lane
+    static_assert(R >= 1, "a lane must own at least one 16-byte reduction chunk");
     unsigned idx = blockIdx.x * (unsigned)kThreads + threadIdx.x;
     const bool active = idx < total;  // tail lanes stay for the shuffles
     if (!active) idx = total - 1;
@@ -474,16 +486,19 @@ fwd_any_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     out[idx] = from_math<T>(acc);
 }
 
-// one warp per (pixel, g); lanes stride over the group's channels
+// `lpu` lanes per (pixel, g) unit (a power of two <= 32, >= min(group_channels, 32) rounded up):
+// a warp holds 32/lpu units; the lanes of a unit stride over its channels and reduce with shuffles
 template <typename T, typename A, bool LOGITS>
 __global__ void __launch_bounds__(kThreads)
 bwd_any_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
                const T *__restrict__ gout, A *__restrict__ gin, T *__restrict__ goff,
-               T *__restrict__ gmask, const Geo q, const size_t n_units) {
+               T *__restrict__ gmask, const Geo q, const size_t n_units, const int lpu) {
     using M = typename OpMath<T>::type;
-    const size_t unit = (blockIdx.x * (size_t)kThreads + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (unit >= n_units) return;  // whole warp leaves together
+    const size_t tid = blockIdx.x * (size_t)kThreads + threadIdx.x;
+    size_t unit = tid / lpu;
+    const int cl = (int)(tid - unit * lpu);  // lane inside the unit
+    const bool active = unit < n_units;      // tail lanes stay for the shuffles
+    if (!active) unit = n_units - 1;
     const size_t pix = unit / q.G;
     const int g = (int)(unit - pix * q.G);
     const size_t row = pix / q.Wo;
@@ -501,6 +516,7 @@ bwd_any_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     const T *go = gout + pix * q.C + (size_t)g * q.gc;
     T *d_o = goff + unit * q.P * 2;
     T *d_m = gmask + unit * q.P;
+    const bool writer = active && cl == 0;
 
     M mx = 0, inv = 1;
     M prob[LOGITS ? kMaxSoftmaxP : 1], gmv[LOGITS ? kMaxSoftmaxP : 1];
@@ -519,39 +535,38 @@ bwd_any_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
             M m = to_math(pm[p]);
             if (LOGITS) m = exp(m - mx) * inv;
             M s_m = 0, s_w = 0, s_h = 0;
-            if (t.inside) {  // warp-uniform: every lane sees the same point
+            if (t.inside) {  // uniform inside a unit
                 const size_t base = ((size_t)t.h_low * q.W + t.w_low) * q.C;
                 const size_t rw = (size_t)q.W * q.C;
                 const M w1 = t.hh * t.hw, w2 = t.hh * t.lw, w3 = t.lh * t.hw, w4 = t.lh * t.lw;
-                for (int ch = lane; ch < q.gc; ch += 32) {
+                for (int ch = cl; ch < q.gc; ch += lpu) {
                     const M top = to_math(go[ch]);
                     const M tg = top * m;
                     M v1 = 0, v2 = 0, v3 = 0, v4 = 0;
-                    if (t.ok1) { v1 = to_math(im[base + ch]); atomic_add(gim + base + ch, w1 * tg); }
-                    if (t.ok2) { v2 = to_math(im[base + q.C + ch]); atomic_add(gim + base + q.C + ch, w2 * tg); }
-                    if (t.ok3) { v3 = to_math(im[base + rw + ch]); atomic_add(gim + base + rw + ch, w3 * tg); }
-                    if (t.ok4) { v4 = to_math(im[base + rw + q.C + ch]); atomic_add(gim + base + rw + q.C + ch, w4 * tg); }
+                    if (t.ok1) { v1 = to_math(im[base + ch]); if (active) atomic_add(gim + base + ch, w1 * tg); }
+                    if (t.ok2) { v2 = to_math(im[base + q.C + ch]); if (active) atomic_add(gim + base + q.C + ch, w2 * tg); }
+                    if (t.ok3) { v3 = to_math(im[base + rw + ch]); if (active) atomic_add(gim + base + rw + ch, w3 * tg); }
+                    if (t.ok4) { v4 = to_math(im[base + rw + q.C + ch]); if (active) atomic_add(gim + base + rw + q.C + ch, w4 * tg); }
                     const M val = w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
                     s_m += top * val;
                     s_w += top * (t.hh * (v2 - v1) + t.lh * (v4 - v3));
                     s_h += top * (t.hw * (v3 - v1) + t.lw * (v4 - v2));
                 }
             }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
+            for (int d = lpu >> 1; d > 0; d >>= 1) {
                 s_m += shfl_xor(s_m, d);
                 s_w += shfl_xor(s_w, d);
                 s_h += shfl_xor(s_h, d);
             }
             const M sm = (M)q.scale * m;
-            if (lane == 0) {
+            if (writer) {
                 d_o[2 * p] = from_math<T>(sm * s_w);
                 d_o[2 * p + 1] = from_math<T>(sm * s_h);
                 if (!LOGITS) d_m[p] = from_math<T>(s_m);
             }
             if (LOGITS) { prob[p] = m; gmv[p] = s_m; }
         }
-    if (LOGITS && lane == 0) {
+    if (LOGITS && writer) {
         M dot = 0;
         for (int k = 0; k < q.P; ++k) dot += prob[k] * gmv[k];
         for (int k = 0; k < q.P; ++k) d_m[k] = from_math<T>(prob[k] * (gmv[k] - dot));
