@@ -244,44 +244,32 @@ def time_ops(wl, steps, warmup):
 
 
 def time_e2e(wl, steps, warmup, dist):
-    """Same step through the public API (DCNv3Function.apply + autograd) with HOST buffers:
-    every step copies its inputs from pinned host memory and reads every result back."""
-    from yolo_dual_b200.ops_dcnv3.functions import DCNv3Function, DCNv3SoftmaxFunction, set_grad_accum
+    """Same step through the public API with HOST buffers: yolo_dual_b200.host.HostPipeline drives
+    DCNv3Function.apply + autograd; every step copies its inputs from pinned host memory and writes
+    every result (output + three grads per site) back to pinned host memory.  Copies in, kernels and
+    copies out run on three streams (PCIe is full duplex), two steps in flight."""
+    from yolo_dual_b200.host import HostPipeline, HostSite
+    from yolo_dual_b200.ops_dcnv3.functions import set_grad_accum
     set_grad_accum("opmath" if wl.accum == 0 else "storage")
-    fn = DCNv3SoftmaxFunction if wl.logits else DCNv3Function
-    host_in, host_out = [], []
-    bufs = wl.sets[0]
-    for b in bufs:
-        host_in.append([t.cpu().pin_memory() for t in (b.input, b.offset, b.mask, b.grad_out)])
-        host_out.append([torch.empty_like(t, device="cpu").pin_memory()
-                         for t in (b.output, b.grad_input, b.grad_offset, b.grad_mask)])
-    h2d = sum(t.numel() * t.element_size() for hs in host_in for t in hs)
-    d2h = sum(t.numel() * t.element_size() for hs in host_out for t in hs)
-
-    def one():
-        live = []
-        for b, hs in zip(bufs, host_in):
-            x, off, m, go = (h.to(wl.dev, non_blocking=True) for h in hs)
-            x.requires_grad_(True); off.requires_grad_(True); m.requires_grad_(True)
-            N, H, W, G, gc = SITES[b.name]
-            y = fn.apply(x, off, m, 3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0, 256)
-            live.append((x, off, m, go, y))
-        for (x, off, m, go, y), ho in zip(reversed(live), reversed(host_out)):
-            y.backward(go)
-            ho[0].copy_(y.detach(), non_blocking=True)
-            ho[1].copy_(x.grad, non_blocking=True)
-            ho[2].copy_(off.grad, non_blocking=True)
-            ho[3].copy_(m.grad, non_blocking=True)
-        torch.cuda.synchronize()  # the caller owns the results only after this
-
+    sites = []
+    for b in wl.sets[0]:
+        N, H, W, G, gc = SITES[b.name]
+        hs = HostSite(*(t.cpu().pin_memory() for t in (b.input, b.offset, b.mask, b.grad_out)),
+                      args=(3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0))
+        sites.append(hs.alloc_outputs(tuple(b.output.shape)))
+    h2d = sum(s.h2d_bytes for s in sites)
+    d2h = sum(s.d2h_bytes for s in sites)
+    pipe = HostPipeline(wl.dev, depth=2, fused_softmax=bool(wl.logits))
     for _ in range(warmup):
-        one()
+        pipe.submit(sites)
+    pipe.drain()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
-        one()
+        pipe.submit(sites)
+    pipe.drain()
     torch.cuda.synchronize()
     ms = (time.perf_counter() - t0) * 1e3
     if dist is not None:
@@ -448,7 +436,7 @@ def main():
     ap.add_argument("--fused-softmax", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-seg", action="store_true")
     ap.add_argument("--seg-steps", type=int, default=10)
@@ -509,7 +497,9 @@ def main():
         e2e = {"value": step_bytes * world * a.e2e_steps / (e2e_ms * 1e-3) / 1e9, "unit": "GB/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.e2e_steps,
                "steps": a.e2e_steps,
-               "api": "DCNv3Function.apply + autograd backward on pinned host tensors (H2D in, D2H out every step)"}
+               "api": "yolo_dual_b200.host.HostPipeline -> DCNv3Function.apply + autograd on pinned host tensors; "
+                      "H2D of input/offset/mask/grad_out and D2H of output + 3 grads every step, copies and kernels "
+                      "on three streams, two steps in flight"}
     seg_res = None
     if not a.no_seg:
         del wl
