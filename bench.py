@@ -286,11 +286,14 @@ def time_e2e(wl, steps, warmup, dist):
 # bf16 autocast, CE + 0.5 Dice, SGD-nesterov; DDP (NCCL) gradient all-reduce when world > 1.
 # Every step copies its images/labels from pinned host memory and reads the loss back.
 # ----------------------------------------------------------------------------------------------
-def time_seg(dev, dist, world, steps, warmup, batch, model_name):
+def time_seg(dev, dist, world, steps, warmup, batch, model_name, channels_last=True):
     from yolo_dual_b200 import seg
     torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = True
     cfg = {"yolov5seg": seg.YOLOV5_SEG, "yolov8seg": seg.YOLOV8_SEG}[model_name]
     model = seg.SegModel(cfg, dcn="dcnv3").to(dev)
+    if channels_last:  # NHWC activations: the NCHW<->NHWC permutes around every DCNv3 become views
+        model = model.to(memory_format=torch.channels_last)
     crit = seg.SegmentationLoss(12, class_weights=seg.CAMVID_CLASS_WEIGHTS).to(dev)
     ddp = seg.wrap_ddp(model, dev)
     opt = seg.smart_optimizer(ddp)
@@ -301,6 +304,8 @@ def time_seg(dev, dist, world, steps, warmup, batch, model_name):
 
     def one():
         imgs = imgs_h.to(dev, non_blocking=True)
+        if channels_last:
+            imgs = imgs.contiguous(memory_format=torch.channels_last)
         lab = lab_h.to(dev, non_blocking=True)
         loss, _ = seg.train_step(ddp, crit, opt, imgs, lab, autocast_dtype=torch.bfloat16)
         return float(loss)  # D2H: the step's result
@@ -326,6 +331,7 @@ def time_seg(dev, dist, world, steps, warmup, batch, model_name):
     return {"model": f"{model_name} with C3_DCNV3 at P3/P4/P5 (DCNv3 C=128/256/512, group_channels 16)",
             "imgs_per_s": batch * world * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps,
             "batch_per_gpu": batch, "global_batch": batch * world, "image": "640x640", "autocast": "bf16",
+            "memory_format": "channels_last" if channels_last else "contiguous",
             "optimizer": "SGD nesterov 3 groups", "params": n_params, "loss_last": last,
             "h2d_bytes_per_step": imgs_h.numel() * 4 + lab_h.numel() * 8, "d2h_bytes_per_step": 4,
             "data_parallel": f"DDP x{world} (NCCL all-reduce of {n_params * 4 / 1e6:.1f} MB fp32 grads)" if world > 1 else "single GPU"}
@@ -442,6 +448,7 @@ def main():
     ap.add_argument("--seg-steps", type=int, default=10)
     ap.add_argument("--seg-batch", type=int, default=16)
     ap.add_argument("--seg-model", default="yolov5seg", choices=["yolov5seg", "yolov8seg"])
+    ap.add_argument("--seg-nchw", action="store_true", help="keep NCHW activations in the seg model")
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3
@@ -505,7 +512,7 @@ def main():
         del wl
         torch.cuda.empty_cache()
         try:
-            seg_res = time_seg(dev, dist, world, a.seg_steps, 3, a.seg_batch, a.seg_model)
+            seg_res = time_seg(dev, dist, world, a.seg_steps, 3, a.seg_batch, a.seg_model, not a.seg_nchw)
         except Exception as ex:
             if world > 1:
                 raise  # a rank must not leave a collective half-done

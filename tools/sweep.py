@@ -20,7 +20,54 @@ import torch  # noqa: E402
 from yolo_dual_b200 import _lib  # noqa: E402
 
 
+def config5():
+    """BASELINE config #5: high-res seg inference, 1280x1280, batch 32 fp16 sharded over 8 GPUs = 4 images per
+    GPU; forward only at the three DCN sites (160^2x128, 80^2x256, 40^2x512, group_channels 16), with the mask
+    softmax fused into the kernel (logits in) and, for comparison, with probabilities in."""
+    lib = _lib.load()
+    dev = torch.device("cuda", 0)
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    N, P, e = 4, 9, 2
+    print("| site | N | HxW | C | G | mask input | fwd us | GB/s | % of HBM peak |")
+    print("|---|---|---|---|---|---|---|---|---|")
+    for name, HW, C in (("P3", 160, 128), ("P4", 80, 256), ("P5", 40, 512)):
+        G, gc = C // 16, 16
+        geo = _lib.Geometry(N, HW, HW, 3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0)
+        by = e * N * HW * HW * (2 * C + 3 * G * P)
+        nset = max(2, int(300e6 // by) + 1)
+        g = torch.Generator(device=dev).manual_seed(HW)
+        sets = []
+        for _ in range(nset):
+            x = torch.randn(N, HW, HW, C, device=dev, generator=g).half()
+            off = torch.randn(N, HW, HW, G * P * 2, device=dev, generator=g).half()
+            lg = torch.randn(N, HW, HW, G, P, device=dev, generator=g)
+            sets.append((x, off, lg.reshape(N, HW, HW, G * P).half().contiguous(),
+                         torch.softmax(lg, -1).reshape(N, HW, HW, G * P).half().contiguous(), torch.empty_like(x)))
+        for logits in (1, 0):
+            def fwd(k):
+                x, off, lgt, pr, out = sets[k % nset]
+                _lib.check(lib.dcnv3_b200_forward(x.data_ptr(), off.data_ptr(), (lgt if logits else pr).data_ptr(),
+                                                  out.data_ptr(), _lib.F16, ctypes.byref(geo), logits, st), "fwd")
+            for k in range(10):
+                fwd(k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for k in range(100):
+                fwd(k)
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) / 100 * 1e3
+            gb = by / us / 1e3
+            print(f"| {name} | {N} | {HW}x{HW} | {C} | {G} | {'logits (fused softmax)' if logits else 'probabilities'} | "
+                  f"{us:.1f} | {gb:.0f} | {100 * gb / peak:.1f} |", flush=True)
+
+
 def main():
+    if "--config5" in sys.argv:
+        return config5()
     lib = _lib.load()
     dev = torch.device("cuda", 0)
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
