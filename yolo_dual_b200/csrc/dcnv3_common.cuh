@@ -4,7 +4,7 @@
 // (/root/reference/models/ops_dcnv3/src/cuda/dcnv3_im2col_cuda.cuh); each block
 // cites the lines it reproduces.  Nothing here is derived from that file's
 // structure: the reference is one-thread-per-scalar SIMT, this is a
-// 16-byte-vector-per-thread design for sm_100a.
+// channel-vector-per-lane design (8 / 16 / 32 bytes) for sm_100a.
 #pragma once
 
 #include <cuda_bf16.h>
@@ -112,41 +112,9 @@ __device__ __forceinline__ void locate(const Geo &q, M p0h_, M p0w_, int i, int 
 }
 
 // ---------------------------------------------------------------------------
-// 16-byte channel vectors
+// packing helpers
 // ---------------------------------------------------------------------------
-template <typename T> struct Vec { static constexpr int N = 16 / (int)sizeof(T); };
-
-__device__ __forceinline__ uint4 ldg128(const void *p) {
-    return __ldg(reinterpret_cast<const uint4 *>(p));
-}
-
-// unpack 16 bytes of storage into op-math floats
-__device__ __forceinline__ void unpack(const uint4 &r, float (&v)[4], const float *) {
-    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y);
-    v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
-}
-__device__ __forceinline__ void unpack(const uint4 &r, float (&v)[8], const __half *) {
-    const unsigned w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[k]));
-        v[2 * k] = f.x; v[2 * k + 1] = f.y;
-    }
-}
-__device__ __forceinline__ void unpack(const uint4 &r, float (&v)[8], const __nv_bfloat16 *) {
-    const unsigned w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {  // bf16 -> f32 is a 16-bit shift
-        v[2 * k] = __uint_as_float(w[k] << 16);
-        v[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
-    }
-}
-
 // pack op-math floats back to 16 bytes of storage (round to nearest even)
-__device__ __forceinline__ uint4 pack(const float (&v)[4], const float *) {
-    return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
-                      __float_as_uint(v[3]));
-}
 __device__ __forceinline__ uint4 pack(const float (&v)[8], const __half *) {
     unsigned w[4];
 #pragma unroll

@@ -1,14 +1,15 @@
 // dcnv3_b200 — kernels.
 //
 // Two families:
-//   *_vec_*    one thread owns a 16-byte channel vector (4 x f32 / 8 x f16|bf16) of one
-//              (n, ho, wo, g); lanes run fastest over the vectors of a pixel, so every corner
-//              fetch is an LDG.128 and the lanes of one group are an aligned power-of-two
-//              segment of a warp (grad_offset / grad_mask reduce with __shfl_xor, no shared
-//              memory, no barriers, no zero-init, one plain store per value).
+//   *_vec_*    one lane owns BPL bytes of channels (8, 16 or 32: LDG.64 / .128 / .256) of one
+//              (n, ho, wo, g); lanes run fastest over the channel vectors of a pixel, so the lanes
+//              of one group are an aligned power-of-two segment of a warp: grad_offset / grad_mask
+//              reduce with __shfl_xor (no shared memory, no barriers, no zero-init, one plain store
+//              per value) and grad_input goes out as vector reductions that fill whole sectors.
 //   *_any_*    generic fallback for shapes the vector path cannot take (group_channels not a
 //              multiple of the vector width, f64, odd alignment, runtime-sized fused softmax).
 //              Still CUDA, still this library: there is no CPU path.
+// (dcnv3_bwd_tile.cuh holds a third, experimental family: the shared-memory privatised backward.)
 //
 // Reference semantics reproduced (models/ops_dcnv3/src/cuda/dcnv3_im2col_cuda.cuh):
 //   forward  dcnv3_im2col_gpu_kernel :216-275 + dcnv3_im2col_bilinear :32-80
