@@ -532,3 +532,50 @@ def test_host_pipeline_matches_direct_calls(fn):
         assert torch.equal(s.grad_offset, w[2]) and torch.equal(s.grad_mask, w[3])
         # grad_input: same values up to the order of the fp32 atomic adds
         assert_close_scaled(s.grad_input.float(), w[1].float(), rtol=1e-2, atol=2e-3, what="grad_input")
+
+
+# ------------------------------------------------------------------------------------------
+# 12. the C-ABI calls are capturable in a CUDA graph (no host sync, no allocation, no state)
+# ------------------------------------------------------------------------------------------
+def test_cuda_graph_capture_and_replay(pixel_oracle):
+    import ctypes
+    from oracle.dcnv3_oracle import make_inputs
+    from yolo_dual_b200 import _lib
+    lib = _lib.load()
+    N, H, W, G, gc = 2, 24, 20, 4, 16
+    args = (3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0)
+    geo = _lib.Geometry(N, H, W, 3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0)
+    x, off, m, go = (t.to(torch.bfloat16).to(DEV) for t in make_inputs(N, H, W, G, gc, dist="unit", seed=50))
+    out, gi, goff, gm = torch.empty_like(x), torch.empty_like(x), torch.empty_like(off), torch.empty_like(m)
+    wsb = lib.dcnv3_b200_backward_workspace_bytes(_lib.BF16, ctypes.byref(geo), 0)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+
+    def launch(stream):
+        st = ctypes.c_void_p(stream.cuda_stream)
+        _lib.check(lib.dcnv3_b200_forward(x.data_ptr(), off.data_ptr(), m.data_ptr(), out.data_ptr(), _lib.BF16,
+                                          ctypes.byref(geo), 0, st), "fwd")
+        _lib.check(lib.dcnv3_b200_backward(x.data_ptr(), off.data_ptr(), m.data_ptr(), go.data_ptr(), gi.data_ptr(),
+                                           goff.data_ptr(), gm.data_ptr(), ws.data_ptr(), wsb, _lib.BF16,
+                                           ctypes.byref(geo), 0, 0, st), "bwd")
+
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        launch(side)  # warm-up outside capture
+        side.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            launch(torch.cuda.current_stream())
+    for t in (out, gi, goff, gm):
+        t.zero_()
+    x2, off2, m2, go2 = (t.to(torch.bfloat16).to(DEV) for t in make_inputs(N, H, W, G, gc, dist="unit", seed=51))
+    for dst, src in ((x, x2), (off, off2), (m, m2), (go, go2)):
+        dst.copy_(src)  # new data in the captured buffers
+    graph.replay()
+    graph.replay()      # idempotent: the zero-fill of the workspace is part of the graph
+    torch.cuda.synchronize()
+    f = lambda t: t.float().cpu()
+    want = pixel_oracle.forward(f(x), f(off), f(m), *args)
+    wgi, wgo, wgm = pixel_oracle.backward(f(x), f(off), f(m), f(go), *args)
+    for got, w_, name in ((out, want, "output"), (gi, wgi, "grad_input"), (goff, wgo, "grad_offset"), (gm, wgm, "grad_mask")):
+        assert_close_scaled(f(got), w_, rtol=1e-2, atol=2e-3, what=name)
