@@ -16,7 +16,8 @@ from __future__ import annotations
 import torch
 from torch import nn
 
-from .ops_dcnv3.modules.dcnv3 import Conv, DCNv3
+from .ops_dcnv3.modules.conv import Conv
+from .ops_dcnv3.modules.dcnv3 import DCNv3
 
 
 def _pick_group(channels: int, g, dcn_group):

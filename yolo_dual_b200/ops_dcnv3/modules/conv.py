@@ -1,0 +1,37 @@
+"""Conv2d + BatchNorm2d + SiLU building block (YOLOv5 style) used in front of DCNv3's offset / mask heads
+and by the YOLO glue blocks.  Attribute names (`conv`, `bn`, `act`) are part of the checkpoint format of the
+reference (modules/dcnv3.py:26-40 there defines an identical-looking local class), so they are kept."""
+from __future__ import annotations
+
+from torch import nn
+
+
+def same_padding(kernel, padding=None, dilation=1):
+    """Padding that keeps H x W for an odd kernel: (effective kernel) // 2 unless given."""
+    if padding is not None:
+        return padding
+    eff = (lambda k: dilation * (k - 1) + 1) if dilation > 1 else (lambda k: k)
+    return eff(kernel) // 2 if isinstance(kernel, int) else [eff(k) // 2 for k in kernel]
+
+
+autopad = same_padding  # the name the reference uses
+
+
+class Conv(nn.Module):
+    """args: (ch_in, ch_out, kernel, stride, padding, groups, dilation, activation)"""
+    default_act = nn.SiLU()
+
+    def __init__(self, c1, c2, k=1, s=1, p=None, g=1, d=1, act=True):
+        super().__init__()
+        self.conv = nn.Conv2d(c1, c2, k, s, same_padding(k, p, d), dilation=d, groups=g, bias=False)
+        self.bn = nn.BatchNorm2d(c2)
+        if act is True:
+            self.act = self.default_act
+        else:
+            self.act = act if isinstance(act, nn.Module) else nn.Identity()
+
+    def forward(self, x):
+        return self.act(self.bn(self.conv(x)))
+
+    def forward_fuse(self, x):  # after conv+bn folding
+        return self.act(self.conv(x))

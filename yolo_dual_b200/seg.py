@@ -30,7 +30,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .blocks import C2f_DCNV3, C3_DCNV3
-from .ops_dcnv3.modules.dcnv3 import Conv
+from .ops_dcnv3.modules.conv import Conv
 
 # ---------------------------------------------------------------------------------------------
 # layer tables: [from, repeat(ignored), module, args] — data restated from the reference yamls
