@@ -121,3 +121,9 @@ def test_pickled_checkpoint_carries_the_dcnv3_class_paths(tmp_path):
     sites = [x for x in back.modules() if isinstance(x, DCNv3)]
     assert len(sites) == 3 and type(sites[0]).__module__ == "yolo_dual_b200.ops_dcnv3.modules.dcnv3"
     assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), back.state_dict().values()))
+
+
+def test_sync_bn_switch_converts_every_batchnorm():
+    t = Trainer(tiny(dcn="dcnv3"), SegmentationLoss(12), batch_size=16, epochs=1, ema=False, sync_bn=True)
+    kinds = {type(m).__name__ for m in t.raw_model.modules() if "BatchNorm" in type(m).__name__}
+    assert kinds == {"SyncBatchNorm"}  # including the BN inside every DCNv3.dw_conv

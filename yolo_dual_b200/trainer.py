@@ -70,8 +70,12 @@ class Trainer:
 
     def __init__(self, model: nn.Module, criterion: nn.Module, batch_size: int, epochs: int = 300,
                  hyp: Optional[dict] = None, cos_lr: bool = False, autocast_dtype=None, device=None,
-                 ema: bool = True):
+                 ema: bool = True, sync_bn: bool = False):
         self.hyp = dict(HYP, **(hyp or {}))
+        if sync_bn:  # --sync-bn, seg_diceloss_yolov5.py:991-992 (only meaningful with a process group)
+            model = nn.SyncBatchNorm.convert_sync_batchnorm(model)
+            if device is not None:
+                model = model.to(device)
         self.raw_model = model
         self.model = wrap_ddp(model, device)
         self.criterion = criterion
