@@ -15,6 +15,7 @@
 
 #include "dcnv3_kernels.cuh"
 #include "dcnv3_bwd_tile.cuh"
+#include "dcnv3_imat.cuh"
 
 using namespace dcnv3;
 
@@ -168,6 +169,65 @@ Plan plan_vec(const Geo &q, size_t n_pix, bool logits, std::initializer_list<con
 
 unsigned blocks_for(size_t threads) { return (unsigned)((threads + kThreads - 1) / kThreads); }
 
+// ---------------------------------------------- interpolation-matrix family
+// Knobs: DCNV3_B200_FWD / DCNV3_B200_BWD = vec | imat force a family (default: imat when eligible).
+int family_knob(const char *name) {  // 0 default, 1 vec, 2 tile, 3 imat
+    const char *e = getenv(name);
+    if (!e) return 0;
+    if (!strcmp(e, "vec")) return 1;
+    if (!strcmp(e, "tile")) return 2;
+    if (!strcmp(e, "imat")) return 3;
+    return 0;
+}
+
+template <typename T>
+bool imat_eligible(const Geo &q, std::initializer_list<const void *> vec_ptrs, const void *off) {
+    if (sizeof(T) != 2) return false;
+    if (q.gc != 16 || q.G % imat::kWarps) return false;
+    if (q.kh != 3 || q.kw != 3 || q.sh != 1 || q.sw != 1 || q.dh != 1 || q.dw != 1) return false;
+    for (const void *p : vec_ptrs) if (!aligned16(p)) return false;
+    if (reinterpret_cast<uintptr_t>(off) & 3u) return false;
+    const unsigned long long blocks = (unsigned long long)q.N * ((q.Ho + 7) / 8) * ((q.Wo + 7) / 8) * (q.G / imat::kWarps);
+    return blocks > 0 && blocks < (1ull << 31);
+}
+
+template <typename K> int set_smem(K kernel, int bytes, const char *what) {
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, what);
+    return 0;
+}
+
+template <typename T>
+int launch_fwd_imat(const T *in, const T *off, const T *mask, T *out, const Geo &q, bool logits, cudaStream_t st) {
+    const int tiles_y = (q.Ho + 7) / 8, tiles_x = (q.Wo + 7) / 8, GQ = q.G / imat::kWarps;
+    const unsigned grid = (unsigned)((size_t)q.N * tiles_y * tiles_x * GQ);
+    int rc;
+    if (logits) {
+        if ((rc = set_smem(imat::fwd_imat_kernel<T, true>, imat::kSmemFwd, "cudaFuncSetAttribute(fwd_imat_kernel)"))) return rc;
+        imat::fwd_imat_kernel<T, true><<<grid, 32 * imat::kWarps, imat::kSmemFwd, st>>>(in, off, mask, out, q, tiles_x, tiles_y, GQ);
+    } else {
+        if ((rc = set_smem(imat::fwd_imat_kernel<T, false>, imat::kSmemFwd, "cudaFuncSetAttribute(fwd_imat_kernel)"))) return rc;
+        imat::fwd_imat_kernel<T, false><<<grid, 32 * imat::kWarps, imat::kSmemFwd, st>>>(in, off, mask, out, q, tiles_x, tiles_y, GQ);
+    }
+    return 0;
+}
+
+template <typename T>
+int launch_bwd_imat(const T *in, const T *off, const T *mask, const T *gout, float *acc, T *goff, T *gmask,
+                    const Geo &q, bool logits, cudaStream_t st) {
+    const int tiles_y = (q.Ho + 7) / 8, tiles_x = (q.Wo + 7) / 8, GQ = q.G / imat::kWarps;
+    const unsigned grid = (unsigned)((size_t)q.N * tiles_y * tiles_x * GQ);
+    int rc;
+    if (logits) {
+        if ((rc = set_smem(imat::bwd_imat_kernel<T, true>, imat::kSmemBwd, "cudaFuncSetAttribute(bwd_imat_kernel)"))) return rc;
+        imat::bwd_imat_kernel<T, true><<<grid, 32 * imat::kWarps, imat::kSmemBwd, st>>>(in, off, mask, gout, acc, goff, gmask, q, tiles_x, tiles_y, GQ);
+    } else {
+        if ((rc = set_smem(imat::bwd_imat_kernel<T, false>, imat::kSmemBwd, "cudaFuncSetAttribute(bwd_imat_kernel)"))) return rc;
+        imat::bwd_imat_kernel<T, false><<<grid, 32 * imat::kWarps, imat::kSmemBwd, st>>>(in, off, mask, gout, acc, goff, gmask, q, tiles_x, tiles_y, GQ);
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------ forward
 template <typename T>
 int forward_t(const void *in_, const void *off_, const void *mask_, void *out_, const Geo &q,
@@ -176,6 +236,11 @@ int forward_t(const void *in_, const void *off_, const void *mask_, void *out_, 
     T *out = (T *)out_;
     const size_t n_pix = (size_t)q.N * q.Ho * q.Wo;
     if (n_pix == 0) return 0;
+    if constexpr (sizeof(T) == 2) {
+        const int fam = family_knob("DCNV3_B200_FWD");
+        if (fam == 3 && imat_eligible<T>(q, {in_, out_}, off_))
+            return launch_fwd_imat<T>(in, off, mask, out, q, logits, st);
+    }
     const Plan pl = plan_vec<T>(q, n_pix, logits, {in_, out_}, off_, sizeof(T));
     if constexpr (sizeof(T) <= 4) {
         if (pl.vec) {
@@ -343,6 +408,13 @@ int backward_t(const void *in_, const void *off_, const void *mask_, const void 
             if constexpr (lowp) {
                 if (plan_tile<T>(q, logits, in_, gout_, off_, acc, tc)) {
                     rc = launch_tile<T>(in, off, mask, gout, acc, goff, gmask, q, logits, tc, st);
+                    tiled = true;
+                }
+            }
+            if constexpr (lowp) {
+                if (!tiled && family_knob("DCNV3_B200_BWD") == 3 && imat_eligible<T>(q, {in_, gout_, ws}, off_) &&
+                    !(reinterpret_cast<uintptr_t>(goff_) & 3u)) {
+                    rc = launch_bwd_imat<T>(in, off, mask, gout, acc, goff, gmask, q, logits, st);
                     tiled = true;
                 }
             }

@@ -1,0 +1,727 @@
+// dcnv3_b200 — "interpolation-matrix" kernels (16-bit storage, group_channels = 16, 3x3 s1 d1).
+//
+// The vector kernels (dcnv3_kernels.cuh) spend one lane-instruction stream per 16-byte channel
+// vector and point: the forward is instruction-issue bound and the backward is bound by the
+// SM -> L2 reduction port.  This family removes the per-channel work from the
+// SIMT lanes altogether:
+//
+//   * a CTA owns an 8x8 tile of output pixels of one image and 4 groups (64 channels); the
+//     16x16-cell input window the tile can reach with |offset| < 3 px is staged ONCE in shared
+//     memory (cp.async, zero-filled outside the image: that IS the reference's per-corner
+//     validity, dcnv3_im2col_cuda.cuh:57-75);
+//   * one warp per group; one LANE per (pixel, group).  The lane turns its 9 sampling points into
+//     a row of a sparse interpolation matrix  Wm[pixel][cell] += w_corner * mask  (4 scalar
+//     shared-memory updates per point, private to the lane: no atomics);
+//   * out[pixel][ch] = sum_cell Wm[pixel][cell] * X[cell][ch] is then a dense [16 x 144] x
+//     [144 x 16] product per 4x4 sub-tile on the tensor cores (mma.sync m16n8k8, TF32 weights,
+//     the 16-bit activations are exact in TF32, fp32 accumulation).
+//
+// Location arithmetic is the shared locate() (bit-exact integer contract).  A point whose corners
+// leave the sub-tile's 12x12 sub-window (|offset*scale| >= 3 px) takes a per-lane slow path that
+// gathers from global memory exactly like the generic kernel, so any offset is handled.
+//
+// Reference semantics: dcnv3_im2col_gpu_kernel :216-275 + dcnv3_im2col_bilinear :32-80.
+#pragma once
+
+#include "dcnv3_kernels.cuh"
+
+namespace dcnv3 {
+namespace imat {
+
+constexpr int kTile = 8;                 // output pixels per tile edge
+constexpr int kWin = 16;                 // window cells per edge (tile + 2*4)
+constexpr int kSub = 12;                 // sub-window cells per edge (4x4 sub-tile + 2*4)
+constexpr int kCells = kSub * kSub;      // 144 = K of the product
+constexpr int kKSteps = kCells / 16;     // 9
+constexpr int kRow = 152;                // words per Wm row (144 + pad; 152 % 32 == 24: LDS.64 conflict-free)
+constexpr int kWarps = 4;                // groups per CTA
+constexpr int kWinBytes = kWin * kWin * 128;       // 64 channels x 2 B per cell
+constexpr int kWmWords = 32 * kRow;                // one Wm buffer: 32 pixels
+constexpr int kSmemFwd = kWinBytes + kWarps * kWmWords * 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+// D += A(16x8, tf32) * B(8x8, tf32), fp32 accumulate
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// two packed 16-bit storage values -> fp32 bit patterns (exact; both are valid TF32 operands)
+template <typename T> __device__ __forceinline__ void unpack2(uint32_t w, uint32_t &lo, uint32_t &hi);
+template <> __device__ __forceinline__ void unpack2<__nv_bfloat16>(uint32_t w, uint32_t &lo, uint32_t &hi) {
+    lo = w << 16; hi = w & 0xffff0000u;
+}
+template <> __device__ __forceinline__ void unpack2<__half>(uint32_t w, uint32_t &lo, uint32_t &hi) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w));
+    lo = __float_as_uint(f.x); hi = __float_as_uint(f.y);
+}
+template <typename T> __device__ __forceinline__ float2 unpack2f(uint32_t w) {
+    uint32_t lo, hi;
+    unpack2<T>(w, lo, hi);
+    return make_float2(__uint_as_float(lo), __uint_as_float(hi));
+}
+template <typename T> __device__ __forceinline__ float half_to_float(unsigned short h);
+template <> __device__ __forceinline__ float half_to_float<__nv_bfloat16>(unsigned short h) {
+    return __uint_as_float((uint32_t)h << 16);
+}
+template <> __device__ __forceinline__ float half_to_float<__half>(unsigned short h) {
+    return __half2float(__ushort_as_half(h));
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+// 16-byte chunk swizzle of the window: chunk' = chunk ^ key(cell); 8 consecutive cells of a
+// sub-window row (also across its 12-cell wrap into the next row) get 8 distinct keys.
+__device__ __forceinline__ int win_key(int cell) { return ((cell & 15) + 4 * (cell >> 4)) & 7; }
+
+struct TileCoord { int n, ty, tx, gq; };
+__device__ __forceinline__ TileCoord decode_tile(unsigned b, int tiles_x, int tiles_y, int GQ) {
+    TileCoord c;
+    c.gq = (int)(b % (unsigned)GQ); b /= (unsigned)GQ;
+    c.tx = (int)(b % (unsigned)tiles_x); b /= (unsigned)tiles_x;
+    c.ty = (int)(b % (unsigned)tiles_y);
+    c.n = (int)(b / (unsigned)tiles_y);
+    return c;
+}
+
+// Stage the 16x16-cell x 64-channel input window of (tile, group quad); zero outside the image.
+// 128 threads: thread = (column, 16-byte chunk), one window row per iteration.
+template <typename T>
+__device__ __forceinline__ void fill_window(unsigned char *win, const T *in, const T *img, const Geo &q,
+                                            int wy0, int wx0, int tid) {
+    const uint32_t ws = smem_u32(win);
+    const int ch = tid & 7, col = tid >> 3;
+    const int ix = wx0 + col;
+    const bool col_ok = (unsigned)ix < (unsigned)q.W;
+    const long long row_stride = (long long)q.W * q.C;
+    const T *p = img + ((long long)wy0 * q.W + ix) * q.C + ch * 8;
+#pragma unroll
+    for (int i = 0; i < kWin; ++i) {
+        const bool ok = col_ok && (unsigned)(wy0 + i) < (unsigned)q.H;
+        const T *src = ok ? p + i * row_stride : in;
+        cp_async16(ws + (i * kWin + col) * 128 + ((ch ^ ((col + 4 * i) & 7)) << 4), src, ok ? 16 : 0);
+    }
+}
+
+// Pixel of the build phase: lane -> (sub-tile column sx, position in the 4x4 sub-tile).
+struct PixCoord { int oy, ox; bool valid; };
+__device__ __forceinline__ PixCoord pix_of(int px, int ty, int tx, int pass, const Geo &q) {
+    const int m = px & 15;
+    PixCoord c;
+    c.oy = ty * kTile + pass * 4 + (m >> 2);
+    c.ox = tx * kTile + (px >> 4) * 4 + (m & 3);
+    c.valid = c.oy < q.Ho && c.ox < q.Wo;
+    return c;
+}
+
+// Byte offset (inside the window) of the ldmatrix row this lane addresses in k-step ks, for
+// sub-tile column 0: matrix jm = lane >> 3 covers cells 16ks + 8(jm >> 1) + (lane & 7) and
+// 16-byte chunk 2*group + (jm & 1).  Sub-tile column s: (off ^ (s << 6)) + s * 512.
+__device__ __forceinline__ int b_row_offset(int ks, int lane, int group_in_quad) {
+    const int jm = lane >> 3, jr = lane & 7;
+    const int kk = 16 * ks + 8 * (jm >> 1) + jr;
+    const int rr = kk / kSub, cc = kk - rr * kSub;
+    const int chunk = 2 * group_in_quad + (jm & 1);
+    return (rr * kWin + cc) * 128 + ((chunk ^ ((cc + 4 * rr) & 7)) << 4);
+}
+
+// One out-of-window sampling point of the forward: gather from global memory (generic semantics).
+template <typename T>
+__device__ __forceinline__ void slow_point_fwd(const T *img_g, const Geo &q, const Point<float> &t, float m,
+                                               float (&v)[16]) {
+    const float hm = t.hh * m, lm = t.lh * m;
+    const float w[4] = {hm * t.hw, hm * t.lw, lm * t.hw, lm * t.lw};
+    const bool ok[4] = {t.ok1, t.ok2, t.ok3, t.ok4};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!ok[k]) continue;
+        const T *p = img_g + ((size_t)(t.h_low + (k >> 1)) * q.W + (t.w_low + (k & 1))) * q.C;
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(p));
+        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
+        const uint32_t wd[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float2 f = unpack2f<T>(wd[e]);
+            v[2 * e] = fmaf(w[k], f.x, v[2 * e]);
+            v[2 * e + 1] = fmaf(w[k], f.y, v[2 * e + 1]);
+        }
+    }
+}
+
+// Offsets / mask of one pass (32 pixels x 9 points of group g), coalesced: word wi = i*32 + lane of
+// the pass belongs to pixel wi / 9, point wi % 9 (pixel order = lane order of the build phase).
+// `off32` / `msk16` point at the image's first pixel; indices inside one image fit 32 bits.
+struct PassIO {
+    int idx[9];  // element index (pixel * G*9 + g*9 + point) or -1 outside the map
+};
+__device__ __forceinline__ void pass_indices(PassIO &io, int lane, int ty, int tx, int pass, int g, const Geo &q) {
+    const int GP = q.G * 9;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const int wi = i * 32 + lane;
+        const int px = wi / 9, w = wi - px * 9;
+        const PixCoord c = pix_of(px, ty, tx, pass, q);
+        io.idx[i] = c.valid ? (c.oy * q.Wo + c.ox) * GP + g * 9 + w : -1;
+    }
+}
+
+// Words 0..287 of the staging area live in Wm rows 0 and 1 (144 words each, the 8-word row pads are
+// left alone: the backward keeps grad_output there), the 288 16-bit values in row 2.
+__device__ __forceinline__ int stage_word(int wi) { return wi < kCells ? wi : wi + (kRow - kCells); }
+constexpr int kStage16 = 2 * kRow * 2;  // index of the first 16-bit slot (row 2), in 16-bit units
+
+template <typename T, bool LOGITS>
+__device__ __forceinline__ void softmax9(float (&m)[9]) {
+    if (!LOGITS) return;
+    float mx = m[0];
+#pragma unroll
+    for (int p = 1; p < 9; ++p) mx = fmaxf(mx, m[p]);
+    float sum = 0.f;
+#pragma unroll
+    for (int p = 0; p < 9; ++p) { m[p] = expf(m[p] - mx); sum += m[p]; }
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int p = 0; p < 9; ++p) m[p] *= inv;
+}
+
+// ===========================================================================
+// forward
+// ===========================================================================
+template <typename T, bool LOGITS>
+__global__ void __launch_bounds__(32 * kWarps, 2)
+fwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
+                T *__restrict__ out, const Geo q, const int tiles_x, const int tiles_y, const int GQ) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const TileCoord tc = decode_tile(blockIdx.x, tiles_x, tiles_y, GQ);
+    const int g = tc.gq * kWarps + warp;
+    const int wy0 = tc.ty * kTile + (q.half_h - q.ph) - 4;  // input row of window cell (0, 0)
+    const int wx0 = tc.tx * kTile + (q.half_w - q.pw) - 4;
+    const T *img = in + (size_t)tc.n * q.H * q.W * q.C + tc.gq * 64;
+    const T *img_g = img + warp * 16;
+
+    fill_window<T>(smem, in, img, q, wy0, wx0, tid);
+
+    const size_t pix0 = (size_t)tc.n * q.Ho * q.Wo * q.G * 9;
+    const uint32_t *off32 = reinterpret_cast<const uint32_t *>(off) + pix0;
+    const unsigned short *msk16 = reinterpret_cast<const unsigned short *>(mask) + pix0;
+    uint32_t roff[2][9];
+    unsigned short rmsk[2][9];
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        PassIO io;
+        pass_indices(io, lane, tc.ty, tc.tx, pass, g, q);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            roff[pass][i] = io.idx[i] >= 0 ? __ldg(off32 + io.idx[i]) : 0u;
+            rmsk[pass][i] = io.idx[i] >= 0 ? __ldg(msk16 + io.idx[i]) : (unsigned short)0;
+        }
+    }
+    cp_async_commit_wait();
+    __syncthreads();
+
+    float *Wm = reinterpret_cast<float *>(smem + kWinBytes) + warp * kWmWords;
+    const uint32_t win_s = smem_u32(smem);
+    const int gID = lane >> 2, tq = lane & 3;
+    int boff[kKSteps];
+#pragma unroll
+    for (int ks = 0; ks < kKSteps; ++ks) boff[ks] = b_row_offset(ks, lane, warp);
+
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        // ---- this lane's 9 offset pairs and mask values (through the Wm buffer)
+        uint32_t *st32 = reinterpret_cast<uint32_t *>(Wm);
+        unsigned short *st16 = reinterpret_cast<unsigned short *>(Wm) + kStage16;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            st32[stage_word(i * 32 + lane)] = roff[pass][i];
+            st16[i * 32 + lane] = rmsk[pass][i];
+        }
+        __syncwarp();
+        uint32_t myoff[9];
+        float mym[9];
+#pragma unroll
+        for (int p = 0; p < 9; ++p) {
+            myoff[p] = st32[stage_word(lane * 9 + p)];
+            mym[p] = half_to_float<T>(st16[lane * 9 + p]);
+        }
+        __syncwarp();
+        {
+            float4 *W4 = reinterpret_cast<float4 *>(Wm);
+#pragma unroll 2
+            for (int i = 0; i < kWmWords / 4 / 32; ++i) W4[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
+
+        // ---- build: lane = pixel; Wm[lane][cell] += corner weight * mask
+        const int sx = lane >> 4;
+        const PixCoord pc = pix_of(lane, tc.ty, tc.tx, pass, q);
+        const int sy0 = wy0 + 4 * pass, sx0 = wx0 + 4 * sx;  // input coords of sub-window cell (0, 0)
+        float p0h_, p0w_;
+        window_origin<float>(q, pc.oy, pc.ox, p0h_, p0w_);
+        softmax9<T, LOGITS>(mym);
+        unsigned slow = 0u;
+        float *Wrow = Wm + lane * kRow;
+        if (pc.valid) {
+#pragma unroll
+            for (int p = 0; p < 9; ++p) {
+                const float2 o = unpack2f<T>(myoff[p]);
+                Point<float> t;
+                locate<float>(q, p0h_, p0w_, p / 3, p % 3, o.x, o.y, t);
+                if (t.inside) {
+                    const unsigned u = (unsigned)(t.w_low - sx0), v = (unsigned)(t.h_low - sy0);
+                    if (u <= (unsigned)(kSub - 2) && v <= (unsigned)(kSub - 2)) {
+                        const float hm = t.hh * mym[p], lm = t.lh * mym[p];
+                        float *c = Wrow + v * kSub + u;
+                        c[0] += hm * t.hw;
+                        c[1] += hm * t.lw;
+                        c[kSub] += lm * t.hw;
+                        c[kSub + 1] += lm * t.lw;
+                    } else {
+                        slow |= 1u << p;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- product: two 4x4 sub-tiles (Wm rows 0-15 / 16-31), 9 k-steps of 16 cells
+        float acc[2][2][4];
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[s][nt][e] = 0.f;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const float *A0 = Wm + (16 * s + gID) * kRow + 2 * tq;
+            const float *A1 = A0 + 8 * kRow;
+            const uint32_t wbase = win_s + pass * (4 * kWin * 128) + s * 512;
+#pragma unroll
+            for (int ks = 0; ks < kKSteps; ++ks) {
+                uint32_t r0, r1, r2, r3;
+                ldmatrix_x4_trans(r0, r1, r2, r3, wbase + (boff[ks] ^ (s << 6)));
+                const float2 a00 = *reinterpret_cast<const float2 *>(A0 + 16 * ks);
+                const float2 a10 = *reinterpret_cast<const float2 *>(A1 + 16 * ks);
+                const float2 a01 = *reinterpret_cast<const float2 *>(A0 + 16 * ks + 8);
+                const float2 a11 = *reinterpret_cast<const float2 *>(A1 + 16 * ks + 8);
+                uint32_t b0, b1;
+                unpack2<T>(r0, b0, b1);
+                mma_tf32(acc[s][0], __float_as_uint(a00.x), __float_as_uint(a10.x), __float_as_uint(a00.y), __float_as_uint(a10.y), b0, b1);
+                unpack2<T>(r1, b0, b1);
+                mma_tf32(acc[s][1], __float_as_uint(a00.x), __float_as_uint(a10.x), __float_as_uint(a00.y), __float_as_uint(a10.y), b0, b1);
+                unpack2<T>(r2, b0, b1);
+                mma_tf32(acc[s][0], __float_as_uint(a01.x), __float_as_uint(a11.x), __float_as_uint(a01.y), __float_as_uint(a11.y), b0, b1);
+                unpack2<T>(r3, b0, b1);
+                mma_tf32(acc[s][1], __float_as_uint(a01.x), __float_as_uint(a11.x), __float_as_uint(a01.y), __float_as_uint(a11.y), b0, b1);
+            }
+        }
+        __syncwarp();
+
+        // ---- epilogue: fragments -> per-pixel rows (stride 20 words), slow points, 32-byte store
+        float *S = Wm;
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                *reinterpret_cast<float2 *>(S + (16 * s + gID) * 20 + nt * 8 + 2 * tq) = make_float2(acc[s][nt][0], acc[s][nt][1]);
+                *reinterpret_cast<float2 *>(S + (16 * s + gID + 8) * 20 + nt * 8 + 2 * tq) = make_float2(acc[s][nt][2], acc[s][nt][3]);
+            }
+        __syncwarp();
+        if (pc.valid) {
+            float v[16];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float4 f = *reinterpret_cast<const float4 *>(S + lane * 20 + 4 * e);
+                v[4 * e] = f.x; v[4 * e + 1] = f.y; v[4 * e + 2] = f.z; v[4 * e + 3] = f.w;
+            }
+            if (slow) {
+#pragma unroll 1
+                for (int p = 0; p < 9; ++p) {
+                    if (!(slow & (1u << p))) continue;
+                    uint32_t ow = myoff[0];
+                    float mm = mym[0];
+#pragma unroll
+                    for (int e = 1; e < 9; ++e) if (e == p) { ow = myoff[e]; mm = mym[e]; }
+                    const float2 o = unpack2f<T>(ow);
+                    Point<float> t;
+                    locate<float>(q, p0h_, p0w_, p / 3, p % 3, o.x, o.y, t);
+                    slow_point_fwd<T>(img_g, q, t, mm, v);
+                }
+            }
+            uint4 lo, hi;
+            lo.x = pack2<T>(v[0], v[1]); lo.y = pack2<T>(v[2], v[3]); lo.z = pack2<T>(v[4], v[5]); lo.w = pack2<T>(v[6], v[7]);
+            hi.x = pack2<T>(v[8], v[9]); hi.y = pack2<T>(v[10], v[11]); hi.z = pack2<T>(v[12], v[13]); hi.w = pack2<T>(v[14], v[15]);
+            uint4 *dst = reinterpret_cast<uint4 *>(out + (((size_t)tc.n * q.Ho + pc.oy) * q.Wo + pc.ox) * q.C + g * 16);
+            dst[0] = lo;
+            dst[1] = hi;
+        }
+        __syncwarp();
+    }
+}
+
+// ===========================================================================
+// backward (16-bit storage, fp32 accumulation of grad_input into `gacc` [N,H,W,C], pre-zeroed)
+//
+// Per pass (32 pixels of one group = two 4x4 sub-tiles), all in the warp's private Wm buffer:
+//   1. D[pixel][cell] = sum_ch go[pixel][ch] * X[cell][ch]          tensor cores  (mma #1)
+//   2. lane = pixel: for its 9 points read the four corner dots d_k from D ->
+//        grad_mask   = sum_k w_k d_k                                   (cuh:144)
+//        grad_offset = scale*m*(hh(d2-d1)+lh(d4-d3), hw(d3-d1)+lw(d4-d2))   (cuh:114-139,145-146)
+//      staged and written coalesced;
+//   3. Wm[pixel][cell] += w_k * m  (the forward's interpolation matrix)
+//   4. GW[cell][ch] += sum_pixel Wm[pixel][cell] * go[pixel][ch]      tensor cores  (mma #2),
+//      accumulated in registers over the four sub-tiles of the tile (16 window rows x 16 ch);
+// then the CTA's GW window (256 cells x 64 channels fp32) goes to `gacc` as 256-byte-contiguous
+// vector reductions: ~4 reduction bytes per grad_input byte instead of the vector kernel's 36.
+// grad_output of a pixel (32 bytes) lives in the 8-word pad of its Wm row.
+// ===========================================================================
+constexpr int kSmemBwd = kSmemFwd;
+
+// One out-of-window sampling point of the backward: corner dots from global memory, grad_input
+// contributions as 64-byte vector reductions (same as the vector kernel).
+template <typename T>
+__device__ __forceinline__ void slow_point_bwd(const T *img_g, float *gacc_g, const Geo &q, const Point<float> &t,
+                                               float m, const float (&go)[16], float (&d)[4]) {
+    const float w[4] = {t.hh * t.hw, t.hh * t.lw, t.lh * t.hw, t.lh * t.lw};
+    const bool ok[4] = {t.ok1, t.ok2, t.ok3, t.ok4};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        d[k] = 0.f;
+        if (!ok[k]) continue;
+        const size_t e = ((size_t)(t.h_low + (k >> 1)) * q.W + (t.w_low + (k & 1))) * q.C;
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(img_g + e));
+        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(img_g + e) + 1);
+        const uint32_t wd[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float2 f = unpack2f<T>(wd[c]);
+            acc = fmaf(go[2 * c], f.x, acc);
+            acc = fmaf(go[2 * c + 1], f.y, acc);
+        }
+        d[k] = acc;
+        const float wm = w[k] * m;
+        float *dst = gacc_g + e;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            red_add_v4_f32(dst + 4 * c, wm * go[4 * c], wm * go[4 * c + 1], wm * go[4 * c + 2], wm * go[4 * c + 3]);
+    }
+}
+
+template <typename T, bool LOGITS>
+__global__ void __launch_bounds__(32 * kWarps, 2)
+bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
+                const T *__restrict__ gout, float *__restrict__ gacc, T *__restrict__ goff,
+                T *__restrict__ gmask, const Geo q, const int tiles_x, const int tiles_y, const int GQ) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const TileCoord tc = decode_tile(blockIdx.x, tiles_x, tiles_y, GQ);
+    const int g = tc.gq * kWarps + warp;
+    const int wy0 = tc.ty * kTile + (q.half_h - q.ph) - 4;
+    const int wx0 = tc.tx * kTile + (q.half_w - q.pw) - 4;
+    const size_t img_off = (size_t)tc.n * q.H * q.W * q.C + tc.gq * 64;
+    const T *img = in + img_off;
+    const T *img_g = img + warp * 16;
+    float *gacc_g = gacc + img_off + warp * 16;
+
+    fill_window<T>(smem, in, img, q, wy0, wx0, tid);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    const size_t pix0 = (size_t)tc.n * q.Ho * q.Wo * q.G * 9;
+    const uint32_t *off32 = reinterpret_cast<const uint32_t *>(off) + pix0;
+    const unsigned short *msk16 = reinterpret_cast<const unsigned short *>(mask) + pix0;
+    uint32_t *goff32 = reinterpret_cast<uint32_t *>(goff) + pix0;
+    unsigned short *gmsk16 = reinterpret_cast<unsigned short *>(gmask) + pix0;
+
+    float *Wm = reinterpret_cast<float *>(smem + kWinBytes) + warp * kWmWords;
+    const uint32_t wm_s = smem_u32(Wm);
+    const uint32_t win_s = smem_u32(smem);
+    const int gID = lane >> 2, tq = lane & 3;
+    const int jm = lane >> 3, jr = lane & 7;
+    int boff[kKSteps];
+#pragma unroll
+    for (int ks = 0; ks < kKSteps; ++ks) boff[ks] = b_row_offset(ks, lane, warp);
+
+    // grad_input window of this (tile, group): 16 rows x (16 cells x 16 channels) as mma accumulators
+    float gw[kWin][2][4];
+#pragma unroll
+    for (int r = 0; r < kWin; ++r)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) gw[r][nt][e] = 0.f;
+
+    bool window_ready = false;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const PixCoord pc = pix_of(lane, tc.ty, tc.tx, pass, q);
+        // ---- loads of the pass: offsets / mask (coalesced, staged) and this pixel's grad_output
+        PassIO io;
+        pass_indices(io, lane, tc.ty, tc.tx, pass, g, q);
+        uint32_t *st32 = reinterpret_cast<uint32_t *>(Wm);
+        unsigned short *st16 = reinterpret_cast<unsigned short *>(Wm) + kStage16;
+        uint4 go_lo = make_uint4(0u, 0u, 0u, 0u), go_hi = go_lo;
+        {
+            uint32_t ro[9];
+            unsigned short rm[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                ro[i] = io.idx[i] >= 0 ? __ldg(off32 + io.idx[i]) : 0u;
+                rm[i] = io.idx[i] >= 0 ? __ldg(msk16 + io.idx[i]) : (unsigned short)0;
+            }
+            if (pc.valid) {
+                const uint4 *gp = reinterpret_cast<const uint4 *>(gout + (((size_t)tc.n * q.Ho + pc.oy) * q.Wo + pc.ox) * q.C + g * 16);
+                go_lo = __ldg(gp);
+                go_hi = __ldg(gp + 1);
+            }
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                st32[stage_word(i * 32 + lane)] = ro[i];
+                st16[i * 32 + lane] = rm[i];
+            }
+        }
+        __syncwarp();
+        uint32_t myoff[9];
+        float mym[9];
+#pragma unroll
+        for (int p = 0; p < 9; ++p) {
+            myoff[p] = st32[stage_word(lane * 9 + p)];
+            mym[p] = half_to_float<T>(st16[lane * 9 + p]);
+        }
+        // grad_output slab of this pixel into the pad of its row (rows' pads are outside the stage)
+        *reinterpret_cast<uint4 *>(Wm + lane * kRow + kCells) = go_lo;
+        *reinterpret_cast<uint4 *>(Wm + lane * kRow + kCells + 4) = go_hi;
+        softmax9<T, LOGITS>(mym);
+        if (!window_ready) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            window_ready = true;
+        } else {
+            __syncwarp();
+        }
+
+        // ---- mma #1: D[pixel][cell] for both sub-tiles
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            uint32_t a[2][4];
+            {
+                uint32_t r0, r1, r2, r3;  // (px 0-7, ch 0-7) (px 8-15, ch 0-7) (px 0-7, ch 8-15) (px 8-15, ch 8-15)
+                ldmatrix_x4(r0, r1, r2, r3, wm_s + ((16 * s + 8 * (jm & 1) + jr) * kRow + kCells) * 4 + (jm >> 1) * 16);
+                unpack2<T>(r0, a[0][0], a[0][2]);
+                unpack2<T>(r1, a[0][1], a[0][3]);
+                unpack2<T>(r2, a[1][0], a[1][2]);
+                unpack2<T>(r3, a[1][1], a[1][3]);
+            }
+            const uint32_t wbase = win_s + pass * (4 * kWin * 128) + s * 512;
+            float *D0 = Wm + (16 * s + gID) * kRow + 2 * tq;
+            float *D1 = D0 + 8 * kRow;
+#pragma unroll
+            for (int ks = 0; ks < kKSteps; ++ks) {
+                uint32_t r0, r1, r2, r3;  // (cells 0-7, ch 0-7) (cells 0-7, ch 8-15) (cells 8-15, ch 0-7) (cells 8-15, ch 8-15)
+                ldmatrix_x4(r0, r1, r2, r3, wbase + (boff[ks] ^ (s << 6)));
+                float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+                uint32_t b0, b1;
+                unpack2<T>(r0, b0, b1);
+                mma_tf32(d0, a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
+                unpack2<T>(r1, b0, b1);
+                mma_tf32(d0, a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
+                unpack2<T>(r2, b0, b1);
+                mma_tf32(d1, a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
+                unpack2<T>(r3, b0, b1);
+                mma_tf32(d1, a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
+                *reinterpret_cast<float2 *>(D0 + 16 * ks) = make_float2(d0[0], d0[1]);
+                *reinterpret_cast<float2 *>(D1 + 16 * ks) = make_float2(d0[2], d0[3]);
+                *reinterpret_cast<float2 *>(D0 + 16 * ks + 8) = make_float2(d1[0], d1[1]);
+                *reinterpret_cast<float2 *>(D1 + 16 * ks + 8) = make_float2(d1[2], d1[3]);
+            }
+        }
+        __syncwarp();
+
+        // ---- pass A: lane = pixel; grad_offset / grad_mask from the corner dots
+        const int sx = lane >> 4;
+        const int sy0 = wy0 + 4 * pass, sx0 = wx0 + 4 * sx;
+        float p0h_, p0w_;
+        window_origin<float>(q, pc.oy, pc.ox, p0h_, p0w_);
+        const float *Drow = Wm + lane * kRow;
+        uint32_t res_off[9];
+        float res_m[9];
+        unsigned fast = 0u;
+#pragma unroll
+        for (int p = 0; p < 9; ++p) {
+            res_off[p] = 0u;
+            res_m[p] = 0.f;
+            if (!pc.valid) continue;
+            const float2 o = unpack2f<T>(myoff[p]);
+            Point<float> t;
+            locate<float>(q, p0h_, p0w_, p / 3, p % 3, o.x, o.y, t);
+            if (!t.inside) continue;
+            const unsigned u = (unsigned)(t.w_low - sx0), v = (unsigned)(t.h_low - sy0);
+            float d[4];
+            if (u <= (unsigned)(kSub - 2) && v <= (unsigned)(kSub - 2)) {
+                const float *c = Drow + v * kSub + u;
+                d[0] = c[0]; d[1] = c[1]; d[2] = c[kSub]; d[3] = c[kSub + 1];
+                fast |= 1u << p;
+            } else {
+                float go[16];
+                const uint4 ga = *reinterpret_cast<const uint4 *>(Drow + kCells);
+                const uint4 gb = *reinterpret_cast<const uint4 *>(Drow + kCells + 4);
+                const uint32_t gwd[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float2 f = unpack2f<T>(gwd[c]);
+                    go[2 * c] = f.x; go[2 * c + 1] = f.y;
+                }
+                slow_point_bwd<T>(img_g, gacc_g, q, t, mym[p], go, d);
+            }
+            const float w1 = t.hh * t.hw, w2 = t.hh * t.lw, w3 = t.lh * t.hw, w4 = t.lh * t.lw;
+            const float s_m = w1 * d[0] + w2 * d[1] + w3 * d[2] + w4 * d[3];
+            const float s_w = t.hh * (d[1] - d[0]) + t.lh * (d[3] - d[2]);
+            const float s_h = t.hw * (d[2] - d[0]) + t.lw * (d[3] - d[1]);
+            const float sm = q.scale * mym[p];
+            res_off[p] = pack2<T>(sm * s_w, sm * s_h);
+            res_m[p] = s_m;
+        }
+        if (LOGITS) {  // softmax Jacobian: dl_p = m_p (gm_p - sum_q m_q gm_q)
+            float dot = 0.f;
+#pragma unroll
+            for (int p = 0; p < 9; ++p) dot = fmaf(mym[p], res_m[p], dot);
+#pragma unroll
+            for (int p = 0; p < 9; ++p) res_m[p] = mym[p] * (res_m[p] - dot);
+        }
+        __syncwarp();  // every lane is done with D
+#pragma unroll
+        for (int p = 0; p < 9; ++p) {
+            st32[stage_word(lane * 9 + p)] = res_off[p];
+            st16[lane * 9 + p] = (unsigned short)(pack2<T>(res_m[p], 0.f) & 0xffffu);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            if (io.idx[i] >= 0) {
+                goff32[io.idx[i]] = st32[stage_word(i * 32 + lane)];
+                gmsk16[io.idx[i]] = st16[i * 32 + lane];
+            }
+        }
+        __syncwarp();
+
+        // ---- pass B: Wm[pixel][cell] += corner weight * mask (rows' pads keep grad_output)
+        {
+            float4 *W4 = reinterpret_cast<float4 *>(Wm);
+#pragma unroll 4
+            for (int i = 0; i < 36; ++i) {
+                const int id = i * 32 + lane, row = id / 36, c4 = id - row * 36;
+                W4[row * (kRow / 4) + c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        __syncwarp();
+        {
+            float *Wrow = Wm + lane * kRow;
+#pragma unroll
+            for (int p = 0; p < 9; ++p) {
+                if (!(fast & (1u << p))) continue;
+                const float2 o = unpack2f<T>(myoff[p]);
+                Point<float> t;
+                locate<float>(q, p0h_, p0w_, p / 3, p % 3, o.x, o.y, t);
+                const unsigned u = (unsigned)(t.w_low - sx0), v = (unsigned)(t.h_low - sy0);
+                const float hm = t.hh * mym[p], lm = t.lh * mym[p];
+                float *c = Wrow + v * kSub + u;
+                c[0] += hm * t.hw;
+                c[1] += hm * t.lw;
+                c[kSub] += lm * t.hw;
+                c[kSub + 1] += lm * t.lw;
+            }
+        }
+        __syncwarp();
+
+        // ---- mma #2: gw[window row][ch] += Wm^T * go, per sub-tile; m-tile = one window row
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            uint32_t b[2][2][2];  // [k8 step][n-tile][2]
+            {
+                uint32_t r0, r1, r2, r3;  // matrix jm = (k8 step jm >> 1, n-tile jm & 1); row jr <-> pixel (jr >> 1) + 4 (jr & 1)
+                ldmatrix_x4_trans(r0, r1, r2, r3,
+                                  wm_s + ((16 * s + 8 * (jm >> 1) + (jr >> 1) + 4 * (jr & 1)) * kRow + kCells) * 4 + (jm & 1) * 16);
+                unpack2<T>(r0, b[0][0][0], b[0][0][1]);
+                unpack2<T>(r1, b[0][1][0], b[0][1][1]);
+                unpack2<T>(r2, b[1][0][0], b[1][0][1]);
+                unpack2<T>(r3, b[1][1][0], b[1][1][1]);
+            }
+            // A(cell col, pixel): a0/a2 use window column gID, a1/a3 column gID + 8; the sub-window
+            // spans columns 4s .. 4s+11
+            const bool lo_ok = (s == 1) ? (gID >= 4) : true;
+            const bool hi_ok = (s == 0) ? (gID <= 3) : true;
+            const int c_lo = lo_ok ? gID - 4 * s : 0, c_hi = hi_ok ? gID + 8 - 4 * s : 0;
+#pragma unroll
+            for (int k8 = 0; k8 < 2; ++k8) {
+                const float *Wp = Wm + (16 * s + 8 * k8 + tq) * kRow;
+#pragma unroll
+                for (int rr = 0; rr < kSub; ++rr) {
+                    float a0 = Wp[rr * kSub + c_lo], a1 = Wp[rr * kSub + c_hi];
+                    float a2 = Wp[4 * kRow + rr * kSub + c_lo], a3 = Wp[4 * kRow + rr * kSub + c_hi];
+                    if (!lo_ok) { a0 = 0.f; a2 = 0.f; }
+                    if (!hi_ok) { a1 = 0.f; a3 = 0.f; }
+                    mma_tf32(gw[4 * pass + rr][0], __float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(a3), b[k8][0][0], b[k8][0][1]);
+                    mma_tf32(gw[4 * pass + rr][1], __float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(a3), b[k8][1][0], b[k8][1][1]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- flush: the four warps' windows side by side (256 B per cell), 16-byte chunks swizzled by
+    // 2*(column & 7), then 256-byte-contiguous vector reductions into gacc
+    __syncthreads();
+    float *GW = reinterpret_cast<float *>(smem + kWinBytes);
+#pragma unroll
+    for (int r = 0; r < kWin; ++r)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            const int chunk = warp * 4 + nt * 2 + (tq >> 1);
+            const int c0 = r * kWin + gID, c1 = c0 + 8;  // same (column & 7) -> same key
+            const int sw = ((chunk ^ (2 * (gID & 7))) << 2) + 2 * (tq & 1);
+            *reinterpret_cast<float2 *>(GW + c0 * 64 + sw) = make_float2(gw[r][nt][0], gw[r][nt][1]);
+            *reinterpret_cast<float2 *>(GW + c1 * 64 + sw) = make_float2(gw[r][nt][2], gw[r][nt][3]);
+        }
+    __syncthreads();
+    float *gacc_q = gacc + img_off;
+#pragma unroll 4
+    for (int i = 0; i < kWin * kWin * 16 / (32 * kWarps); ++i) {
+        const int id = i * (32 * kWarps) + tid;
+        const int cell = id >> 4, j = id & 15;
+        const int iy = wy0 + (cell >> 4), ix = wx0 + (cell & 15);
+        const float4 v = *reinterpret_cast<const float4 *>(GW + cell * 64 + ((j ^ (2 * (cell & 7))) << 2));
+        const bool ok = (unsigned)iy < (unsigned)q.H && (unsigned)ix < (unsigned)q.W &&
+                        (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f);
+        red_add_v4_f32(gacc_q + ((size_t)(ok ? iy : 0) * q.W + (ok ? ix : 0)) * q.C + 4 * j, v.x, v.y, v.z, v.w, ok);
+    }
+}
+
+}  // namespace imat
+}  // namespace dcnv3
