@@ -1,7 +1,7 @@
 """Quick GPU check of the interpolation-matrix kernel family against the vector family and the
 CPU pixel oracle (test infrastructure), plus CUDA-event timings at the BASELINE sites.
 
-    python tools/imat_check.py [fwd] [bwd] [time]
+    python tools/imat_check.py [parity] [bwd] [time]
 """
 import os
 import sys
@@ -140,7 +140,7 @@ if __name__ == "__main__":
     a = sys.argv[1:]
     do_bwd = "bwd" in a
     rc = 0
-    if "fwd" in a or do_bwd:
+    if "parity" in a:
         rc = parity(do_bwd)
     if "time" in a:
         timing(do_bwd)

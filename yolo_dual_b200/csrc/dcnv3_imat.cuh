@@ -402,37 +402,84 @@ fwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
 // vector reductions: ~4 reduction bytes per grad_input byte instead of the vector kernel's 36.
 // grad_output of a pixel (32 bytes) lives in the 8-word pad of its Wm row.
 // ===========================================================================
-constexpr int kSmemBwd = kSmemFwd;
+constexpr int kSmemBwd = kSmemFwd + 16;  // + one 16-byte zero word (operand of masked mma #2 lanes)
 
-// One out-of-window sampling point of the backward: corner dots from global memory, grad_input
-// contributions as 64-byte vector reductions (same as the vector kernel).
+// The point loops of the backward are calls into these two non-inlined functions: the kernel is
+// otherwise ~190 KB of straight-line SASS and stalls on instruction fetch (ncu: no_instruction 2.0
+// per issue with 8 warps per SM).  dilation is 1 in this family, so locate() only needs these.
+struct PtGeo { int H, W; float scale; };
+__device__ __forceinline__ Geo geo_of(const PtGeo &g) {
+    Geo q{};
+    q.H = g.H; q.W = g.W; q.scale = g.scale; q.dh = 1; q.dw = 1;
+    return q;
+}
+struct PtResA { uint32_t off; float m; uint32_t kq; uint32_t frac; };  // kq: cell | 256 when in-window; frac: (lh, lw) as 16-bit fixed point
+
+// pass A of one point: corner dots (from D, or from global memory when the point leaves the
+// sub-window; then its grad_input contributions go out right here as 64-byte vector reductions)
 template <typename T>
-__device__ __forceinline__ void slow_point_bwd(const T *img_g, float *gacc_g, const Geo &q, const Point<float> &t,
-                                               float m, const float (&go)[16], float (&d)[4]) {
-    const float w[4] = {t.hh * t.hw, t.hh * t.lw, t.lh * t.hw, t.lh * t.lw};
-    const bool ok[4] = {t.ok1, t.ok2, t.ok3, t.ok4};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        d[k] = 0.f;
-        if (!ok[k]) continue;
-        const size_t e = ((size_t)(t.h_low + (k >> 1)) * q.W + (t.w_low + (k & 1))) * q.C;
-        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(img_g + e));
-        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(img_g + e) + 1);
-        const uint32_t wd[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        float acc = 0.f;
+__device__ __noinline__ PtResA bwd_point_a(const PtGeo pg, const float p0h_, const float p0w_, const int p,
+                                           const uint32_t offw, const float m, const float *Drow,
+                                           const int sy0, const int sx0, const T *img_g, float *gacc_g,
+                                           const int C) {
+    PtResA r{0u, 0.f, 0u, 0u};
+    const Geo q = geo_of(pg);
+    const int i = p / 3, j = p - 3 * i;
+    const float2 o = unpack2f<T>(offw);
+    Point<float> t;
+    locate<float>(q, p0h_, p0w_, i, j, o.x, o.y, t);
+    if (!t.inside) return r;
+    const unsigned u = (unsigned)(t.w_low - sx0), v = (unsigned)(t.h_low - sy0);
+    float d[4];
+    if (u <= (unsigned)(kSub - 2) && v <= (unsigned)(kSub - 2)) {
+        const float *c = Drow + v * kSub + u;
+        d[0] = c[0]; d[1] = c[1]; d[2] = c[kSub]; d[3] = c[kSub + 1];
+        r.kq = 256u | (v * kSub + u);
+        // fractions for pass B, truncated to 2^-16 (the weights there feed TF32 operands anyway)
+        r.frac = (__float2uint_rz(t.lh * 65536.f) << 16) | __float2uint_rz(t.lw * 65536.f);
+    } else {
+        float go[16];
+        const uint4 ga = *reinterpret_cast<const uint4 *>(Drow + kCells);
+        const uint4 gb = *reinterpret_cast<const uint4 *>(Drow + kCells + 4);
+        const uint32_t gwd[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const float2 f = unpack2f<T>(wd[c]);
-            acc = fmaf(go[2 * c], f.x, acc);
-            acc = fmaf(go[2 * c + 1], f.y, acc);
+            const float2 f = unpack2f<T>(gwd[c]);
+            go[2 * c] = f.x; go[2 * c + 1] = f.y;
         }
-        d[k] = acc;
-        const float wm = w[k] * m;
-        float *dst = gacc_g + e;
+        const float w[4] = {t.hh * t.hw, t.hh * t.lw, t.lh * t.hw, t.lh * t.lw};
+        const bool ok[4] = {t.ok1, t.ok2, t.ok3, t.ok4};
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            d[k] = 0.f;
+            if (!ok[k]) continue;
+            const size_t e = ((size_t)(t.h_low + (k >> 1)) * q.W + (t.w_low + (k & 1))) * C;
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(img_g + e));
+            const uint4 b = __ldg(reinterpret_cast<const uint4 *>(img_g + e) + 1);
+            const uint32_t wd[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            float acc = 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-            red_add_v4_f32(dst + 4 * c, wm * go[4 * c], wm * go[4 * c + 1], wm * go[4 * c + 2], wm * go[4 * c + 3]);
+            for (int c = 0; c < 8; ++c) {
+                const float2 f = unpack2f<T>(wd[c]);
+                acc = fmaf(go[2 * c], f.x, acc);
+                acc = fmaf(go[2 * c + 1], f.y, acc);
+            }
+            d[k] = acc;
+            const float wm = w[k] * m;
+            float *dst = gacc_g + e;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                red_add_v4_f32(dst + 4 * c, wm * go[4 * c], wm * go[4 * c + 1], wm * go[4 * c + 2], wm * go[4 * c + 3]);
+        }
     }
+    const float w1 = t.hh * t.hw, w2 = t.hh * t.lw, w3 = t.lh * t.hw, w4 = t.lh * t.lw;
+    const float s_m = w1 * d[0] + w2 * d[1] + w3 * d[2] + w4 * d[3];
+    const float s_w = t.hh * (d[1] - d[0]) + t.lh * (d[3] - d[2]);
+    const float s_h = t.hw * (d[2] - d[0]) + t.lw * (d[3] - d[1]);
+    const float sm = q.scale * m;
+    r.off = pack2<T>(sm * s_w, sm * s_h);
+    r.m = s_m;
+    return r;
 }
 
 template <typename T, bool LOGITS>
@@ -450,6 +497,7 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
     const T *img = in + img_off;
     const T *img_g = img + warp * 16;
     float *gacc_g = gacc + img_off + warp * 16;
+    const PtGeo pg{q.H, q.W, q.scale};
 
     fill_window<T>(smem, in, img, q, wy0, wx0, tid);
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -465,9 +513,6 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
     const uint32_t win_s = smem_u32(smem);
     const int gID = lane >> 2, tq = lane & 3;
     const int jm = lane >> 3, jr = lane & 7;
-    int boff[kKSteps];
-#pragma unroll
-    for (int ks = 0; ks < kKSteps; ++ks) boff[ks] = b_row_offset(ks, lane, warp);
 
     // grad_input window of this (tile, group): 16 rows x (16 cells x 16 channels) as mma accumulators
     float gw[kWin][2][4];
@@ -478,17 +523,40 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
 #pragma unroll
             for (int e = 0; e < 4; ++e) gw[r][nt][e] = 0.f;
 
+    // element indices of this lane's 9 staging words in pass 0; pass 1 is 4 rows further down
+    PassIO io;
+    unsigned io1 = 0u;  // validity of the same words in pass 1
+    const int pass_stride = 4 * q.Wo * q.G * 9;
+    {
+        const int GP = q.G * 9;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const int wi = i * 32 + lane;
+            const int px = wi / 9, w = wi - px * 9;
+            const PixCoord c = pix_of(px, tc.ty, tc.tx, 0, q);
+            io.idx[i] = c.valid ? (c.oy * q.Wo + c.ox) * GP + g * 9 + w : -1;
+            io1 |= (c.oy + 4 < q.Ho && c.ox < q.Wo ? 1u : 0u) << i;
+        }
+    }
+    float *zero16 = reinterpret_cast<float *>(smem + kSmemFwd);
+    if (tid < 4) zero16[tid] = 0.f;
+
     bool window_ready = false;
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
         const PixCoord pc = pix_of(lane, tc.ty, tc.tx, pass, q);
+        if (pass == 1) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                // (a word valid in pass 1 is valid in pass 0: same column, higher row)
+                io.idx[i] = ((io1 >> i) & 1u) ? io.idx[i] + pass_stride : -1;
+            }
+        }
         // ---- loads of the pass: offsets / mask (coalesced, staged) and this pixel's grad_output
-        PassIO io;
-        pass_indices(io, lane, tc.ty, tc.tx, pass, g, q);
         uint32_t *st32 = reinterpret_cast<uint32_t *>(Wm);
         unsigned short *st16 = reinterpret_cast<unsigned short *>(Wm) + kStage16;
-        uint4 go_lo = make_uint4(0u, 0u, 0u, 0u), go_hi = go_lo;
         {
+            uint4 go_lo = make_uint4(0u, 0u, 0u, 0u), go_hi = go_lo;
             uint32_t ro[9];
             unsigned short rm[9];
 #pragma unroll
@@ -506,6 +574,9 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
                 st32[stage_word(i * 32 + lane)] = ro[i];
                 st16[i * 32 + lane] = rm[i];
             }
+            // grad_output slab of this pixel into the pad of its row (outside the staging words)
+            *reinterpret_cast<uint4 *>(Wm + lane * kRow + kCells) = go_lo;
+            *reinterpret_cast<uint4 *>(Wm + lane * kRow + kCells + 4) = go_hi;
         }
         __syncwarp();
         uint32_t myoff[9];
@@ -515,9 +586,6 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
             myoff[p] = st32[stage_word(lane * 9 + p)];
             mym[p] = half_to_float<T>(st16[lane * 9 + p]);
         }
-        // grad_output slab of this pixel into the pad of its row (rows' pads are outside the stage)
-        *reinterpret_cast<uint4 *>(Wm + lane * kRow + kCells) = go_lo;
-        *reinterpret_cast<uint4 *>(Wm + lane * kRow + kCells + 4) = go_hi;
         softmax9<T, LOGITS>(mym);
         if (!window_ready) {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -527,8 +595,8 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
             __syncwarp();
         }
 
-        // ---- mma #1: D[pixel][cell] for both sub-tiles
-#pragma unroll
+        // ---- mma #1: D[pixel][cell] for both sub-tiles (rolled: 2 x 9 iterations)
+#pragma unroll 1
         for (int s = 0; s < 2; ++s) {
             uint32_t a[2][4];
             {
@@ -541,72 +609,63 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
             }
             const uint32_t wbase = win_s + pass * (4 * kWin * 128) + s * 512;
             float *D0 = Wm + (16 * s + gID) * kRow + 2 * tq;
-            float *D1 = D0 + 8 * kRow;
+            // B rows: cell 16ks + 8(jm>>1) + jr of the sub-window.  Three k-steps are exactly four
+            // sub-window rows, so the offsets of ks = 3m + r are those of ks = r plus m*4 window rows
+            // (and the swizzle key does not change).
+            const int chunk = (2 * warp + (jm & 1)) ^ (4 * s);
+            uint32_t bo[3];
 #pragma unroll
-            for (int ks = 0; ks < kKSteps; ++ks) {
-                uint32_t r0, r1, r2, r3;  // (cells 0-7, ch 0-7) (cells 0-7, ch 8-15) (cells 8-15, ch 0-7) (cells 8-15, ch 8-15)
-                ldmatrix_x4(r0, r1, r2, r3, wbase + (boff[ks] ^ (s << 6)));
-                float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
-                uint32_t b0, b1;
-                unpack2<T>(r0, b0, b1);
-                mma_tf32(d0, a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
-                unpack2<T>(r1, b0, b1);
-                mma_tf32(d0, a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
-                unpack2<T>(r2, b0, b1);
-                mma_tf32(d1, a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
-                unpack2<T>(r3, b0, b1);
-                mma_tf32(d1, a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
-                *reinterpret_cast<float2 *>(D0 + 16 * ks) = make_float2(d0[0], d0[1]);
-                *reinterpret_cast<float2 *>(D1 + 16 * ks) = make_float2(d0[2], d0[3]);
-                *reinterpret_cast<float2 *>(D0 + 16 * ks + 8) = make_float2(d1[0], d1[1]);
-                *reinterpret_cast<float2 *>(D1 + 16 * ks + 8) = make_float2(d1[2], d1[3]);
+            for (int r = 0; r < 3; ++r) {
+                const int kk = 16 * r + 8 * (jm >> 1) + jr;
+                const int rr = kk / kSub, cc = kk - rr * kSub;
+                bo[r] = wbase + (rr * kWin + cc) * 128 + ((chunk ^ ((cc + 4 * rr) & 7)) << 4);
+            }
+#pragma unroll 1
+            for (int m = 0; m < 3; ++m) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    uint32_t r0, r1, r2, r3;  // (cells 0-7, ch 0-7) (cells 0-7, ch 8-15) (cells 8-15, ch 0-7) (cells 8-15, ch 8-15)
+                    ldmatrix_x4(r0, r1, r2, r3, bo[r] + m * (4 * kWin * 128));
+                    float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+                    uint32_t b0, b1;
+                    unpack2<T>(r0, b0, b1);
+                    mma_tf32(d0, a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
+                    unpack2<T>(r1, b0, b1);
+                    mma_tf32(d0, a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
+                    unpack2<T>(r2, b0, b1);
+                    mma_tf32(d1, a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
+                    unpack2<T>(r3, b0, b1);
+                    mma_tf32(d1, a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
+                    float *Dk = D0 + 48 * m + 16 * r;
+                    *reinterpret_cast<float2 *>(Dk) = make_float2(d0[0], d0[1]);
+                    *reinterpret_cast<float2 *>(Dk + 8 * kRow) = make_float2(d0[2], d0[3]);
+                    *reinterpret_cast<float2 *>(Dk + 8) = make_float2(d1[0], d1[1]);
+                    *reinterpret_cast<float2 *>(Dk + 8 * kRow + 8) = make_float2(d1[2], d1[3]);
+                }
             }
         }
         __syncwarp();
 
         // ---- pass A: lane = pixel; grad_offset / grad_mask from the corner dots
-        const int sx = lane >> 4;
-        const int sy0 = wy0 + 4 * pass, sx0 = wx0 + 4 * sx;
+        const int sy0 = wy0 + 4 * pass, sx0 = wx0 + 4 * (lane >> 4);
         float p0h_, p0w_;
         window_origin<float>(q, pc.oy, pc.ox, p0h_, p0w_);
-        const float *Drow = Wm + lane * kRow;
-        uint32_t res_off[9];
+        float *Wrow = Wm + lane * kRow;
+        uint32_t res_off[9], frac[9];
         float res_m[9];
-        unsigned fast = 0u;
+        uint32_t kq[3] = {0u, 0u, 0u};  // 9 x (cell | in-window bit), 10 bits each
 #pragma unroll
         for (int p = 0; p < 9; ++p) {
             res_off[p] = 0u;
             res_m[p] = 0.f;
-            if (!pc.valid) continue;
-            const float2 o = unpack2f<T>(myoff[p]);
-            Point<float> t;
-            locate<float>(q, p0h_, p0w_, p / 3, p % 3, o.x, o.y, t);
-            if (!t.inside) continue;
-            const unsigned u = (unsigned)(t.w_low - sx0), v = (unsigned)(t.h_low - sy0);
-            float d[4];
-            if (u <= (unsigned)(kSub - 2) && v <= (unsigned)(kSub - 2)) {
-                const float *c = Drow + v * kSub + u;
-                d[0] = c[0]; d[1] = c[1]; d[2] = c[kSub]; d[3] = c[kSub + 1];
-                fast |= 1u << p;
-            } else {
-                float go[16];
-                const uint4 ga = *reinterpret_cast<const uint4 *>(Drow + kCells);
-                const uint4 gb = *reinterpret_cast<const uint4 *>(Drow + kCells + 4);
-                const uint32_t gwd[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float2 f = unpack2f<T>(gwd[c]);
-                    go[2 * c] = f.x; go[2 * c + 1] = f.y;
-                }
-                slow_point_bwd<T>(img_g, gacc_g, q, t, mym[p], go, d);
+            frac[p] = 0u;
+            if (pc.valid) {
+                const PtResA r = bwd_point_a<T>(pg, p0h_, p0w_, p, myoff[p], mym[p], Wrow, sy0, sx0, img_g, gacc_g, q.C);
+                res_off[p] = r.off;
+                res_m[p] = r.m;
+                frac[p] = r.frac;
+                kq[p / 3] |= r.kq << (10 * (p % 3));
             }
-            const float w1 = t.hh * t.hw, w2 = t.hh * t.lw, w3 = t.lh * t.hw, w4 = t.lh * t.lw;
-            const float s_m = w1 * d[0] + w2 * d[1] + w3 * d[2] + w4 * d[3];
-            const float s_w = t.hh * (d[1] - d[0]) + t.lh * (d[3] - d[2]);
-            const float s_h = t.hw * (d[2] - d[0]) + t.lw * (d[3] - d[1]);
-            const float sm = q.scale * mym[p];
-            res_off[p] = pack2<T>(sm * s_w, sm * s_h);
-            res_m[p] = s_m;
         }
         if (LOGITS) {  // softmax Jacobian: dl_p = m_p (gm_p - sum_q m_q gm_q)
             float dot = 0.f;
@@ -632,36 +691,32 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
         __syncwarp();
 
         // ---- pass B: Wm[pixel][cell] += corner weight * mask (rows' pads keep grad_output)
-        {
+        {   // zero words 0..143 of the 32 rows: 32 float4 of a row per instruction, then the last 4
             float4 *W4 = reinterpret_cast<float4 *>(Wm);
-#pragma unroll 4
-            for (int i = 0; i < 36; ++i) {
-                const int id = i * 32 + lane, row = id / 36, c4 = id - row * 36;
-                W4[row * (kRow / 4) + c4] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < 32; ++r) W4[r * (kRow / 4) + lane] = z;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) W4[(8 * r + (lane >> 2)) * (kRow / 4) + 32 + (lane & 3)] = z;
         }
         __syncwarp();
-        {
-            float *Wrow = Wm + lane * kRow;
 #pragma unroll
-            for (int p = 0; p < 9; ++p) {
-                if (!(fast & (1u << p))) continue;
-                const float2 o = unpack2f<T>(myoff[p]);
-                Point<float> t;
-                locate<float>(q, p0h_, p0w_, p / 3, p % 3, o.x, o.y, t);
-                const unsigned u = (unsigned)(t.w_low - sx0), v = (unsigned)(t.h_low - sy0);
-                const float hm = t.hh * mym[p], lm = t.lh * mym[p];
-                float *c = Wrow + v * kSub + u;
-                c[0] += hm * t.hw;
-                c[1] += hm * t.lw;
-                c[kSub] += lm * t.hw;
-                c[kSub + 1] += lm * t.lw;
+        for (int p = 0; p < 9; ++p) {
+            const uint32_t e = kq[p / 3] >> (10 * (p % 3));
+            if (e & 256u) {
+                const float lh = (float)(frac[p] >> 16) * (1.f / 65536.f), lw = (float)(frac[p] & 0xffffu) * (1.f / 65536.f);
+                const float hm = (1.f - lh) * mym[p], lm = lh * mym[p], hw = 1.f - lw;
+                float *c = Wrow + (e & 255u);
+                c[0] += hm * hw;
+                c[1] += hm * lw;
+                c[kSub] += lm * hw;
+                c[kSub + 1] += lm * lw;
             }
         }
         __syncwarp();
 
         // ---- mma #2: gw[window row][ch] += Wm^T * go, per sub-tile; m-tile = one window row
-#pragma unroll
+#pragma unroll 1
         for (int s = 0; s < 2; ++s) {
             uint32_t b[2][2][2];  // [k8 step][n-tile][2]
             {
@@ -677,16 +732,18 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
             // spans columns 4s .. 4s+11
             const bool lo_ok = (s == 1) ? (gID >= 4) : true;
             const bool hi_ok = (s == 0) ? (gID <= 3) : true;
-            const int c_lo = lo_ok ? gID - 4 * s : 0, c_hi = hi_ok ? gID + 8 - 4 * s : 0;
 #pragma unroll
             for (int k8 = 0; k8 < 2; ++k8) {
+                // masked lanes read the shared zero word (stride 0): no selects in the loop
                 const float *Wp = Wm + (16 * s + 8 * k8 + tq) * kRow;
+                const float *Plo = lo_ok ? Wp + gID - 4 * s : zero16;
+                const float *Phi = hi_ok ? Wp + gID + 8 - 4 * s : zero16;
+                const int st_lo = lo_ok ? kSub : 0, st_hi = hi_ok ? kSub : 0;
+                const int up_lo = lo_ok ? 4 * kRow : 0, up_hi = hi_ok ? 4 * kRow : 0;
 #pragma unroll
                 for (int rr = 0; rr < kSub; ++rr) {
-                    float a0 = Wp[rr * kSub + c_lo], a1 = Wp[rr * kSub + c_hi];
-                    float a2 = Wp[4 * kRow + rr * kSub + c_lo], a3 = Wp[4 * kRow + rr * kSub + c_hi];
-                    if (!lo_ok) { a0 = 0.f; a2 = 0.f; }
-                    if (!hi_ok) { a1 = 0.f; a3 = 0.f; }
+                    const float a0 = Plo[rr * st_lo], a1 = Phi[rr * st_hi];
+                    const float a2 = Plo[rr * st_lo + up_lo], a3 = Phi[rr * st_hi + up_hi];
                     mma_tf32(gw[4 * pass + rr][0], __float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(a3), b[k8][0][0], b[k8][0][1]);
                     mma_tf32(gw[4 * pass + rr][1], __float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(a3), b[k8][1][0], b[k8][1][1]);
                 }
@@ -710,16 +767,24 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
             *reinterpret_cast<float2 *>(GW + c1 * 64 + sw) = make_float2(gw[r][nt][2], gw[r][nt][3]);
         }
     __syncthreads();
-    float *gacc_q = gacc + img_off;
+    {   // thread = (16-byte chunk j of the 256-byte cell row, cell tid >> 4 of every 8)
+        const int j = tid & 15, c8 = tid >> 4;
+        const int ix0 = wx0 + c8, ix1 = ix0 + 8;
+        const bool ok0 = (unsigned)ix0 < (unsigned)q.W, ok1 = (unsigned)ix1 < (unsigned)q.W;
+        const long long row_stride = (long long)q.W * q.C;
+        float *dst0 = gacc + img_off + ((long long)wy0 * q.W + ix0) * q.C + 4 * j;
+        const float *src = GW + c8 * 64 + ((j ^ (2 * (c8 & 7))) << 2);  // (cell & 7) == c8 for both halves
 #pragma unroll 4
-    for (int i = 0; i < kWin * kWin * 16 / (32 * kWarps); ++i) {
-        const int id = i * (32 * kWarps) + tid;
-        const int cell = id >> 4, j = id & 15;
-        const int iy = wy0 + (cell >> 4), ix = wx0 + (cell & 15);
-        const float4 v = *reinterpret_cast<const float4 *>(GW + cell * 64 + ((j ^ (2 * (cell & 7))) << 2));
-        const bool ok = (unsigned)iy < (unsigned)q.H && (unsigned)ix < (unsigned)q.W &&
-                        (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f);
-        red_add_v4_f32(gacc_q + ((size_t)(ok ? iy : 0) * q.W + (ok ? ix : 0)) * q.C + 4 * j, v.x, v.y, v.z, v.w, ok);
+        for (int r = 0; r < kWin; ++r) {
+            const bool row_ok = (unsigned)(wy0 + r) < (unsigned)q.H;
+            const float4 v0 = *reinterpret_cast<const float4 *>(src + r * (kWin * 64));
+            const float4 v1 = *reinterpret_cast<const float4 *>(src + r * (kWin * 64) + 8 * 64);
+            const bool nz0 = ((__float_as_uint(v0.x) | __float_as_uint(v0.y) | __float_as_uint(v0.z) | __float_as_uint(v0.w)) << 1) != 0u;
+            const bool nz1 = ((__float_as_uint(v1.x) | __float_as_uint(v1.y) | __float_as_uint(v1.z) | __float_as_uint(v1.w)) << 1) != 0u;
+            float *d = dst0 + r * row_stride;
+            red_add_v4_f32(row_ok && ok0 ? d : gacc, v0.x, v0.y, v0.z, v0.w, row_ok && ok0 && nz0);
+            red_add_v4_f32(row_ok && ok1 ? d + 8 * q.C : gacc, v1.x, v1.y, v1.z, v1.w, row_ok && ok1 && nz1);
+        }
     }
 }
 
