@@ -541,7 +541,8 @@ def main():
         t["frac_of_hbm"] = t["GBps"] / peak
         table[nm] = t
     dom = max(table, key=lambda k: table[k]["us_mean"])
-    roofline = {"bound": "hbm", "kernel": dom + (" (memset + bwd_vec_kernel + cast_ws_kernel)" if dom.startswith("bwd") and e == 2 and a.grad_accum == "opmath" else ""),
+    roofline = {"bound": "hbm", "kernel": dom + ((" (memset + " + ("bwd_vec_kernel" if os.environ.get("DCNV3_B200_BWD") == "vec" else "bwd_imat_kernel") +
+                                         " + cast_ws_kernel)") if dom.startswith("bwd") and e == 2 and a.grad_accum == "opmath" else ""),
                 "achieved": table[dom]["GBps"], "peak": peak, "unit": "GB/s", "frac": table[dom]["GBps"] / peak,
                 "peak_source": peak_src, "traffic": ncu_traffic(dom),
                 "step_frac": value / world / peak}

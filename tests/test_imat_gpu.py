@@ -1,0 +1,122 @@
+"""GPU parity of the interpolation-matrix kernel family (csrc/dcnv3_imat.cuh) through the C-ABI.
+
+The family is the default backward for 16-bit storage with group_channels = 16, 3x3 / stride 1 /
+dilation 1 (the C3-DCN shapes); its forward is opt-in (DCNV3_B200_FWD=imat).  Checked against the CPU
+pixel oracle (test infrastructure) on shapes that exercise: whole and partial 8x8 tiles, maps smaller
+than one tile, pad 0, offset_scale != 1, G = 4 ... 32, offsets far outside the staged window (the
+per-lane global-memory path: the reference test's own `rand*10` distribution), fused softmax.
+
+Tolerance: bf16/fp16 rtol 1e-2, atol 2e-3 after scaling by max|ref| (north_star).  The products run on
+the tensor cores with TF32 interpolation weights (2^-11 relative) and exact 16-bit activations, fp32
+accumulation; grad_input additionally sums per-tile partial windows with fp32 reductions.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+CASES = {
+    "cfg1_G4": ((2, 80, 80, 4, 16), dict()),
+    "partial_tiles_G8": ((2, 21, 19, 8, 16), dict()),
+    "pad0": ((1, 12, 12, 4, 16), dict(pad=0)),
+    "scale1.5": ((1, 17, 23, 4, 16), dict(scale=1.5)),
+    "smaller_than_a_tile": ((1, 3, 5, 4, 16), dict()),
+    "P5_like_G32": ((1, 20, 20, 32, 16), dict()),
+    "pad2": ((1, 10, 14, 4, 16), dict(pad=2)),
+}
+
+
+def _run(fn, x, off, m, go, args, dtype):
+    xs, os_, ms = (t.to(DEV, dtype).contiguous().requires_grad_(True) for t in (x, off, m))
+    out = fn.apply(xs, os_, ms, *args, 256)
+    out.backward(go.to(DEV, dtype))
+    torch.cuda.synchronize()
+    return [t.float().cpu() for t in (out.detach(), xs.grad, os_.grad, ms.grad)]
+
+
+def _close(got, want, what, rtol=1e-2, atol=2e-3):
+    scale = max(1.0, float(want.abs().max()))
+    torch.testing.assert_close(got.double() / scale, want.double() / scale, rtol=rtol, atol=atol,
+                               msg=lambda s: f"{what}: {s}")
+
+
+@pytest.mark.parametrize("fwd", ["vec", "imat"])
+@pytest.mark.parametrize("dist", ["unit", "ref"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("case", list(CASES))
+def test_imat_vs_pixel_oracle(case, dtype, dist, fwd, pixel_oracle, monkeypatch):
+    from oracle.dcnv3_oracle import make_inputs
+    from yolo_dual_b200.ops_dcnv3.functions import DCNv3Function
+    monkeypatch.setenv("DCNV3_B200_FWD", fwd)
+    monkeypatch.setenv("DCNV3_B200_BWD", "imat")
+    (N, H, W, G, gc), kw = CASES[case]
+    pad, scale = kw.get("pad", 1), kw.get("scale", 1.0)
+    args = (3, 3, 1, 1, pad, pad, 1, 1, G, gc, scale)
+    x, off, m, go = make_inputs(N, H, W, G, gc, 3, 3, 1, 1, pad, pad, 1, 1, dist=dist, seed=5)
+    xr, offr, mr, gor = (t.to(dtype).float() for t in (x, off, m, go))
+    want = [pixel_oracle.forward(xr, offr, mr, *args)] + list(pixel_oracle.backward(xr, offr, mr, gor, *args))
+    got = _run(DCNv3Function, x, off, m, go, args, dtype)
+    for g_, w_, name in zip(got, want, ("output", "grad_input", "grad_offset", "grad_mask")):
+        _close(g_, w_, name)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+def test_imat_matches_vector_family(dtype, monkeypatch):
+    """Same inputs through both families (P3-like, 2 images): they must agree to storage rounding."""
+    from oracle.dcnv3_oracle import make_inputs
+    from yolo_dual_b200.ops_dcnv3.functions import DCNv3Function
+    N, H, W, G, gc = 2, 80, 80, 8, 16
+    args = (3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0)
+    x, off, m, go = make_inputs(N, H, W, G, gc, dist="unit", seed=11)
+    res = {}
+    for fam in ("vec", "imat"):
+        monkeypatch.setenv("DCNV3_B200_FWD", fam)
+        monkeypatch.setenv("DCNV3_B200_BWD", fam)
+        res[fam] = _run(DCNv3Function, x, off, m, go, args, dtype)
+    eps = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -10
+    for a, b, name in zip(res["imat"], res["vec"], ("output", "grad_input", "grad_offset", "grad_mask")):
+        _close(a, b, name, rtol=2 * eps, atol=2 * eps)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+def test_imat_fused_softmax(dtype, pixel_oracle, monkeypatch):
+    from oracle.dcnv3_oracle import make_inputs
+    from yolo_dual_b200.ops_dcnv3.functions import DCNv3SoftmaxFunction
+    monkeypatch.setenv("DCNV3_B200_FWD", "imat")
+    monkeypatch.setenv("DCNV3_B200_BWD", "imat")
+    N, H, W, G, gc = 2, 21, 19, 8, 16
+    P = 9
+    args = (3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0)
+    x, off, _, go = make_inputs(N, H, W, G, gc, dist="unit", seed=4)
+    logits = torch.randn(N, H, W, G * P, generator=torch.Generator().manual_seed(8)) * 2
+    xr, offr, lr, gor = (t.to(dtype).float() for t in (x, off, logits, go))
+    prob = torch.softmax(lr.view(N, H, W, G, P), -1)
+    pm = prob.reshape(N, H, W, G * P).contiguous()
+    want_out = pixel_oracle.forward(xr, offr, pm, *args)
+    want_gi, want_go, gm = pixel_oracle.backward(xr, offr, pm, gor, *args)
+    gmv = gm.view(N, H, W, G, P)
+    want_gl = (prob * (gmv - (prob * gmv).sum(-1, keepdim=True))).reshape(N, H, W, G * P)
+    got = _run(DCNv3SoftmaxFunction, x, off, logits, go, args, dtype)
+    for g_, w_, name in zip(got, (want_out, want_gi, want_go, want_gl), ("output", "grad_input", "grad_offset", "grad_logits")):
+        _close(g_, w_, name)
+
+
+def test_imat_is_the_default_backward_and_adjoint_holds(monkeypatch):
+    """At a BASELINE site (P4, bf16) with no knobs set: <go, f(x)> = <grad_input, x> (the op is linear
+    in the input), which only holds if the tiled reductions neither drop nor double-count a cell."""
+    from oracle.dcnv3_oracle import make_inputs
+    from yolo_dual_b200.ops_dcnv3.functions import DCNv3Function
+    monkeypatch.delenv("DCNV3_B200_FWD", raising=False)
+    monkeypatch.delenv("DCNV3_B200_BWD", raising=False)
+    N, H, W, G, gc = 4, 40, 40, 16, 16
+    args = (3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0)
+    x, off, m, go = make_inputs(N, H, W, G, gc, dist="unit", seed=3)
+    out, gi, _, gm = _run(DCNv3Function, x, off, m, go, args, torch.bfloat16)
+    xb, gob, mb = (t.to(torch.bfloat16).double() for t in (x, go, m))
+    lhs = float((gob * out.double()).sum())
+    rhs = float((gi.double() * xb).sum())
+    assert abs(lhs - rhs) <= 2e-3 * max(abs(lhs), abs(rhs), float(N * H * W)), (lhs, rhs)
+    rhs_m = float((gm.double() * mb).sum())  # and <grad_mask, mask> = <go, f>
+    assert abs(lhs - rhs_m) <= 2e-3 * max(abs(lhs), abs(rhs_m), float(N * H * W)), (lhs, rhs_m)

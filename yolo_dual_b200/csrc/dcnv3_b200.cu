@@ -170,7 +170,9 @@ Plan plan_vec(const Geo &q, size_t n_pix, bool logits, std::initializer_list<con
 unsigned blocks_for(size_t threads) { return (unsigned)((threads + kThreads - 1) / kThreads); }
 
 // ---------------------------------------------- interpolation-matrix family
-// Knobs: DCNV3_B200_FWD / DCNV3_B200_BWD = vec | imat force a family (default: imat when eligible).
+// Knobs: DCNV3_B200_FWD / DCNV3_B200_BWD = vec | imat force a family.  Defaults: the backward takes the
+// interpolation-matrix kernel when eligible (16-bit, gc = 16, 3x3 s1 d1, fp32 accumulation), the forward the
+// vector kernel (its imat variant is correct but slower: profiles/r01_imat.md).
 int family_knob(const char *name) {  // 0 default, 1 vec, 2 tile, 3 imat
     const char *e = getenv(name);
     if (!e) return 0;
@@ -412,7 +414,8 @@ int backward_t(const void *in_, const void *off_, const void *mask_, const void 
                 }
             }
             if constexpr (lowp) {
-                if (!tiled && family_knob("DCNV3_B200_BWD") == 3 && imat_eligible<T>(q, {in_, gout_, ws}, off_) &&
+                const int fam = family_knob("DCNV3_B200_BWD");  // default: imat when eligible
+                if (!tiled && (fam == 0 || fam == 3) && imat_eligible<T>(q, {in_, gout_, ws}, off_) &&
                     !(reinterpret_cast<uintptr_t>(goff_) & 3u)) {
                     rc = launch_bwd_imat<T>(in, off, mask, gout, acc, goff, gmask, q, logits, st);
                     tiled = true;

@@ -544,7 +544,9 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
     bool window_ready = false;
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
+        if (tc.ty * kTile + 4 * pass >= q.Ho) break;  // the tile's lower half lies below the map (warp-uniform)
         const PixCoord pc = pix_of(lane, tc.ty, tc.tx, pass, q);
+        const int n_sub = (tc.tx * kTile + 4 < q.Wo) ? 2 : 1;  // right sub-tile column outside the map?
         if (pass == 1) {
 #pragma unroll
             for (int i = 0; i < 9; ++i) {
@@ -597,7 +599,7 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
 
         // ---- mma #1: D[pixel][cell] for both sub-tiles (rolled: 2 x 9 iterations)
 #pragma unroll 1
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < n_sub; ++s) {
             uint32_t a[2][4];
             {
                 uint32_t r0, r1, r2, r3;  // (px 0-7, ch 0-7) (px 8-15, ch 0-7) (px 0-7, ch 8-15) (px 8-15, ch 8-15)
@@ -717,7 +719,7 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
 
         // ---- mma #2: gw[window row][ch] += Wm^T * go, per sub-tile; m-tile = one window row
 #pragma unroll 1
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < n_sub; ++s) {
             uint32_t b[2][2][2];  // [k8 step][n-tile][2]
             {
                 uint32_t r0, r1, r2, r3;  // matrix jm = (k8 step jm >> 1, n-tile jm & 1); row jr <-> pixel (jr >> 1) + 4 (jr & 1)
