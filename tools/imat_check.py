@@ -16,6 +16,8 @@ from oracle.dcnv3_oracle import PixelOracle, make_inputs  # noqa: E402
 from yolo_dual_b200.ops_dcnv3.functions import DCNv3Function, DCNv3SoftmaxFunction  # noqa: E402
 
 DEV = "cuda:0"
+DIST = os.environ.get("IMAT_DIST", "unit")
+OFFSCALE = float(os.environ.get("IMAT_OFFSCALE", "1.0"))
 
 
 def run(fn, x, off, m, go, args, dtype, env):
@@ -101,7 +103,9 @@ def timing(do_bwd):
         geo = _lib.Geometry(N, H, W, 3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0)
         sets = []
         for s in range(4):
-            x, off, m, go = make_inputs(N, H, W, G, gc, dist="unit", seed=s)
+            x, off, m, go = make_inputs(N, H, W, G, gc, dist=DIST, seed=s)
+            if OFFSCALE != 1.0:
+                off = off * OFFSCALE
             sets.append([t.to(DEV, torch.bfloat16).contiguous() for t in (x, off, m, go)])
         out = torch.empty_like(sets[0][0])
         gi, goff, gm = (torch.empty_like(sets[0][k]) for k in (0, 1, 2))

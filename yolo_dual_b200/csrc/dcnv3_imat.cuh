@@ -415,68 +415,104 @@ __device__ __forceinline__ Geo geo_of(const PtGeo &g) {
 }
 struct PtResA { uint32_t off; float m; uint32_t kq; uint32_t frac; };  // kq: cell | 256 when in-window; frac: (lh, lw) as 16-bit fixed point
 
-// pass A of one point: corner dots (from D, or from global memory when the point leaves the
-// sub-window; then its grad_input contributions go out right here as 64-byte vector reductions)
+// Location of one point with the arithmetic of locate() (same operations in the same order, so the
+// same h_low / w_low / fractions bit for bit) but without the per-corner validity flags: inside the
+// staged window the zero fill plays that role.  dilation is 1: (float)(i * dw) == fi.
+struct LeanPoint { int h_low, w_low; float lh, lw; bool inside; };
+__device__ __forceinline__ LeanPoint locate_lean(const PtGeo &g, float p0h_, float p0w_, float fi, float fj,
+                                                 float off_w, float off_h) {
+    LeanPoint t;
+    const float loc_w = add_rn(p0w_, mul_rn(add_rn(fi, off_w), g.scale));
+    const float loc_h = add_rn(p0h_, mul_rn(add_rn(fj, off_h), g.scale));
+    t.inside = loc_h > -1.f && loc_w > -1.f && loc_h < (float)g.H && loc_w < (float)g.W;
+    t.h_low = floor_to_int(loc_h);
+    t.w_low = floor_to_int(loc_w);
+    t.lh = sub_rn(loc_h, (float)t.h_low);
+    t.lw = sub_rn(loc_w, (float)t.w_low);
+    return t;
+}
+
+// Out-of-window point of pass A: corner dots from global memory; its grad_input contributions go out
+// right here as 64-byte vector reductions (the vector kernel's path).  Rare: |offset*scale| >= 3 px.
 template <typename T>
-__device__ __noinline__ PtResA bwd_point_a(const PtGeo pg, const float p0h_, const float p0w_, const int p,
-                                           const uint32_t offw, const float m, const float *Drow,
-                                           const int sy0, const int sx0, const T *img_g, float *gacc_g,
-                                           const int C) {
+__device__ __noinline__ PtResA bwd_point_slow(const PtGeo pg, const float p0h_, const float p0w_, const int p,
+                                              const uint32_t offw, const float m, const float *Drow,
+                                              const T *img_g, float *gacc_g, const int C) {
     PtResA r{0u, 0.f, 0u, 0u};
     const Geo q = geo_of(pg);
     const int i = p / 3, j = p - 3 * i;
     const float2 o = unpack2f<T>(offw);
     Point<float> t;
     locate<float>(q, p0h_, p0w_, i, j, o.x, o.y, t);
-    if (!t.inside) return r;
-    const unsigned u = (unsigned)(t.w_low - sx0), v = (unsigned)(t.h_low - sy0);
+    float go[16];
+    const uint4 ga = *reinterpret_cast<const uint4 *>(Drow + kCells);
+    const uint4 gb = *reinterpret_cast<const uint4 *>(Drow + kCells + 4);
+    const uint32_t gwd[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float2 f = unpack2f<T>(gwd[c]);
+        go[2 * c] = f.x; go[2 * c + 1] = f.y;
+    }
+    const float w[4] = {t.hh * t.hw, t.hh * t.lw, t.lh * t.hw, t.lh * t.lw};
+    const bool ok[4] = {t.ok1, t.ok2, t.ok3, t.ok4};
     float d[4];
-    if (u <= (unsigned)(kSub - 2) && v <= (unsigned)(kSub - 2)) {
-        const float *c = Drow + v * kSub + u;
-        d[0] = c[0]; d[1] = c[1]; d[2] = c[kSub]; d[3] = c[kSub + 1];
-        r.kq = 256u | (v * kSub + u);
-        // fractions for pass B, truncated to 2^-16 (the weights there feed TF32 operands anyway)
-        r.frac = (__float2uint_rz(t.lh * 65536.f) << 16) | __float2uint_rz(t.lw * 65536.f);
-    } else {
-        float go[16];
-        const uint4 ga = *reinterpret_cast<const uint4 *>(Drow + kCells);
-        const uint4 gb = *reinterpret_cast<const uint4 *>(Drow + kCells + 4);
-        const uint32_t gwd[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        d[k] = 0.f;
+        if (!ok[k]) continue;
+        const size_t e = ((size_t)(t.h_low + (k >> 1)) * q.W + (t.w_low + (k & 1))) * C;
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(img_g + e));
+        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(img_g + e) + 1);
+        const uint32_t wd[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        float acc = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const float2 f = unpack2f<T>(gwd[c]);
-            go[2 * c] = f.x; go[2 * c + 1] = f.y;
+            const float2 f = unpack2f<T>(wd[c]);
+            acc = fmaf(go[2 * c], f.x, acc);
+            acc = fmaf(go[2 * c + 1], f.y, acc);
         }
-        const float w[4] = {t.hh * t.hw, t.hh * t.lw, t.lh * t.hw, t.lh * t.lw};
-        const bool ok[4] = {t.ok1, t.ok2, t.ok3, t.ok4};
-#pragma unroll 1
-        for (int k = 0; k < 4; ++k) {
-            d[k] = 0.f;
-            if (!ok[k]) continue;
-            const size_t e = ((size_t)(t.h_low + (k >> 1)) * q.W + (t.w_low + (k & 1))) * C;
-            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(img_g + e));
-            const uint4 b = __ldg(reinterpret_cast<const uint4 *>(img_g + e) + 1);
-            const uint32_t wd[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            float acc = 0.f;
+        d[k] = acc;
+        const float wm = w[k] * m;
+        float *dst = gacc_g + e;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float2 f = unpack2f<T>(wd[c]);
-                acc = fmaf(go[2 * c], f.x, acc);
-                acc = fmaf(go[2 * c + 1], f.y, acc);
-            }
-            d[k] = acc;
-            const float wm = w[k] * m;
-            float *dst = gacc_g + e;
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                red_add_v4_f32(dst + 4 * c, wm * go[4 * c], wm * go[4 * c + 1], wm * go[4 * c + 2], wm * go[4 * c + 3]);
-        }
+        for (int c = 0; c < 4; ++c)
+            red_add_v4_f32(dst + 4 * c, wm * go[4 * c], wm * go[4 * c + 1], wm * go[4 * c + 2], wm * go[4 * c + 3]);
     }
-    const float w1 = t.hh * t.hw, w2 = t.hh * t.lw, w3 = t.lh * t.hw, w4 = t.lh * t.lw;
-    const float s_m = w1 * d[0] + w2 * d[1] + w3 * d[2] + w4 * d[3];
+    const float s_m = w[0] * d[0] + w[1] * d[1] + w[2] * d[2] + w[3] * d[3];
     const float s_w = t.hh * (d[1] - d[0]) + t.lh * (d[3] - d[2]);
     const float s_h = t.hw * (d[2] - d[0]) + t.lw * (d[3] - d[1]);
     const float sm = q.scale * m;
+    r.off = pack2<T>(sm * s_w, sm * s_h);
+    r.m = s_m;
+    return r;
+}
+
+// pass A of one point: corner dots from D (or the slow path), grad_offset / grad_mask terms, and the
+// cell + fractions pass B reuses
+template <typename T>
+__device__ __noinline__ PtResA bwd_point_a(const PtGeo pg, const float p0h_, const float p0w_, const int p,
+                                           const float fi, const float fj, const uint32_t offw, const float m,
+                                           const float *Drow, const int sy0, const int sx0, const T *img_g,
+                                           float *gacc_g, const int C) {
+    const float2 o = unpack2f<T>(offw);
+    const LeanPoint t = locate_lean(pg, p0h_, p0w_, fi, fj, o.x, o.y);
+    if (!t.inside) return PtResA{0u, 0.f, 0u, 0u};
+    const unsigned u = (unsigned)(t.w_low - sx0), v = (unsigned)(t.h_low - sy0);
+    if (u > (unsigned)(kSub - 2) || v > (unsigned)(kSub - 2))
+        return bwd_point_slow<T>(pg, p0h_, p0w_, p, offw, m, Drow, img_g, gacc_g, C);
+    PtResA r;
+    const unsigned k = v * kSub + u;
+    const float *c = Drow + k;
+    const float d0 = c[0], d1 = c[1], d2 = c[kSub], d3 = c[kSub + 1];
+    r.kq = 256u | k;
+    // fractions for pass B, truncated to 2^-16 (the weights there feed TF32 operands anyway)
+    r.frac = (__float2uint_rz(t.lh * 65536.f) << 16) | __float2uint_rz(t.lw * 65536.f);
+    const float hh = sub_rn(1.f, t.lh), hw = sub_rn(1.f, t.lw);
+    const float w1 = hh * hw, w2 = hh * t.lw, w3 = t.lh * hw, w4 = t.lh * t.lw;
+    const float s_m = w1 * d0 + w2 * d1 + w3 * d2 + w4 * d3;
+    const float s_w = hh * (d1 - d0) + t.lh * (d3 - d2);
+    const float s_h = hw * (d2 - d0) + t.lw * (d3 - d1);
+    const float sm = pg.scale * m;
     r.off = pack2<T>(sm * s_w, sm * s_h);
     r.m = s_m;
     return r;
@@ -662,7 +698,7 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
             res_m[p] = 0.f;
             frac[p] = 0u;
             if (pc.valid) {
-                const PtResA r = bwd_point_a<T>(pg, p0h_, p0w_, p, myoff[p], mym[p], Wrow, sy0, sx0, img_g, gacc_g, q.C);
+                const PtResA r = bwd_point_a<T>(pg, p0h_, p0w_, p, (float)(p / 3), (float)(p % 3), myoff[p], mym[p], Wrow, sy0, sx0, img_g, gacc_g, q.C);
                 res_off[p] = r.off;
                 res_m[p] = r.m;
                 frac[p] = r.frac;
