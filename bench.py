@@ -169,8 +169,12 @@ class Workload:
                 b.alloc_ws(self.lib, self.accum)
             self.sets.append(bufs)
         lowp = esize(dtype) == 2
-        # my kernels per step: 1 forward + 1 backward (+ 1 workspace cast for 16-bit ACC_OPMATH) per site
-        self.launches_per_step = len(sites) * (2 + (1 if lowp and accum == "opmath" else 0))
+        # my kernels per step and site: 1 forward + backward.  16-bit ACC_OPMATH backward at these shapes =
+        # zero_select_kernel + bwd_imat_kernel + bwd_vec_kernel (returns at once unless the selector picked
+        # it) + cast_ws_kernel; with a family forced by DCNV3_B200_BWD: backward kernel + cast (+ a driver memset).
+        forced = os.environ.get("DCNV3_B200_BWD") in ("vec", "imat", "tile")
+        bwd = (2 if forced else 4) if (lowp and accum == "opmath") else 1
+        self.launches_per_step = len(sites) * (1 + bwd)
 
     def fwd(self, b, st):
         rc = self.lib.dcnv3_b200_forward(b.input.data_ptr(), b.offset.data_ptr(), b.mask.data_ptr(),
@@ -541,8 +545,8 @@ def main():
         t["frac_of_hbm"] = t["GBps"] / peak
         table[nm] = t
     dom = max(table, key=lambda k: table[k]["us_mean"])
-    roofline = {"bound": "hbm", "kernel": dom + ((" (memset + " + ("bwd_vec_kernel" if os.environ.get("DCNV3_B200_BWD") == "vec" else "bwd_imat_kernel") +
-                                         " + cast_ws_kernel)") if dom.startswith("bwd") and e == 2 and a.grad_accum == "opmath" else ""),
+    roofline = {"bound": "hbm", "kernel": dom + ((" (memset + bwd_vec_kernel + cast_ws_kernel)" if os.environ.get("DCNV3_B200_BWD") == "vec" else
+                                        " (zero_select_kernel + bwd_imat_kernel [+ bwd_vec_kernel, skipped by the selector] + cast_ws_kernel)") if dom.startswith("bwd") and e == 2 and a.grad_accum == "opmath" else ""),
                 "achieved": table[dom]["GBps"], "peak": peak, "unit": "GB/s", "frac": table[dom]["GBps"] / peak,
                 "peak_source": peak_src, "traffic": ncu_traffic(dom),
                 "step_frac": value / world / peak}

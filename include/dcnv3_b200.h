@@ -110,7 +110,9 @@ int dcnv3_b200_forward(const void *input, const void *offset, const void *mask,
                        void *output, int dtype, const dcnv3_b200_geometry *geo,
                        int mask_is_logits, void *cuda_stream);
 
-/* Bytes of scratch dcnv3_b200_backward needs for this call (0 when none). */
+/* Bytes of scratch dcnv3_b200_backward needs for this call (0 when none): for 16-bit storage
+ * with ACC_OPMATH the fp32 accumulators of grad_input plus 256 bytes in which the library keeps
+ * the device-side choice between its two backward kernel families for that call. */
 size_t dcnv3_b200_backward_workspace_bytes(int dtype, const dcnv3_b200_geometry *geo,
                                            int grad_accum);
 

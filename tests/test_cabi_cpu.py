@@ -88,7 +88,8 @@ def test_argument_validation_order(lib):
     assert lib.dcnv3_b200_backward(1, 1, 1, 1, 1, 1, 1, None, 0, 0, ctypes.byref(g), 0, 5, None) == -1
     # empty batch: nothing to do, no device needed
     assert lib.dcnv3_b200_forward(None, None, None, None, 0, ctypes.byref(_geo(N=0)), 0, None) == 0
-    assert lib.dcnv3_b200_backward_workspace_bytes(2, ctypes.byref(g), 0) == 2 * 8 * 8 * 64 * 4
+    # fp32 accumulators (rounded up to 256 B) + 256 B for the kernel-family selector word
+    assert lib.dcnv3_b200_backward_workspace_bytes(2, ctypes.byref(g), 0) == 2 * 8 * 8 * 64 * 4 + 256
     assert lib.dcnv3_b200_backward_workspace_bytes(2, ctypes.byref(g), 1) == 0
     assert lib.dcnv3_b200_backward_workspace_bytes(0, ctypes.byref(g), 0) == 0
 

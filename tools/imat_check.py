@@ -112,9 +112,13 @@ def timing(do_bwd):
         wsb = lib.dcnv3_b200_backward_workspace_bytes(_lib.BF16, ctypes.byref(geo), _lib.ACC_OPMATH)
         ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=DEV)
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        for fam in ("vec", "imat"):
-            os.environ["DCNV3_B200_FWD"] = fam
-            os.environ["DCNV3_B200_BWD"] = fam
+        for fam in ("vec", "imat", "auto"):
+            if fam == "auto":  # no knobs: the library's own choice (device-side selector for the backward)
+                os.environ.pop("DCNV3_B200_FWD", None)
+                os.environ.pop("DCNV3_B200_BWD", None)
+            else:
+                os.environ["DCNV3_B200_FWD"] = fam
+                os.environ["DCNV3_B200_BWD"] = fam
             res = {}
             for what in (("fwd", "bwd") if do_bwd else ("fwd",)):
                 def step(i):

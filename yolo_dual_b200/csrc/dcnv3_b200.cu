@@ -216,16 +216,16 @@ int launch_fwd_imat(const T *in, const T *off, const T *mask, T *out, const Geo 
 
 template <typename T>
 int launch_bwd_imat(const T *in, const T *off, const T *mask, const T *gout, float *acc, T *goff, T *gmask,
-                    const Geo &q, bool logits, cudaStream_t st) {
+                    const Geo &q, bool logits, const int *sel, cudaStream_t st) {
     const int tiles_y = (q.Ho + 7) / 8, tiles_x = (q.Wo + 7) / 8, GQ = q.G / imat::kWarps;
     const unsigned grid = (unsigned)((size_t)q.N * tiles_y * tiles_x * GQ);
     int rc;
     if (logits) {
         if ((rc = set_smem(imat::bwd_imat_kernel<T, true>, imat::kSmemBwd, "cudaFuncSetAttribute(bwd_imat_kernel)"))) return rc;
-        imat::bwd_imat_kernel<T, true><<<grid, 32 * imat::kWarps, imat::kSmemBwd, st>>>(in, off, mask, gout, acc, goff, gmask, q, tiles_x, tiles_y, GQ);
+        imat::bwd_imat_kernel<T, true><<<grid, 32 * imat::kWarps, imat::kSmemBwd, st>>>(in, off, mask, gout, acc, goff, gmask, q, tiles_x, tiles_y, GQ, sel);
     } else {
         if ((rc = set_smem(imat::bwd_imat_kernel<T, false>, imat::kSmemBwd, "cudaFuncSetAttribute(bwd_imat_kernel)"))) return rc;
-        imat::bwd_imat_kernel<T, false><<<grid, 32 * imat::kWarps, imat::kSmemBwd, st>>>(in, off, mask, gout, acc, goff, gmask, q, tiles_x, tiles_y, GQ);
+        imat::bwd_imat_kernel<T, false><<<grid, 32 * imat::kWarps, imat::kSmemBwd, st>>>(in, off, mask, gout, acc, goff, gmask, q, tiles_x, tiles_y, GQ, sel);
     }
     return 0;
 }
@@ -342,15 +342,17 @@ int launch_tile(const T *in, const T *off, const T *mask, const T *gout, float *
 template <typename T, typename A>
 int backward_launch(const T *in, const T *off, const T *mask, const T *gout, A *acc, T *goff,
                     T *gmask, const Geo &q, bool logits, const Plan &pl, size_t n_pix,
-                    cudaStream_t st) {
+                    cudaStream_t st, const int *sel = nullptr) {
     if constexpr (sizeof(T) <= 4) {
         if (pl.vec) {
-            const unsigned grid = blocks_for(pl.total_vec);
+            const unsigned n_blocks = blocks_for(pl.total_vec);
+            const unsigned per_cta = sel ? 4u : 1u;  // selector-guarded launch: fewer, fatter CTAs
+            const unsigned grid = (n_blocks + per_cta - 1) / per_cta;
             const bool k9 = (q.kh == 3 && q.kw == 3);
 #define LAUNCH_BWD(BPL, KP, LG)                                                                  \
     bwd_vec_kernel<T, A, BPL, KP, LG><<<grid, kThreads, 0, st>>>(in, off, mask, gout, acc, goff, \
                                                                  gmask, q, pl.vec_per_pix,       \
-                                                                 pl.lanes_per_group, pl.total_vec)
+                                                                 pl.lanes_per_group, pl.total_vec, sel, per_cta, n_blocks)
 #define LAUNCH_BWD_B(BPL)                      \
     if (k9 && logits) LAUNCH_BWD(BPL, 9, true); \
     else if (k9) LAUNCH_BWD(BPL, 9, false);     \
@@ -397,36 +399,53 @@ int backward_t(const void *in_, const void *off_, const void *mask_, const void 
     constexpr bool lowp = sizeof(T) == 2;
     if (lowp && grad_accum == DCNV3_B200_ACC_OPMATH) {
         // reference semantics (dcnv3_cuda.cu:126-133,168-170): fp32 accumulation, one rounding
-        const size_t need = n_in * sizeof(float);
+        const size_t acc_bytes = (n_in * sizeof(float) + 255) & ~(size_t)255;
+        const size_t need = acc_bytes + 256;  // + the family selector word (imat::select_kernel)
         if (!ws || ws_bytes < need)
             return fail(DCNV3_B200_EWORKSPACE, "workspace of %zu bytes required, got %zu", need, ws ? ws_bytes : 0);
         if (!aligned16(ws)) return fail(DCNV3_B200_EALIGN, "workspace must be 16-byte aligned");
         float *acc = (float *)ws;
-        if ((e = cudaMemsetAsync(acc, 0, need, st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
+        bool zeroed = false;
         if (n_pix) {
             TileCfg tc;
             int rc = 0;
             bool tiled = false;
             if constexpr (lowp) {
                 if (plan_tile<T>(q, logits, in_, gout_, off_, acc, tc)) {
+                    if ((e = cudaMemsetAsync(acc, 0, need, st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
+                    zeroed = true;
                     rc = launch_tile<T>(in, off, mask, gout, acc, goff, gmask, q, logits, tc, st);
                     tiled = true;
                 }
             }
             if constexpr (lowp) {
-                const int fam = family_knob("DCNV3_B200_BWD");  // default: imat when eligible
+                // Default for eligible shapes: a 16 K-sample look at the offsets picks the family on
+                // the device (imat::select_kernel); both kernels are launched, one returns at once.
+                // DCNV3_B200_BWD=vec|imat forces one (no selector).
+                const int fam = family_knob("DCNV3_B200_BWD");
                 if (!tiled && (fam == 0 || fam == 3) && imat_eligible<T>(q, {in_, gout_, ws}, off_) &&
                     !(reinterpret_cast<uintptr_t>(goff_) & 3u)) {
-                    rc = launch_bwd_imat<T>(in, off, mask, gout, acc, goff, gmask, q, logits, st);
+                    const Plan pl = plan_vec<T>(q, n_pix, logits, {in_, gout_}, off_, sizeof(float), true);
+                    int *sel = nullptr;
+                    if (fam == 0 && pl.vec) sel = reinterpret_cast<int *>(static_cast<char *>(ws) + acc_bytes);
+                    // zero fill of the accumulators (the memset) with the selector riding along in block 0
+                    imat::zero_select_kernel<T><<<148 * 4, imat::kSelThreads, 0, st>>>(
+                        reinterpret_cast<uint4 *>(acc), acc_bytes / 16, off, (unsigned long long)n_pix * q.G * q.P, q.scale, sel);
+                    zeroed = true;
+                    rc = launch_bwd_imat<T>(in, off, mask, gout, acc, goff, gmask, q, logits, sel, st);
+                    if (!rc && sel) rc = backward_launch<T, float>(in, off, mask, gout, acc, goff, gmask, q, logits, pl, n_pix, st, sel);
                     tiled = true;
                 }
             }
             if (!tiled) {
+                if ((e = cudaMemsetAsync(acc, 0, need, st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
+                zeroed = true;
                 const Plan pl = plan_vec<T>(q, n_pix, logits, {in_, gout_}, off_, sizeof(float), true);
                 rc = backward_launch<T, float>(in, off, mask, gout, acc, goff, gmask, q, logits, pl, n_pix, st);
             }
             if (rc) return rc;
         }
+        if (!zeroed && (e = cudaMemsetAsync(acc, 0, need, st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(workspace)");
         if constexpr (lowp) {
             const bool v8 = aligned16(gin_);
             const size_t n8 = v8 ? n_in / 8 : 0;
@@ -502,7 +521,7 @@ size_t dcnv3_b200_backward_workspace_bytes(int dtype, const dcnv3_b200_geometry 
     Geo q;
     if (make_geo(geo, q)) return 0;
     if (dtype_size(dtype) == 2 && grad_accum == DCNV3_B200_ACC_OPMATH)
-        return (size_t)q.N * q.H * q.W * q.C * sizeof(float);
+        return (((size_t)q.N * q.H * q.W * q.C * sizeof(float) + 255) & ~(size_t)255) + 256;
     return 0;
 }
 

@@ -290,17 +290,17 @@ __device__ __forceinline__ void load_go_chunk(const T *p, float (&g)[CPQ]) {
 }
 
 template <typename T, typename A, int BPL, int KP, bool LOGITS>
-__global__ void __launch_bounds__(kThreads)
-bwd_vec_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
-               const T *__restrict__ gout, A *__restrict__ gin, T *__restrict__ goff,
-               T *__restrict__ gmask, const Geo q, const int vec_per_pix,
-               const int lanes_per_group, const unsigned total) {
+__device__ __forceinline__ void
+bwd_vec_body(const unsigned block, const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
+             const T *__restrict__ gout, A *__restrict__ gin, T *__restrict__ goff,
+             T *__restrict__ gmask, const Geo &q, const int vec_per_pix,
+             const int lanes_per_group, const unsigned total) {
     static_assert(!LOGITS || KP > 0, "fused softmax in the vector path needs a compile-time P");
     constexpr int CH = Lane<T, BPL>::CH, NP = Lane<T, BPL>::NP;
     constexpr int CPQ = RedChunk<A>::CPQ;                 // channels per 16-byte reduction
     constexpr int R = CH * (int)sizeof(A) / 16;           // reductions per corner per lane
     static_assert(R >= 1, "a lane must own at least one 16-byte reduction chunk");
-    unsigned idx = blockIdx.x * (unsigned)kThreads + threadIdx.x;
+    unsigned idx = block * (unsigned)kThreads + threadIdx.x;
     const bool active = idx < total;  // tail lanes stay for the shuffles
     if (!active) idx = total - 1;
     const VecCoord c = decode_vec(idx, q, vec_per_pix, lanes_per_group);
@@ -416,6 +416,25 @@ bwd_vec_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
 #pragma unroll
         for (int k = 0; k < (KP ? KP : 1); ++k) d_m[k] = from_math<T>(prob[k] * (gm[k] - dot));
     }
+}
+
+// `per_cta` consecutive logical blocks per CTA (1 except for the selector-guarded launch, where a
+// kernel that returns at once should not cost 12800 CTA launches).  `sel`: family selector written by
+// imat::zero_select_kernel on the same stream (this kernel runs when it reads 1).
+template <typename T, typename A, int BPL, int KP, bool LOGITS>
+__global__ void __launch_bounds__(kThreads)
+bwd_vec_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
+               const T *__restrict__ gout, A *__restrict__ gin, T *__restrict__ goff,
+               T *__restrict__ gmask, const Geo q, const int vec_per_pix,
+               const int lanes_per_group, const unsigned total, const int *__restrict__ sel = nullptr,
+               const unsigned per_cta = 1, const unsigned n_blocks = 0) {
+    if (sel != nullptr && *sel != 1) return;
+    if (per_cta == 1) {
+        bwd_vec_body<T, A, BPL, KP, LOGITS>(blockIdx.x, in, off, mask, gout, gin, goff, gmask, q, vec_per_pix, lanes_per_group, total);
+        return;
+    }
+    for (unsigned b = blockIdx.x * per_cta, e = min(b + per_cta, n_blocks); b < e; ++b)
+        bwd_vec_body<T, A, BPL, KP, LOGITS>(b, in, off, mask, gout, gin, goff, gmask, q, vec_per_pix, lanes_per_group, total);
 }
 
 // fp32 workspace -> 16-bit grad_input (ACC_OPMATH), 8 elements per thread
