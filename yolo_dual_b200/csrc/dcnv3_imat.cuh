@@ -421,20 +421,23 @@ zero_select_kernel(uint4 *__restrict__ ws, const size_t n16, const T *__restrict
         __shared__ int cnt;
         if (threadIdx.x == 0) cnt = 0;
         __syncthreads();
-        const unsigned long long stride = n_points / (kSelThreads * kSelPerThread) + 1;
+        // 32-bit sample ids: the stride is capped so that id stays below 2^32 (the samples then
+        // cover the first 2^32 points, far beyond any real tensor)
+        const unsigned long long capped = n_points < 0xffff0000ull ? n_points : 0xffff0000ull;
+        const unsigned np = (unsigned)capped, stride = np / (kSelThreads * kSelPerThread) + 1;
         float2 o[kSelPerThread];
         bool live[kSelPerThread];
 #pragma unroll
         for (int k = 0; k < kSelPerThread; ++k) {
-            const unsigned long long id = ((unsigned long long)(k * kSelThreads + threadIdx.x)) * stride;
-            live[k] = id < n_points;
-            o[k] = live[k] ? load_offset_pair(off + 2 * id) : make_float2(0.f, 0.f);
+            const unsigned id = (unsigned)(k * kSelThreads + threadIdx.x) * stride;
+            live[k] = id < np;
+            o[k] = live[k] ? load_offset_pair(off + 2 * (size_t)id) : make_float2(0.f, 0.f);
         }
         int v = 0;
 #pragma unroll
         for (int k = 0; k < kSelPerThread; ++k) {
-            const unsigned long long id = ((unsigned long long)(k * kSelThreads + threadIdx.x)) * stride;
-            const int p = (int)(id % 9);
+            const unsigned id = (unsigned)(k * kSelThreads + threadIdx.x) * stride;
+            const int p = (int)(id % 9u);
             const float dx = ((float)(p / 3 - 1) + o[k].x) * scale, dy = ((float)(p % 3 - 1) + o[k].y) * scale;
             if (live[k]) v += ((fabsf(dx) < 4.f && fabsf(dy) < 4.f) ? 0 : (1 << 16)) | 1;
         }
@@ -661,6 +664,16 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
                 const uint4 *gp = reinterpret_cast<const uint4 *>(gout + (((size_t)tc.n * q.Ho + pc.oy) * q.Wo + pc.ox) * q.C + g * 16);
                 go_lo = __ldg(gp);
                 go_hi = __ldg(gp + 1);
+                if (pass == 0 && pc.oy + 4 < q.Ho)  // next pass's grad_output row: 4 map rows further down
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(gp) + (size_t)4 * q.Wo * q.C * sizeof(T)));
+            }
+            if (pass == 0) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i)
+                    if ((io1 >> i) & 1u) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(off32 + io.idx[i] + pass_stride));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(msk16 + io.idx[i] + pass_stride));
+                    }
             }
 #pragma unroll
             for (int i = 0; i < 9; ++i) {
@@ -845,33 +858,32 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
         __syncwarp();
     }
 
-    // ---- flush: the four warps' windows side by side (256 B per cell), 16-byte chunks swizzled by
-    // 2*(column & 7), then 256-byte-contiguous vector reductions into gacc
-    __syncthreads();
-    float *GW = reinterpret_cast<float *>(smem + kWinBytes);
+    // ---- flush, per warp (no CTA barrier): the group's window goes through the warp's own Wm buffer as
+    // [256 cells][16 ch] fp32 (16-byte chunks swizzled by 2*((cell >> 1) & 1): conflict-free both ways),
+    // then out as 64-byte-contiguous vector reductions; cells that received nothing are skipped
+    {
+        float *GW = Wm;
 #pragma unroll
-    for (int r = 0; r < kWin; ++r)
+        for (int r = 0; r < kWin; ++r)
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-            const int chunk = warp * 4 + nt * 2 + (tq >> 1);
-            const int c0 = r * kWin + gID, c1 = c0 + 8;  // same (column & 7) -> same key
-            const int sw = ((chunk ^ (2 * (gID & 7))) << 2) + 2 * (tq & 1);
-            *reinterpret_cast<float2 *>(GW + c0 * 64 + sw) = make_float2(gw[r][nt][0], gw[r][nt][1]);
-            *reinterpret_cast<float2 *>(GW + c1 * 64 + sw) = make_float2(gw[r][nt][2], gw[r][nt][3]);
-        }
-    __syncthreads();
-    {   // thread = (16-byte chunk j of the 256-byte cell row, cell tid >> 4 of every 8)
-        const int j = tid & 15, c8 = tid >> 4;
+            for (int nt = 0; nt < 2; ++nt) {
+                const int c0 = r * kWin + gID;  // and c0 + 8: same swizzle key
+                const int sw = (((2 * nt + (tq >> 1)) ^ (((gID >> 1) & 1) << 1)) << 2) + 2 * (tq & 1);
+                *reinterpret_cast<float2 *>(GW + c0 * 16 + sw) = make_float2(gw[r][nt][0], gw[r][nt][1]);
+                *reinterpret_cast<float2 *>(GW + (c0 + 8) * 16 + sw) = make_float2(gw[r][nt][2], gw[r][nt][3]);
+            }
+        __syncwarp();
+        const int j = lane & 3, c8 = lane >> 2;  // 16-byte chunk of the cell, cell within 8
         const int ix0 = wx0 + c8, ix1 = ix0 + 8;
         const bool ok0 = (unsigned)ix0 < (unsigned)q.W, ok1 = (unsigned)ix1 < (unsigned)q.W;
         const long long row_stride = (long long)q.W * q.C;
-        float *dst0 = gacc + img_off + ((long long)wy0 * q.W + ix0) * q.C + 4 * j;
-        const float *src = GW + c8 * 64 + ((j ^ (2 * (c8 & 7))) << 2);  // (cell & 7) == c8 for both halves
+        float *dst0 = gacc_g + ((long long)wy0 * q.W + ix0) * q.C + 4 * j;
+        const float *src = GW + c8 * 16 + ((j ^ (((c8 >> 1) & 1) << 1)) << 2);
 #pragma unroll 4
         for (int r = 0; r < kWin; ++r) {
             const bool row_ok = (unsigned)(wy0 + r) < (unsigned)q.H;
-            const float4 v0 = *reinterpret_cast<const float4 *>(src + r * (kWin * 64));
-            const float4 v1 = *reinterpret_cast<const float4 *>(src + r * (kWin * 64) + 8 * 64);
+            const float4 v0 = *reinterpret_cast<const float4 *>(src + r * (kWin * 16));
+            const float4 v1 = *reinterpret_cast<const float4 *>(src + r * (kWin * 16) + 8 * 16);
             const bool nz0 = ((__float_as_uint(v0.x) | __float_as_uint(v0.y) | __float_as_uint(v0.z) | __float_as_uint(v0.w)) << 1) != 0u;
             const bool nz1 = ((__float_as_uint(v1.x) | __float_as_uint(v1.y) | __float_as_uint(v1.z) | __float_as_uint(v1.w)) << 1) != 0u;
             float *d = dst0 + r * row_stride;
