@@ -64,6 +64,25 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// D += A(16x16) * B(16x8) in the storage dtype (bf16 / fp16 operands are used as they are), fp32 accumulate
+template <typename T>
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                          uint32_t b0, uint32_t b1);
+template <>
+__device__ __forceinline__ void mma_16816<__nv_bfloat16>(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2,
+                                                         uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+template <>
+__device__ __forceinline__ void mma_16816<__half>(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                  uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
 // two packed 16-bit storage values -> fp32 bit patterns (exact; both are valid TF32 operands)
 template <typename T> __device__ __forceinline__ void unpack2(uint32_t w, uint32_t &lo, uint32_t &hi);
 template <> __device__ __forceinline__ void unpack2<__nv_bfloat16>(uint32_t w, uint32_t &lo, uint32_t &hi) {
@@ -390,7 +409,7 @@ fwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
 // backward (16-bit storage, fp32 accumulation of grad_input into `gacc` [N,H,W,C], pre-zeroed)
 //
 // Per pass (32 pixels of one group = two 4x4 sub-tiles), all in the warp's private Wm buffer:
-//   1. D[pixel][cell] = sum_ch go[pixel][ch] * X[cell][ch]          tensor cores  (mma #1)
+//   1. D[pixel][cell] = sum_ch go[pixel][ch] * X[cell][ch]          tensor cores  (mma #1, m16n8k16 in the storage dtype)
 //   2. lane = pixel: for its 9 points read the four corner dots d_k from D ->
 //        grad_mask   = sum_k w_k d_k                                   (cuh:144)
 //        grad_offset = scale*m*(hh(d2-d1)+lh(d4-d3), hw(d3-d1)+lw(d4-d2))   (cuh:114-139,145-146)
@@ -704,15 +723,10 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
         // ---- mma #1: D[pixel][cell] for both sub-tiles (rolled: 2 x 9 iterations)
 #pragma unroll 1
         for (int s = 0; s < n_sub; ++s) {
-            uint32_t a[2][4];
-            {
-                uint32_t r0, r1, r2, r3;  // (px 0-7, ch 0-7) (px 8-15, ch 0-7) (px 0-7, ch 8-15) (px 8-15, ch 8-15)
-                ldmatrix_x4(r0, r1, r2, r3, wm_s + ((16 * s + 8 * (jm & 1) + jr) * kRow + kCells) * 4 + (jm >> 1) * 16);
-                unpack2<T>(r0, a[0][0], a[0][2]);
-                unpack2<T>(r1, a[0][1], a[0][3]);
-                unpack2<T>(r2, a[1][0], a[1][2]);
-                unpack2<T>(r3, a[1][1], a[1][3]);
-            }
+            // both operands are exact in the storage dtype: one m16n8k16 per 8 cells, no conversions.
+            // A = go [16 px x 16 ch]: (px 0-7, ch 0-7) (px 8-15, ch 0-7) (px 0-7, ch 8-15) (px 8-15, ch 8-15)
+            uint32_t a0, a1, a2, a3;
+            ldmatrix_x4(a0, a1, a2, a3, wm_s + ((16 * s + 8 * (jm & 1) + jr) * kRow + kCells) * 4 + (jm >> 1) * 16);
             const uint32_t wbase = win_s + pass * (4 * kWin * 128) + s * 512;
             float *D0 = Wm + (16 * s + gID) * kRow + 2 * tq;
             // B rows: cell 16ks + 8(jm>>1) + jr of the sub-window.  Three k-steps are exactly four
@@ -733,15 +747,8 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
                     uint32_t r0, r1, r2, r3;  // (cells 0-7, ch 0-7) (cells 0-7, ch 8-15) (cells 8-15, ch 0-7) (cells 8-15, ch 8-15)
                     ldmatrix_x4(r0, r1, r2, r3, bo[r] + m * (4 * kWin * 128));
                     float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
-                    uint32_t b0, b1;
-                    unpack2<T>(r0, b0, b1);
-                    mma_tf32(d0, a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
-                    unpack2<T>(r1, b0, b1);
-                    mma_tf32(d0, a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
-                    unpack2<T>(r2, b0, b1);
-                    mma_tf32(d1, a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
-                    unpack2<T>(r3, b0, b1);
-                    mma_tf32(d1, a[1][0], a[1][1], a[1][2], a[1][3], b0, b1);
+                    mma_16816<T>(d0, a0, a1, a2, a3, r0, r1);
+                    mma_16816<T>(d1, a0, a1, a2, a3, r2, r3);
                     float *Dk = D0 + 48 * m + 16 * r;
                     *reinterpret_cast<float2 *>(Dk) = make_float2(d0[0], d0[1]);
                     *reinterpret_cast<float2 *>(Dk + 8 * kRow) = make_float2(d0[2], d0[3]);
