@@ -169,6 +169,28 @@ Plan plan_vec(const Geo &q, size_t n_pix, bool logits, std::initializer_list<con
 
 unsigned blocks_for(size_t threads) { return (unsigned)((threads + kThreads - 1) / kThreads); }
 
+// Launch with programmatic stream serialization (the kernel may be scheduled while its predecessor on
+// the stream drains; it calls pdl_enter() before touching memory, dcnv3_common.cuh).  DCNV3_B200_PDL=0
+// turns the attribute off (plain stream order).  Errors surface through cudaGetLastError in finish().
+bool pdl_on() {
+    const char *e = getenv("DCNV3_B200_PDL");
+    return !(e && e[0] == '0');
+}
+template <typename... P, typename... A>
+void launch(void (*kernel)(P...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, A... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = pdl_on() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 // ---------------------------------------------- interpolation-matrix family
 // Knobs: DCNV3_B200_FWD / DCNV3_B200_BWD = vec | imat force a family.  Defaults: the backward takes the
 // interpolation-matrix kernel when eligible (16-bit, gc = 16, 3x3 s1 d1, fp32 accumulation), the forward the
@@ -206,10 +228,10 @@ int launch_fwd_imat(const T *in, const T *off, const T *mask, T *out, const Geo 
     int rc;
     if (logits) {
         if ((rc = set_smem(imat::fwd_imat_kernel<T, true>, imat::kSmemFwd, "cudaFuncSetAttribute(fwd_imat_kernel)"))) return rc;
-        imat::fwd_imat_kernel<T, true><<<grid, 32 * imat::kWarps, imat::kSmemFwd, st>>>(in, off, mask, out, q, tiles_x, tiles_y, GQ);
+        launch(imat::fwd_imat_kernel<T, true>, grid, 32 * imat::kWarps, imat::kSmemFwd, st, in, off, mask, out, q, tiles_x, tiles_y, GQ);
     } else {
         if ((rc = set_smem(imat::fwd_imat_kernel<T, false>, imat::kSmemFwd, "cudaFuncSetAttribute(fwd_imat_kernel)"))) return rc;
-        imat::fwd_imat_kernel<T, false><<<grid, 32 * imat::kWarps, imat::kSmemFwd, st>>>(in, off, mask, out, q, tiles_x, tiles_y, GQ);
+        launch(imat::fwd_imat_kernel<T, false>, grid, 32 * imat::kWarps, imat::kSmemFwd, st, in, off, mask, out, q, tiles_x, tiles_y, GQ);
     }
     return 0;
 }
@@ -222,10 +244,10 @@ int launch_bwd_imat(const T *in, const T *off, const T *mask, const T *gout, flo
     int rc;
     if (logits) {
         if ((rc = set_smem(imat::bwd_imat_kernel<T, true>, imat::kSmemBwd, "cudaFuncSetAttribute(bwd_imat_kernel)"))) return rc;
-        imat::bwd_imat_kernel<T, true><<<grid, 32 * imat::kWarps, imat::kSmemBwd, st>>>(in, off, mask, gout, acc, goff, gmask, q, tiles_x, tiles_y, GQ, sel);
+        launch(imat::bwd_imat_kernel<T, true>, grid, 32 * imat::kWarps, imat::kSmemBwd, st, in, off, mask, gout, acc, goff, gmask, q, tiles_x, tiles_y, GQ, sel);
     } else {
         if ((rc = set_smem(imat::bwd_imat_kernel<T, false>, imat::kSmemBwd, "cudaFuncSetAttribute(bwd_imat_kernel)"))) return rc;
-        imat::bwd_imat_kernel<T, false><<<grid, 32 * imat::kWarps, imat::kSmemBwd, st>>>(in, off, mask, gout, acc, goff, gmask, q, tiles_x, tiles_y, GQ, sel);
+        launch(imat::bwd_imat_kernel<T, false>, grid, 32 * imat::kWarps, imat::kSmemBwd, st, in, off, mask, gout, acc, goff, gmask, q, tiles_x, tiles_y, GQ, sel);
     }
     return 0;
 }
@@ -249,9 +271,8 @@ int forward_t(const void *in_, const void *off_, const void *mask_, void *out_, 
             const unsigned grid = blocks_for(pl.total_vec);
             const bool k9 = (q.kh == 3 && q.kw == 3);
 #define LAUNCH_FWD(BPL, KP, LG)                                                               \
-    fwd_vec_kernel<T, BPL, KP, LG><<<grid, kThreads, 0, st>>>(in, off, mask, out, q,          \
-                                                              pl.vec_per_pix, pl.lanes_per_group, \
-                                                              pl.total_vec)
+    launch(fwd_vec_kernel<T, BPL, KP, LG>, grid, kThreads, 0, st, in, off, mask, out, q,      \
+           pl.vec_per_pix, pl.lanes_per_group, pl.total_vec)
 #define LAUNCH_FWD_B(BPL)                      \
     if (k9 && logits) LAUNCH_FWD(BPL, 9, true); \
     else if (k9) LAUNCH_FWD(BPL, 9, false);     \
@@ -346,13 +367,14 @@ int backward_launch(const T *in, const T *off, const T *mask, const T *gout, A *
     if constexpr (sizeof(T) <= 4) {
         if (pl.vec) {
             const unsigned n_blocks = blocks_for(pl.total_vec);
-            const unsigned per_cta = sel ? 4u : 1u;  // selector-guarded launch: fewer, fatter CTAs
+            // selector-guarded launch: about three CTAs per SM that walk the logical blocks, so that a
+            // launch the selector turns into a no-op costs one resident wave, not thousands of CTAs
+            const unsigned per_cta = sel ? (n_blocks + 148u * 3u - 1u) / (148u * 3u) : 1u;
             const unsigned grid = (n_blocks + per_cta - 1) / per_cta;
             const bool k9 = (q.kh == 3 && q.kw == 3);
 #define LAUNCH_BWD(BPL, KP, LG)                                                                  \
-    bwd_vec_kernel<T, A, BPL, KP, LG><<<grid, kThreads, 0, st>>>(in, off, mask, gout, acc, goff, \
-                                                                 gmask, q, pl.vec_per_pix,       \
-                                                                 pl.lanes_per_group, pl.total_vec, sel, per_cta, n_blocks)
+    launch(bwd_vec_kernel<T, A, BPL, KP, LG>, grid, kThreads, 0, st, in, off, mask, gout, acc, goff, \
+           gmask, q, pl.vec_per_pix, pl.lanes_per_group, pl.total_vec, sel, per_cta, n_blocks)
 #define LAUNCH_BWD_B(BPL)                      \
     if (k9 && logits) LAUNCH_BWD(BPL, 9, true); \
     else if (k9) LAUNCH_BWD(BPL, 9, false);     \
@@ -419,7 +441,7 @@ int backward_t(const void *in_, const void *off_, const void *mask_, const void 
                 }
             }
             if constexpr (lowp) {
-                // Default for eligible shapes: a 16 K-sample look at the offsets picks the family on
+                // Default for eligible shapes: a 2 K-sample look at the offsets picks the family on
                 // the device (imat::select_kernel); both kernels are launched, one returns at once.
                 // DCNV3_B200_BWD=vec|imat forces one (no selector).
                 const int fam = family_knob("DCNV3_B200_BWD");
@@ -429,8 +451,8 @@ int backward_t(const void *in_, const void *off_, const void *mask_, const void 
                     int *sel = nullptr;
                     if (fam == 0 && pl.vec) sel = reinterpret_cast<int *>(static_cast<char *>(ws) + acc_bytes);
                     // zero fill of the accumulators (the memset) with the selector riding along in block 0
-                    imat::zero_select_kernel<T><<<148 * 4, imat::kSelThreads, 0, st>>>(
-                        reinterpret_cast<uint4 *>(acc), acc_bytes / 16, off, (unsigned long long)n_pix * q.G * q.P, q.scale, sel);
+                    launch(imat::zero_select_kernel<T>, 148 * 4, imat::kSelThreads, 0, st,
+                           reinterpret_cast<uint4 *>(acc), acc_bytes / 16, off, (unsigned long long)n_pix * q.G * q.P, q.scale, sel);
                     zeroed = true;
                     rc = launch_bwd_imat<T>(in, off, mask, gout, acc, goff, gmask, q, logits, sel, st);
                     if (!rc && sel) rc = backward_launch<T, float>(in, off, mask, gout, acc, goff, gmask, q, logits, pl, n_pix, st, sel);
@@ -449,7 +471,7 @@ int backward_t(const void *in_, const void *off_, const void *mask_, const void 
         if constexpr (lowp) {
             const bool v8 = aligned16(gin_);
             const size_t n8 = v8 ? n_in / 8 : 0;
-            cast_ws_kernel<T><<<blocks_for(n8 + 1), kThreads, 0, st>>>(acc, gin, n8, n_in);
+            launch(cast_ws_kernel<T>, blocks_for(n8 + 1), kThreads, 0, st, (const float *)acc, gin, n8, n_in);
         }
         return 0;
     }

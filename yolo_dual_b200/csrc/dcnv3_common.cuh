@@ -178,6 +178,18 @@ __device__ __forceinline__ void atomic_add(double *p, double v) { atomicAdd(p, v
 __device__ __forceinline__ void atomic_add(__half *p, float v) { atomicAdd(p, __float2half_rn(v)); }
 __device__ __forceinline__ void atomic_add(__nv_bfloat16 *p, float v) { atomicAdd(p, __float2bfloat16_rn(v)); }
 
+// ---------------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+).  Every kernel of the vector / imat families starts with
+// pdl_enter(): wait until the previous kernel of the stream has completed and its writes are visible,
+// then let the NEXT kernel of the stream be scheduled early (its CTAs sit in their own wait).  Because
+// every kernel waits before it touches memory the chain is transitive and behaves exactly like plain
+// stream order; what is saved is the launch latency between the 3-4 short kernels of one backward.
+// Both instructions are no-ops when the kernel was launched without the attribute.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_release(); }
+
 template <typename M> __device__ __forceinline__ M shfl_xor(M v, int m) {
     return __shfl_xor_sync(0xffffffffu, v, m);
 }

@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(32 * kWarps, 2)
 fwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
                 T *__restrict__ out, const Geo q, const int tiles_x, const int tiles_y, const int GQ) {
     extern __shared__ __align__(128) unsigned char smem[];
+    pdl_enter();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TileCoord tc = decode_tile(blockIdx.x, tiles_x, tiles_y, GQ);
     const int g = tc.gq * kWarps + warp;
@@ -424,18 +425,22 @@ fwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
 // ---------------------------------------------------------------------------------------------
 // Family selector.  The imat backward is ~1.7x faster than the vector kernel while the sampling
 // points stay inside the staged window, and slower once more than ~1 in 7 leave it (each one is a
-// divergent trip through global memory).  This kernel looks at 16 K offset pairs spread over the
+// divergent trip through global memory).  This kernel looks at 2 K offset pairs spread over the
 // tensor and writes which family runs; both kernels are launched and the other one returns at once.
 // A point is out of window when |(i - 1 + off) * scale| >= 4 (x: i = p / 3; y: j = p % 3).
 // ---------------------------------------------------------------------------------------------
 constexpr int kSelVec = 1, kSelImat = 3;
-constexpr int kSelThreads = 1024, kSelPerThread = 16, kSelMaxSlowPct = 6;
+// 2 K samples: block 0 is ONE SM, and its load/store unit takes the scattered 4-byte loads one lane per
+// cycle, so 16 K samples cost ~10 us of latency in front of a 3-10 us zero fill; 2 K decide the same
+// question (6 % +- 0.5 %).
+constexpr int kSelThreads = 1024, kSelPerThread = 2, kSelMaxSlowPct = 6;
 // Zero fill of the fp32 workspace (replaces cudaMemsetAsync) with the selector riding along in block
-// 0: 16 independent samples per thread, one round trip to memory, no cross-block traffic.
+// 0: independent samples per thread, one round trip to memory, no cross-block traffic.
 template <typename T>
 __global__ void __launch_bounds__(kSelThreads)
 zero_select_kernel(uint4 *__restrict__ ws, const size_t n16, const T *__restrict__ off,
                    const unsigned long long n_points, const float scale, int *__restrict__ sel) {
+    pdl_enter();
     if (blockIdx.x == 0 && sel != nullptr) {
         __shared__ int cnt;
         if (threadIdx.x == 0) cnt = 0;
@@ -600,6 +605,7 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
                 T *__restrict__ gmask, const Geo q, const int tiles_x, const int tiles_y, const int GQ,
                 const int *__restrict__ sel) {
     extern __shared__ __align__(128) unsigned char smem[];
+    pdl_enter();
     if (sel != nullptr && *sel != kSelImat) return;  // select_kernel chose the vector family
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TileCoord tc = decode_tile(blockIdx.x, tiles_x, tiles_y, GQ);

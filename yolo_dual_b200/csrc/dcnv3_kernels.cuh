@@ -148,6 +148,7 @@ fwd_vec_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                T *__restrict__ out, const Geo q, const int vec_per_pix,
                const int lanes_per_group, const unsigned total) {
     constexpr int CH = Lane<T, BPL>::CH, NP = Lane<T, BPL>::NP;
+    pdl_enter();
     const unsigned idx = blockIdx.x * (unsigned)kThreads + threadIdx.x;
     if (idx >= total) return;
     const VecCoord c = decode_vec(idx, q, vec_per_pix, lanes_per_group);
@@ -428,6 +429,7 @@ bwd_vec_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                T *__restrict__ gmask, const Geo q, const int vec_per_pix,
                const int lanes_per_group, const unsigned total, const int *__restrict__ sel = nullptr,
                const unsigned per_cta = 1, const unsigned n_blocks = 0) {
+    pdl_enter();
     if (sel != nullptr && *sel != 1) return;
     if (per_cta == 1) {
         bwd_vec_body<T, A, BPL, KP, LOGITS>(blockIdx.x, in, off, mask, gout, gin, goff, gmask, q, vec_per_pix, lanes_per_group, total);
@@ -442,6 +444,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 cast_ws_kernel(const float *__restrict__ ws, T *__restrict__ dst, const size_t n_vec8,
                const size_t n_total) {
+    pdl_enter();
     const size_t i = blockIdx.x * (size_t)kThreads + threadIdx.x;
     if (i < n_vec8) {
         const float4 a = *reinterpret_cast<const float4 *>(ws + i * 8);
