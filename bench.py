@@ -251,7 +251,7 @@ def time_e2e(wl, steps, warmup, dist):
     """Same step through the public API with HOST buffers: yolo_dual_b200.host.HostPipeline drives
     DCNv3Function.apply + autograd; every step copies its inputs from pinned host memory and writes
     every result (output + three grads per site) back to pinned host memory.  Copies in, kernels and
-    copies out run on three streams (PCIe is full duplex), two steps in flight."""
+    copies out run on three streams (PCIe is full duplex), three steps in flight."""
     from yolo_dual_b200.host import HostPipeline, HostSite
     from yolo_dual_b200.ops_dcnv3.functions import set_grad_accum
     set_grad_accum("opmath" if wl.accum == 0 else "storage")
@@ -263,7 +263,7 @@ def time_e2e(wl, steps, warmup, dist):
         sites.append(hs.alloc_outputs(tuple(b.output.shape)))
     h2d = sum(s.h2d_bytes for s in sites)
     d2h = sum(s.d2h_bytes for s in sites)
-    pipe = HostPipeline(wl.dev, depth=2, fused_softmax=bool(wl.logits))
+    pipe = HostPipeline(wl.dev, depth=3, fused_softmax=bool(wl.logits))
     for _ in range(warmup):
         pipe.submit(sites)
     pipe.drain()
@@ -510,7 +510,7 @@ def main():
                "steps": a.e2e_steps,
                "api": "yolo_dual_b200.host.HostPipeline -> DCNv3Function.apply + autograd on pinned host tensors; "
                       "H2D of input/offset/mask/grad_out and D2H of output + 3 grads every step, copies and kernels "
-                      "on three streams, two steps in flight"}
+                      "on three streams, three steps in flight"}
     seg_res = None
     if not a.no_seg:
         del wl

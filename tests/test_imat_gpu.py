@@ -7,8 +7,10 @@ than one tile, pad 0, offset_scale != 1, G = 4 ... 32, offsets far outside the s
 per-lane global-memory path: the reference test's own `rand*10` distribution), fused softmax.
 
 Tolerance: bf16/fp16 rtol 1e-2, atol 2e-3 after scaling by max|ref| (north_star).  The products run on
-the tensor cores with TF32 interpolation weights (2^-11 relative) and exact 16-bit activations, fp32
-accumulation; grad_input additionally sums per-tile partial windows with fp32 reductions.
+the tensor cores with fp16 interpolation weights (2^-11 relative) and exact 16-bit activations, fp32
+accumulation; grad_input additionally sums per-tile partial windows with fp32 reductions.  For bf16
+storage grad_output enters that product scaled by a power of two per (tile, group) so that it fits
+fp16 (`test_imat_bf16_gradient_range` drives the scaling through tiny, huge and mixed magnitudes).
 """
 import pytest
 import torch
@@ -120,3 +122,41 @@ def test_imat_is_the_default_backward_and_adjoint_holds(monkeypatch):
     assert abs(lhs - rhs) <= 2e-3 * max(abs(lhs), abs(rhs), float(N * H * W)), (lhs, rhs)
     rhs_m = float((gm.double() * mb).sum())  # and <grad_mask, mask> = <go, f>
     assert abs(lhs - rhs_m) <= 2e-3 * max(abs(lhs), abs(rhs_m), float(N * H * W)), (lhs, rhs_m)
+
+
+@pytest.mark.parametrize("mode", ["tiny", "huge", "rows_mixed", "outlier_pixel"])
+def test_imat_bf16_gradient_range(mode, pixel_oracle, monkeypatch):
+    """bf16 grad_output spans far more than fp16's range; the imat backward rescales it by a power of two per
+    (tile, group) and, when a later pass of a tile is > 2^14 larger than an earlier one, rescales its
+    accumulators.  grad_input must stay within the bf16 bar relative to max|ref| in every regime, and
+    grad_offset / grad_mask (which never see the scaling) as always."""
+    from oracle.dcnv3_oracle import make_inputs
+    from yolo_dual_b200.ops_dcnv3.functions import DCNv3Function
+    monkeypatch.setenv("DCNV3_B200_BWD", "imat")
+    N, H, W, G, gc = 1, 16, 16, 4, 16
+    args = (3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0)
+    x, off, m, go = make_inputs(N, H, W, G, gc, 3, 3, 1, 1, 1, 1, 1, 1, dist="unit", seed=11)
+    if mode == "tiny":
+        go = go * 1e-30
+    elif mode == "huge":
+        go = go * 1e30
+    elif mode == "rows_mixed":      # upper half of every tile (pass 0) tiny, lower half (pass 1) 2^40 larger
+        rows = torch.arange(H) % 8 < 4
+        go = go * torch.where(rows, 2.0 ** -30, 2.0 ** 10).view(1, H, 1, 1)
+    else:                           # one pixel 2^20 above its neighbours
+        go = go * 2.0 ** -10
+        go[0, 5, 6] *= 2.0 ** 20
+    dtype = torch.bfloat16
+    xr, offr, mr, gor = (t.to(dtype).float() for t in (x, off, m, go))
+    want = list(pixel_oracle.backward(xr, offr, mr, gor, *args))
+    got = _run(DCNv3Function, x, off, m, go, args, dtype)[1:]
+    for g_, w_, name in zip(got, want, ("grad_input", "grad_offset", "grad_mask")):
+        assert torch.isfinite(g_).all(), name
+        scale = float(w_.abs().max())
+        torch.testing.assert_close(g_.double() / scale, w_.double() / scale, rtol=1e-2, atol=2e-3,
+                                   msg=lambda s: f"{mode} {name}: {s}")
+    if mode == "rows_mixed":
+        # the small half is 2^-40 of the tile maximum: below fp16 after scaling, but the cells only IT reaches
+        # (window rows above the large half's reach) must not be garbage: absolute error stays below 2^-24 max
+        gi, wi = got[0].double(), want[0].double()
+        assert float((gi - wi).abs().max()) <= 2.0 ** -8 * float(wi.abs().max())

@@ -23,6 +23,8 @@
 // Reference semantics: dcnv3_im2col_gpu_kernel :216-275 + dcnv3_im2col_bilinear :32-80.
 #pragma once
 
+#include <type_traits>
+
 #include "dcnv3_kernels.cuh"
 
 namespace dcnv3 {
@@ -38,6 +40,12 @@ constexpr int kWarps = 4;                // groups per CTA
 constexpr int kWinBytes = kWin * kWin * 128;       // 64 channels x 2 B per cell
 constexpr int kWmWords = 32 * kRow;                // one Wm buffer: 32 pixels
 constexpr int kSmemFwd = kWinBytes + kWarps * kWmWords * 4;
+// backward, pass B / mma #2: the interpolation matrix in the storage dtype inside the same per-warp buffer
+constexpr int kW16Stride = 400;                    // bytes per pixel row: 12 x 16 elements + 16 B skew
+constexpr int kW16Bytes = 32 * kW16Stride;         // 12800
+constexpr int kGoStride = 48;                      // grad_output rows behind it: 32 B + 16 B skew
+static_assert(kW16Bytes + 32 * kGoStride <= kWmWords * 4, "Wm16 + grad_output must fit the Wm buffer");
+static_assert(kW16Bytes % 512 == 0, "zero fill: whole 512-byte warp stores");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
@@ -112,6 +120,17 @@ template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, fl
 template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+// packed add of two storage-dtype pairs, round to nearest (HADD2 / HADD2.BF16)
+template <typename T> __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b);
+template <> __device__ __forceinline__ uint32_t add2<__nv_bfloat16>(uint32_t a, uint32_t b) {
+    const __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162 *>(&a), *reinterpret_cast<const __nv_bfloat162 *>(&b));
+    return *reinterpret_cast<const uint32_t *>(&r);
+}
+template <> __device__ __forceinline__ uint32_t add2<__half>(uint32_t a, uint32_t b) {
+    const __half2 r = __hadd2(*reinterpret_cast<const __half2 *>(&a), *reinterpret_cast<const __half2 *>(&b));
+    return *reinterpret_cast<const uint32_t *>(&r);
 }
 
 // 16-byte chunk swizzle of the window: chunk' = chunk ^ key(cell); 8 consecutive cells of a
@@ -567,34 +586,71 @@ __device__ __noinline__ PtResA bwd_point_slow(const PtGeo pg, const float p0h_, 
     return r;
 }
 
-// pass A of one point: corner dots from D (or the slow path), grad_offset / grad_mask terms, and the
-// cell + fractions pass B reuses
+// pass A of one kernel column (three points p = 3i + j, j = 0..2): corner dots from D (or the slow
+// path), grad_offset / grad_mask terms, and the cell + fractions pass B reuses.  Three points per call
+// so that their location chains and the twelve D look-ups overlap (one point at a time was a serial
+// chain of locate -> 4 shared loads -> math per point: 20 % of the kernel's stall samples); the
+// look-ups are unconditional at a clamped cell so that no branch separates them.
+struct PtRes3 { uint32_t off[3]; float m[3]; uint32_t frac[3]; uint32_t kq; };  // kq: 3 x (Wm16 element | 256 when in-window), 10 bits each
 template <typename T>
-__device__ __noinline__ PtResA bwd_point_a(const PtGeo pg, const float p0h_, const float p0w_, const int p,
-                                           const float fi, const float fj, const uint32_t offw, const float m,
-                                           const float *Drow, const int sy0, const int sx0, const T *img_g,
-                                           float *gacc_g, const int C) {
-    const float2 o = unpack2f<T>(offw);
-    const LeanPoint t = locate_lean(pg, p0h_, p0w_, fi, fj, o.x, o.y);
-    if (!t.inside) return PtResA{0u, 0.f, 0u, 0u};
-    const unsigned u = (unsigned)(t.w_low - sx0), v = (unsigned)(t.h_low - sy0);
-    if (u > (unsigned)(kSub - 2) || v > (unsigned)(kSub - 2))
-        return bwd_point_slow<T>(pg, p0h_, p0w_, p, offw, m, Drow, img_g, gacc_g, C);
-    PtResA r;
-    const unsigned k = v * kSub + u;
-    const float *c = Drow + k;
-    const float d0 = c[0], d1 = c[1], d2 = c[kSub], d3 = c[kSub + 1];
-    r.kq = 256u | k;
-    // fractions for pass B, truncated to 2^-16 (the weights there feed TF32 operands anyway)
-    r.frac = (__float2uint_rz(t.lh * 65536.f) << 16) | __float2uint_rz(t.lw * 65536.f);
-    const float hh = sub_rn(1.f, t.lh), hw = sub_rn(1.f, t.lw);
-    const float w1 = hh * hw, w2 = hh * t.lw, w3 = t.lh * hw, w4 = t.lh * t.lw;
-    const float s_m = w1 * d0 + w2 * d1 + w3 * d2 + w4 * d3;
-    const float s_w = hh * (d1 - d0) + t.lh * (d3 - d2);
-    const float s_h = hw * (d2 - d0) + t.lw * (d3 - d1);
-    const float sm = pg.scale * m;
-    r.off = pack2<T>(sm * s_w, sm * s_h);
-    r.m = s_m;
+__device__ __noinline__ PtRes3 bwd_points3_a(const PtGeo pg, const float p0h_, const float p0w_, const int i,
+                                             const uint32_t offw0, const uint32_t offw1, const uint32_t offw2,
+                                             const float m0, const float m1, const float m2, const float *Drow,
+                                             const int sy0, const int sx0, const int cshift, const T *img_g,
+                                             float *gacc_g, const int C) {
+    const uint32_t offw[3] = {offw0, offw1, offw2};
+    const float m[3] = {m0, m1, m2};
+    const float fi = (float)i;
+    LeanPoint t[3];
+    unsigned k[3], e16[3];
+    bool inwin[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float2 o = unpack2f<T>(offw[j]);
+        t[j] = locate_lean(pg, p0h_, p0w_, fi, (float)j, o.x, o.y);
+        const unsigned u = (unsigned)(t[j].w_low - sx0), v = (unsigned)(t[j].h_low - sy0);
+        inwin[j] = t[j].inside && u <= (unsigned)(kSub - 2) && v <= (unsigned)(kSub - 2);
+        k[j] = inwin[j] ? v * kSub + u : 0u;
+        e16[j] = v * kWin + u + cshift;  // element of the pixel's Wm16 row: sub-window row x window column
+    }
+    float d[3][4];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float *c = Drow + k[j];
+        d[j][0] = c[0]; d[j][1] = c[1]; d[j][2] = c[kSub]; d[j][3] = c[kSub + 1];
+    }
+    PtRes3 r;
+    r.kq = 0u;
+    unsigned slow = 0u;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        slow |= (t[j].inside && !inwin[j] ? 1u : 0u) << j;
+        const float lh = t[j].lh, lw = t[j].lw;
+        const float hh = sub_rn(1.f, lh), hw = sub_rn(1.f, lw);
+        const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+        const float s_m = w1 * d[j][0] + w2 * d[j][1] + w3 * d[j][2] + w4 * d[j][3];
+        const float s_w = hh * (d[j][1] - d[j][0]) + lh * (d[j][3] - d[j][2]);
+        const float s_h = hw * (d[j][2] - d[j][0]) + lw * (d[j][3] - d[j][1]);
+        const float sm = pg.scale * m[j];
+        r.off[j] = inwin[j] ? pack2<T>(sm * s_w, sm * s_h) : 0u;
+        r.m[j] = inwin[j] ? s_m : 0.f;
+        // fractions for pass B, truncated to 2^-16 (the weights there feed TF32 operands anyway)
+        r.frac[j] = (__float2uint_rz(lh * 65536.f) << 16) | __float2uint_rz(lw * 65536.f);
+        r.kq |= (inwin[j] ? (256u | e16[j]) : 0u) << (10 * j);
+    }
+    if (slow)
+#pragma unroll 1
+    for (int j = 0; j < 3; ++j) {
+        if ((slow >> j) & 1u) {  // rare: |offset * scale| >= 3 px
+            uint32_t ow = offw0; float mm = m0;
+            if (j == 1) { ow = offw1; mm = m1; }
+            if (j == 2) { ow = offw2; mm = m2; }
+            const PtResA s = bwd_point_slow<T>(pg, p0h_, p0w_, 3 * i + j, ow, mm, Drow, img_g, gacc_g, C);
+            if (j == 0) { r.off[0] = s.off; r.m[0] = s.m; }
+            if (j == 1) { r.off[1] = s.off; r.m[1] = s.m; }
+            if (j == 2) { r.off[2] = s.off; r.m[2] = s.m; }
+        }
+    }
     return r;
 }
 
@@ -634,6 +690,8 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
     const int jm = lane >> 3, jr = lane & 7;
 
     // grad_input window of this (tile, group): 16 rows x (16 cells x 16 channels) as mma accumulators
+    constexpr bool kScaled = sizeof(T) == 2 && !std::is_same<T, __half>::value;  // bf16: see pass B
+    int e_ref = -1;
     float gw[kWin][2][4];
 #pragma unroll
     for (int r = 0; r < kWin; ++r)
@@ -657,8 +715,6 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
             io1 |= (c.oy + 4 < q.Ho && c.ox < q.Wo ? 1u : 0u) << i;
         }
     }
-    float *zero16 = reinterpret_cast<float *>(smem + kSmemFwd);
-    if (tid < 4) zero16[tid] = 0.f;
 
     bool window_ready = false;
 #pragma unroll
@@ -778,12 +834,19 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
             res_off[p] = 0u;
             res_m[p] = 0.f;
             frac[p] = 0u;
-            if (pc.valid) {
-                const PtResA r = bwd_point_a<T>(pg, p0h_, p0w_, p, (float)(p / 3), (float)(p % 3), myoff[p], mym[p], Wrow, sy0, sx0, img_g, gacc_g, q.C);
-                res_off[p] = r.off;
-                res_m[p] = r.m;
-                frac[p] = r.frac;
-                kq[p / 3] |= r.kq << (10 * (p % 3));
+        }
+        if (pc.valid) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const PtRes3 r = bwd_points3_a<T>(pg, p0h_, p0w_, i, myoff[3 * i], myoff[3 * i + 1], myoff[3 * i + 2],
+                                                  mym[3 * i], mym[3 * i + 1], mym[3 * i + 2], Wrow, sy0, sx0, 4 * (lane >> 4), img_g, gacc_g, q.C);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    res_off[3 * i + j] = r.off[j];
+                    res_m[3 * i + j] = r.m[j];
+                    frac[3 * i + j] = r.frac[j];
+                }
+                kq[i] = r.kq;
             }
         }
         if (LOGITS) {  // softmax Jacobian: dl_p = m_p (gm_p - sum_q m_q gm_q)
@@ -809,62 +872,107 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
         }
         __syncwarp();
 
-        // ---- pass B: Wm[pixel][cell] += corner weight * mask (rows' pads keep grad_output)
-        {   // zero words 0..143 of the 32 rows: 32 float4 of a row per instruction, then the last 4
-            float4 *W4 = reinterpret_cast<float4 *>(Wm);
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        // ---- pass B: the interpolation matrix in 16 bits.  Wm16[pixel][sub-window row][window
+        // column] (12 x 16 elements = 384 B of a 400-byte row: the 16-byte skew makes the eight rows of
+        // every ldmatrix hit distinct banks) replaces the fp32 [pixel][144] matrix: 12.5 KB to zero instead
+        // of 18 KB, and mma #2 reads it with ONE ldmatrix.trans per window row (16 cells x 16 pixels)
+        // instead of 8 scalar loads, with K = 16 pixels per m16n8k16.  The matrix is fp16 for both storage
+        // dtypes (11-bit weights, what TF32 gave); accumulation stays fp32.
+        // The window column is absolute (0..15), so sub-tile 0 never touches columns 12-15 and sub-tile
+        // 1 never columns 0-3: they stay zero and no operand masking is needed.
+        unsigned char *W16 = reinterpret_cast<unsigned char *>(Wm);
+        {
+            // this pixel's grad_output moves out of the D-layout pad (the zero fill runs over it)
+            uint4 g0 = *reinterpret_cast<const uint4 *>(Wrow + kCells);
+            uint4 g1 = *reinterpret_cast<const uint4 *>(Wrow + kCells + 4);
+            if constexpr (kScaled) {
+                // bf16 storage: mma #2 runs in fp16 (weights keep 11 bits, as TF32 did), so grad_output is
+                // brought into fp16 range by a power of two per (tile, group): go' = go * 2^(127 - e_ref)
+                // with e_ref the biased exponent of the largest |go| seen so far.  Exact for every value
+                // within 2^-14 of that maximum (smaller ones lose low bits: an absolute error below
+                // 2^-24 of the tile's largest gradient).  A later pass that would overflow fp16 rescales
+                // the accumulators instead (online max, warp-uniform, rare).
+                uint32_t w[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                uint32_t mx = 0u;
 #pragma unroll
-            for (int r = 0; r < 32; ++r) W4[r * (kRow / 4) + lane] = z;
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t a = w[c] & 0x7fff7fffu;  // |bf16| compares like an integer
+                    mx = max(mx, max(a >> 16, a & 0xffffu));
+                }
+                mx = __reduce_max_sync(0xffffffffu, mx);
+                const int e = min(max((int)(mx >> 7), 1), 253);
+                if (e_ref < 0) {
+                    e_ref = e;
+                } else if (e > e_ref + 14) {
+                    const int d = e_ref - e;  // < -14
+                    const float f = d >= -126 ? __uint_as_float((uint32_t)(127 + d) << 23) : 0.f;
 #pragma unroll
-            for (int r = 0; r < 4; ++r) W4[(8 * r + (lane >> 2)) * (kRow / 4) + 32 + (lane & 3)] = z;
+                    for (int r = 0; r < kWin; ++r)
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) gw[r][nt][c] *= f;
+                    e_ref = e;
+                }
+                const float sc = __uint_as_float((uint32_t)(254 - e_ref) << 23);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float2 f = unpack2f<T>(w[c]);
+                    w[c] = pack2<__half>(f.x * sc, f.y * sc);
+                }
+                g0 = make_uint4(w[0], w[1], w[2], w[3]);
+                g1 = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+            __syncwarp();
+            uint4 *Z = reinterpret_cast<uint4 *>(W16);
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int r = 0; r < kW16Bytes / 512; ++r) Z[r * 32 + lane] = z;
+            uint4 *G = reinterpret_cast<uint4 *>(W16 + kW16Bytes + lane * kGoStride);
+            G[0] = g0;
+            G[1] = g1;
         }
         __syncwarp();
+        {
+            uint32_t *R32 = reinterpret_cast<uint32_t *>(W16 + lane * kW16Stride);
 #pragma unroll
-        for (int p = 0; p < 9; ++p) {
-            const uint32_t e = kq[p / 3] >> (10 * (p % 3));
-            if (e & 256u) {
-                const float lh = (float)(frac[p] >> 16) * (1.f / 65536.f), lw = (float)(frac[p] & 0xffffu) * (1.f / 65536.f);
-                const float hm = (1.f - lh) * mym[p], lm = lh * mym[p], hw = 1.f - lw;
-                float *c = Wrow + (e & 255u);
-                c[0] += hm * hw;
-                c[1] += hm * lw;
-                c[kSub] += lm * hw;
-                c[kSub + 1] += lm * lw;
+            for (int p = 0; p < 9; ++p) {
+                const uint32_t e = kq[p / 3] >> (10 * (p % 3));
+                if (e & 256u) {
+                    const float lh = (float)(frac[p] >> 16) * (1.f / 65536.f), lw = (float)(frac[p] & 0xffffu) * (1.f / 65536.f);
+                    const float hm = (1.f - lh) * mym[p], lm = lh * mym[p], hw = 1.f - lw;
+                    // the two corners of a row are adjacent elements: one packed add when the left one is
+                    // even, else the pair straddles two words (the funnel shift splits it; adding 0 is free)
+                    const uint32_t top = pack2<__half>(hm * hw, hm * lw), bot = pack2<__half>(lm * hw, lm * lw);
+                    const uint32_t sh = (e & 1u) << 4;
+                    uint32_t *w = R32 + ((e & 255u) >> 1);
+                    w[0] = add2<__half>(w[0], top << sh);
+                    w[1] = add2<__half>(w[1], __funnelshift_l(top, 0u, sh));
+                    w[kWin / 2] = add2<__half>(w[kWin / 2], bot << sh);
+                    w[kWin / 2 + 1] = add2<__half>(w[kWin / 2 + 1], __funnelshift_l(bot, 0u, sh));
+                }
             }
         }
         __syncwarp();
 
-        // ---- mma #2: gw[window row][ch] += Wm^T * go, per sub-tile; m-tile = one window row
+        // ---- mma #2: gw[window row][ch] += Wm16^T * go, per sub-tile; m-tile = one window row (16 cells),
+        // K = the 16 pixels of the sub-tile, both operands in the storage dtype (m16n8k16)
+        {
+            const uint32_t w16_s = smem_u32(W16);
 #pragma unroll 1
-        for (int s = 0; s < n_sub; ++s) {
-            uint32_t b[2][2][2];  // [k8 step][n-tile][2]
-            {
-                uint32_t r0, r1, r2, r3;  // matrix jm = (k8 step jm >> 1, n-tile jm & 1); row jr <-> pixel (jr >> 1) + 4 (jr & 1)
-                ldmatrix_x4_trans(r0, r1, r2, r3,
-                                  wm_s + ((16 * s + 8 * (jm >> 1) + (jr >> 1) + 4 * (jr & 1)) * kRow + kCells) * 4 + (jm & 1) * 16);
-                unpack2<T>(r0, b[0][0][0], b[0][0][1]);
-                unpack2<T>(r1, b[0][1][0], b[0][1][1]);
-                unpack2<T>(r2, b[1][0][0], b[1][0][1]);
-                unpack2<T>(r3, b[1][1][0], b[1][1][1]);
-            }
-            // A(cell col, pixel): a0/a2 use window column gID, a1/a3 column gID + 8; the sub-window
-            // spans columns 4s .. 4s+11
-            const bool lo_ok = (s == 1) ? (gID >= 4) : true;
-            const bool hi_ok = (s == 0) ? (gID <= 3) : true;
-#pragma unroll
-            for (int k8 = 0; k8 < 2; ++k8) {
-                // masked lanes read the shared zero word (stride 0): no selects in the loop
-                const float *Wp = Wm + (16 * s + 8 * k8 + tq) * kRow;
-                const float *Plo = lo_ok ? Wp + gID - 4 * s : zero16;
-                const float *Phi = hi_ok ? Wp + gID + 8 - 4 * s : zero16;
-                const int st_lo = lo_ok ? kSub : 0, st_hi = hi_ok ? kSub : 0;
-                const int up_lo = lo_ok ? 4 * kRow : 0, up_hi = hi_ok ? 4 * kRow : 0;
+            for (int s = 0; s < n_sub; ++s) {
+                // B = go [16 px x 16 ch]: matrix jm = (px 8(jm & 1).., ch 8(jm >> 1)..)
+                uint32_t b00, b01, b10, b11;  // n-tile 0: (k 0-7, k 8-15); n-tile 1: (k 0-7, k 8-15)
+                ldmatrix_x4_trans(b00, b01, b10, b11,
+                                  w16_s + kW16Bytes + (16 * s + 8 * (jm & 1) + jr) * kGoStride + (jm >> 1) * 16);
+                // A = Wm16^T [16 cells x 16 px]: matrix jm = (cells 8(jm & 1).., px 8(jm >> 1)..)
+                const uint32_t abase = w16_s + (16 * s + 8 * (jm >> 1) + jr) * kW16Stride + (jm & 1) * 16;
 #pragma unroll
                 for (int rr = 0; rr < kSub; ++rr) {
-                    const float a0 = Plo[rr * st_lo], a1 = Phi[rr * st_hi];
-                    const float a2 = Plo[rr * st_lo + up_lo], a3 = Phi[rr * st_hi + up_hi];
-                    mma_tf32(gw[4 * pass + rr][0], __float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(a3), b[k8][0][0], b[k8][0][1]);
-                    mma_tf32(gw[4 * pass + rr][1], __float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(a3), b[k8][1][0], b[k8][1][1]);
+                    uint32_t a0, a1, a2, a3;
+                    ldmatrix_x4_trans(a0, a1, a2, a3, abase + rr * (kWin * 2));
+                    mma_16816<__half>(gw[4 * pass + rr][0], a0, a1, a2, a3, b00, b01);
+                    mma_16816<__half>(gw[4 * pass + rr][1], a0, a1, a2, a3, b10, b11);
                 }
             }
         }
@@ -892,11 +1000,16 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
         const long long row_stride = (long long)q.W * q.C;
         float *dst0 = gacc_g + ((long long)wy0 * q.W + ix0) * q.C + 4 * j;
         const float *src = GW + c8 * 16 + ((j ^ (((c8 >> 1) & 1) << 1)) << 2);
+        const float unscale = __uint_as_float((uint32_t)max(e_ref, 1) << 23);  // 2^(e_ref - 127), bf16 storage only
 #pragma unroll 4
         for (int r = 0; r < kWin; ++r) {
             const bool row_ok = (unsigned)(wy0 + r) < (unsigned)q.H;
-            const float4 v0 = *reinterpret_cast<const float4 *>(src + r * (kWin * 16));
-            const float4 v1 = *reinterpret_cast<const float4 *>(src + r * (kWin * 16) + 8 * 16);
+            float4 v0 = *reinterpret_cast<const float4 *>(src + r * (kWin * 16));
+            float4 v1 = *reinterpret_cast<const float4 *>(src + r * (kWin * 16) + 8 * 16);
+            if constexpr (kScaled) {
+                v0.x *= unscale; v0.y *= unscale; v0.z *= unscale; v0.w *= unscale;
+                v1.x *= unscale; v1.y *= unscale; v1.z *= unscale; v1.w *= unscale;
+            }
             const bool nz0 = ((__float_as_uint(v0.x) | __float_as_uint(v0.y) | __float_as_uint(v0.z) | __float_as_uint(v0.w)) << 1) != 0u;
             const bool nz1 = ((__float_as_uint(v1.x) | __float_as_uint(v1.y) | __float_as_uint(v1.z) | __float_as_uint(v1.w)) << 1) != 0u;
             float *d = dst0 + r * row_stride;

@@ -56,7 +56,7 @@ class HostSite:
 
 
 class HostPipeline:
-    def __init__(self, device, depth: int = 2, fused_softmax: bool = False):
+    def __init__(self, device, depth: int = 3, fused_softmax: bool = False):
         self.device = torch.device(device)
         self.depth = depth
         self.fn = DCNv3SoftmaxFunction if fused_softmax else DCNv3Function
