@@ -124,7 +124,7 @@ def test_imat_is_the_default_backward_and_adjoint_holds(monkeypatch):
     assert abs(lhs - rhs_m) <= 2e-3 * max(abs(lhs), abs(rhs_m), float(N * H * W)), (lhs, rhs_m)
 
 
-@pytest.mark.parametrize("mode", ["tiny", "huge", "rows_mixed", "outlier_pixel"])
+@pytest.mark.parametrize("mode", ["tiny", "huge", "rows_mixed", "rows_mixed_rev", "outlier_pixel"])
 def test_imat_bf16_gradient_range(mode, pixel_oracle, monkeypatch):
     """bf16 grad_output spans far more than fp16's range; the imat backward rescales it by a power of two per
     (tile, group) and, when a later pass of a tile is > 2^14 larger than an earlier one, rescales its
@@ -143,6 +143,9 @@ def test_imat_bf16_gradient_range(mode, pixel_oracle, monkeypatch):
     elif mode == "rows_mixed":      # upper half of every tile (pass 0) tiny, lower half (pass 1) 2^40 larger
         rows = torch.arange(H) % 8 < 4
         go = go * torch.where(rows, 2.0 ** -30, 2.0 ** 10).view(1, H, 1, 1)
+    elif mode == "rows_mixed_rev":  # the large half first: the small half underflows fp16 after scaling (by design)
+        rows = torch.arange(H) % 8 < 4
+        go = go * torch.where(rows, 2.0 ** 10, 2.0 ** -30).view(1, H, 1, 1)
     else:                           # one pixel 2^20 above its neighbours
         go = go * 2.0 ** -10
         go[0, 5, 6] *= 2.0 ** 20
