@@ -195,12 +195,13 @@ void launch(void (*kernel)(P...), unsigned grid, unsigned block, size_t smem, cu
 // Knobs: DCNV3_B200_FWD / DCNV3_B200_BWD = vec | imat force a family.  Defaults: the backward takes the
 // interpolation-matrix kernel when eligible (16-bit, gc = 16, 3x3 s1 d1, fp32 accumulation), the forward the
 // vector kernel (its imat variant is correct but slower: profiles/r01_imat.md).
-int family_knob(const char *name) {  // 0 default, 1 vec, 2 tile, 3 imat
+int family_knob(const char *name) {  // 0 default, 1 vec, 2 tile, 3 imat, 4 pts
     const char *e = getenv(name);
     if (!e) return 0;
     if (!strcmp(e, "vec")) return 1;
     if (!strcmp(e, "tile")) return 2;
     if (!strcmp(e, "imat")) return 3;
+    if (!strcmp(e, "pts")) return 4;
     return 0;
 }
 
@@ -264,6 +265,18 @@ int forward_t(const void *in_, const void *off_, const void *mask_, void *out_, 
         const int fam = family_knob("DCNV3_B200_FWD");
         if (fam == 3 && imat_eligible<T>(q, {in_, out_}, off_))
             return launch_fwd_imat<T>(in, off, mask, out, q, logits, st);
+        // opt-in (DCNV3_B200_FWD=pts): the point-split kernel — 25 % fewer instructions, measured SLOWER
+        // (P3 98.7 vs 82.3 us): a lane's 32-byte LDG.256 costs L1 two passes where the channel-split
+        // pair of 16-byte lanes shares one; the forward is bound by L1 wavefronts, not by issue slots
+        const unsigned long long lanes = (unsigned long long)n_pix * q.G * 2ull;
+        if (fam == 4 && q.gc == 16 && q.kh == 3 && q.kw == 3 && aligned_to(in_, 32) && aligned16(out_) &&
+            !(reinterpret_cast<uintptr_t>(off_) & 3u) && lanes < (1ull << 31) &&
+            (unsigned long long)q.H * q.W * q.C * 2ull < (1ull << 31)) {
+            const unsigned total = (unsigned)lanes;
+            if (logits) launch(fwd_pts_kernel<T, true>, blocks_for(total), kThreads, 0, st, in, off, mask, out, q, total);
+            else launch(fwd_pts_kernel<T, false>, blocks_for(total), kThreads, 0, st, in, off, mask, out, q, total);
+            return 0;
+        }
     }
     const Plan pl = plan_vec<T>(q, n_pix, logits, {in_, out_}, off_, sizeof(T));
     if constexpr (sizeof(T) <= 4) {

@@ -91,6 +91,25 @@ __device__ __forceinline__ void mma_16816<__half>(float (&c)[4], uint32_t a0, ui
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// D = A * B (zero accumulator input: no registers to clear per product)
+template <typename T>
+__device__ __forceinline__ void mma_16816_z(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                            uint32_t b0, uint32_t b1);
+template <>
+__device__ __forceinline__ void mma_16816_z<__nv_bfloat16>(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2,
+                                                           uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%10, %10, %10, %10};"
+                 : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+}
+template <>
+__device__ __forceinline__ void mma_16816_z<__half>(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                    uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%10, %10, %10, %10};"
+                 : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+}
+
 // two packed 16-bit storage values -> fp32 bit patterns (exact; both are valid TF32 operands)
 template <typename T> __device__ __forceinline__ void unpack2(uint32_t w, uint32_t &lo, uint32_t &hi);
 template <> __device__ __forceinline__ void unpack2<__nv_bfloat16>(uint32_t w, uint32_t &lo, uint32_t &hi) {
@@ -144,6 +163,29 @@ __device__ __forceinline__ TileCoord decode_tile(unsigned b, int tiles_x, int ti
     c.tx = (int)(b % (unsigned)tiles_x); b /= (unsigned)tiles_x;
     c.ty = (int)(b % (unsigned)tiles_y);
     c.n = (int)(b / (unsigned)tiles_y);
+    return c;
+}
+// Longest-first order for the backward: CTAs are dealt to SMs in blockIdx order and one CTA runs ~20 us, so a
+// map whose extent is not a multiple of 8 (P5: 20 x 20 -> 4 whole, 4 half and 1 quarter tile per image)
+// should start its whole tiles first and leave the cheap partial ones to fill the tail.  Classes: whole
+// tiles of all images, then right-edge column, bottom-edge row, corner.
+__device__ __forceinline__ TileCoord decode_tile_lpt(unsigned b, int Ho, int Wo, int N, int GQ) {
+    const unsigned fy = (unsigned)Ho / kTile, fx = (unsigned)Wo / kTile;
+    const unsigned ry = (Ho % kTile) ? 1u : 0u, rx = (Wo % kTile) ? 1u : 0u;
+    const unsigned nA = fy * fx * (unsigned)N, nB = fy * rx * (unsigned)N, nC = fx * ry * (unsigned)N;
+    TileCoord c;
+    c.gq = (int)(b % (unsigned)GQ); b /= (unsigned)GQ;
+    unsigned cls, pc;  // class and its tiles per image (non-zero in the class b falls into)
+    if (b < nA) { cls = 0; pc = fy * fx; }
+    else if ((b -= nA) < nB) { cls = 1; pc = fy; }
+    else if ((b -= nB) < nC) { cls = 2; pc = fx; }
+    else { b -= nC; cls = 3; pc = 1; }
+    const unsigned t = b % pc;
+    c.n = (int)(b / pc);
+    if (cls == 0) { c.ty = (int)(t / fx); c.tx = (int)(t % fx); }
+    else if (cls == 1) { c.ty = (int)t; c.tx = (int)fx; }
+    else if (cls == 2) { c.ty = (int)fy; c.tx = (int)t; }
+    else { c.ty = (int)fy; c.tx = (int)fx; }
     return c;
 }
 
@@ -664,7 +706,7 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
     pdl_enter();
     if (sel != nullptr && *sel != kSelImat) return;  // select_kernel chose the vector family
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const TileCoord tc = decode_tile(blockIdx.x, tiles_x, tiles_y, GQ);
+    const TileCoord tc = decode_tile_lpt(blockIdx.x, q.Ho, q.Wo, q.N, GQ);
     const int g = tc.gq * kWarps + warp;
     const int wy0 = tc.ty * kTile + (q.half_h - q.ph) - 4;
     const int wx0 = tc.tx * kTile + (q.half_w - q.pw) - 4;
@@ -802,20 +844,33 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
                 const int rr = kk / kSub, cc = kk - rr * kSub;
                 bo[r] = wbase + (rr * kWin + cc) * 128 + ((chunk ^ ((cc + 4 * rr) & 7)) << 4);
             }
-#pragma unroll 1
+            // software pipeline over the three groups of three k-steps: the ldmatrix of group m + 1 are in
+            // flight while group m multiplies and stores (every asm here is volatile, so program order is
+            // issue order: without this each mma waited out its own ldmatrix)
+            uint32_t fr[2][3][4];  // (cells 0-7, ch 0-7) (cells 0-7, ch 8-15) (cells 8-15, ch 0-7) (cells 8-15, ch 8-15)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) ldmatrix_x4(fr[0][r][0], fr[0][r][1], fr[0][r][2], fr[0][r][3], bo[r]);
+#pragma unroll
             for (int m = 0; m < 3; ++m) {
+                if (m < 2) {
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+                        ldmatrix_x4(fr[(m + 1) & 1][r][0], fr[(m + 1) & 1][r][1], fr[(m + 1) & 1][r][2], fr[(m + 1) & 1][r][3],
+                                    bo[r] + (m + 1) * (4 * kWin * 128));
+                }
+                float d[3][2][4];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    uint32_t r0, r1, r2, r3;  // (cells 0-7, ch 0-7) (cells 0-7, ch 8-15) (cells 8-15, ch 0-7) (cells 8-15, ch 8-15)
-                    ldmatrix_x4(r0, r1, r2, r3, bo[r] + m * (4 * kWin * 128));
-                    float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
-                    mma_16816<T>(d0, a0, a1, a2, a3, r0, r1);
-                    mma_16816<T>(d1, a0, a1, a2, a3, r2, r3);
+                    mma_16816_z<T>(d[r][0], a0, a1, a2, a3, fr[m & 1][r][0], fr[m & 1][r][1]);
+                    mma_16816_z<T>(d[r][1], a0, a1, a2, a3, fr[m & 1][r][2], fr[m & 1][r][3]);
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
                     float *Dk = D0 + 48 * m + 16 * r;
-                    *reinterpret_cast<float2 *>(Dk) = make_float2(d0[0], d0[1]);
-                    *reinterpret_cast<float2 *>(Dk + 8 * kRow) = make_float2(d0[2], d0[3]);
-                    *reinterpret_cast<float2 *>(Dk + 8) = make_float2(d1[0], d1[1]);
-                    *reinterpret_cast<float2 *>(Dk + 8 * kRow + 8) = make_float2(d1[2], d1[3]);
+                    *reinterpret_cast<float2 *>(Dk) = make_float2(d[r][0][0], d[r][0][1]);
+                    *reinterpret_cast<float2 *>(Dk + 8 * kRow) = make_float2(d[r][0][2], d[r][0][3]);
+                    *reinterpret_cast<float2 *>(Dk + 8) = make_float2(d[r][1][0], d[r][1][1]);
+                    *reinterpret_cast<float2 *>(Dk + 8 * kRow + 8) = make_float2(d[r][1][2], d[r][1][3]);
                 }
             }
         }
@@ -942,7 +997,8 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
                     const float lh = (float)(frac[p] >> 16) * (1.f / 65536.f), lw = (float)(frac[p] & 0xffffu) * (1.f / 65536.f);
                     const float hm = (1.f - lh) * mym[p], lm = lh * mym[p], hw = 1.f - lw;
                     // the two corners of a row are adjacent elements: one packed add when the left one is
-                    // even, else the pair straddles two words (the funnel shift splits it; adding 0 is free)
+                    // even, else the pair straddles two words (the funnel shift splits it; adding 0 is free;
+                    // predicating the second add on the parity was measured slower)
                     const uint32_t top = pack2<__half>(hm * hw, hm * lw), bot = pack2<__half>(lm * hw, lm * lw);
                     const uint32_t sh = (e & 1u) << 4;
                     uint32_t *w = R32 + ((e & 255u) >> 1);

@@ -210,6 +210,125 @@ fwd_vec_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
 }
 
 // ===========================================================================
+// forward, point-split path (16-bit storage, group_channels = 16, 3x3): the two lanes of a
+// (n, ho, wo, g) split the nine sampling POINTS instead of the sixteen channels.
+//
+// fwd_vec_kernel gives each of the two lanes 8 channels and lets both of them locate all nine points:
+// per point ~70 of its ~135 instructions are location / weight / address arithmetic that the partner
+// lane repeats (ncu: issue slots 77 % busy, the binding resource).  Here lane h takes points 4h..4h+3
+// with all 16 channels (one 32-byte LDG.256 per corner = the group's whole slab = one sector) and the
+// lanes share point 8 by channel halves; the partial sums meet in one shuffle exchange at the end.
+// 4.5 locates per lane instead of 9, the same number of sectors requested from L1.
+// Semantics and arithmetic per point are fwd_vec_kernel's (shared locate(), fp32 accumulation).
+// ===========================================================================
+template <typename T, bool LOGITS>
+__global__ void __launch_bounds__(kThreads)
+fwd_pts_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
+               T *__restrict__ out, const Geo q, const unsigned total) {
+    static_assert(sizeof(T) == 2, "point-split forward: 16-bit storage");
+    pdl_enter();
+    unsigned idx = blockIdx.x * (unsigned)kThreads + threadIdx.x;
+    const bool active = idx < total;  // tail lanes stay for the shuffle (total is even: pairs are whole)
+    if (!active) idx = total - 2u + (idx & 1u);
+    const unsigned unit = idx >> 1;  // (pixel, group)
+    const int h = (int)(idx & 1u);
+    const unsigned pix = unit / (unsigned)q.G;
+    const int g = (int)(unit - pix * (unsigned)q.G);
+    const unsigned row = pix / (unsigned)q.Wo;
+    const int wo = (int)(pix - row * (unsigned)q.Wo);
+    const int n = (int)(row / (unsigned)q.Ho);
+    const int ho = (int)(row - (unsigned)n * (unsigned)q.Ho);
+
+    float p0h_, p0w_;
+    window_origin<float>(q, ho, wo, p0h_, p0w_);
+    const char *im = reinterpret_cast<const char *>(in + (size_t)n * q.H * q.W * q.C + g * 16);
+    const int sC = q.C * 2, sW = q.W * sC;
+    const T *po = off + (size_t)unit * 18;
+    const T *pm = mask + (size_t)unit * 9;
+
+    float mx = 0.f, inv = 1.f;
+    if (LOGITS) softmax_stats<T, 9>(pm, 9, mx, inv);
+
+    float2 acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = make_float2(0.f, 0.f);
+
+    // ---- four whole points: p = 4h + k  (i = p / 3 indexes kernel_w, j = p % 3 kernel_h, cuh:253-254)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int p = 4 * h + k;
+        const int i = h ? (4 + k) / 3 : k / 3, j = h ? (4 + k) % 3 : k % 3;
+        const float2 o = load_offset_pair(po + 2 * p);
+        Point<float> t;
+        locate<float>(q, p0h_, p0w_, i, j, o.x, o.y, t);
+        float m = to_math(pm[p]);
+        if (LOGITS) m = expf(m - mx) * inv;
+        const float hm = t.hh * m, lm = t.lh * m;
+        const float w1 = hm * t.hw, w2 = hm * t.lw, w3 = lm * t.hw, w4 = lm * t.lw;
+        const char *r1 = im + (t.h_low * q.W + t.w_low) * sC;
+        const Words<32> c1 = ldg_pred<32>(r1, t.ok1);
+        const Words<32> c2 = ldg_pred<32>(r1 + sC, t.ok2);
+        const Words<32> c3 = ldg_pred<32>(r1 + sW, t.ok3);
+        const Words<32> c4 = ldg_pred<32>(r1 + sW + sC, t.ok4);
+        float2 v[8];
+        to_pairs<32>(c1, v, (const T *)nullptr);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = __ffma2_rn(v[c], make_float2(w1, w1), acc[c]);
+        to_pairs<32>(c2, v, (const T *)nullptr);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = __ffma2_rn(v[c], make_float2(w2, w2), acc[c]);
+        to_pairs<32>(c3, v, (const T *)nullptr);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = __ffma2_rn(v[c], make_float2(w3, w3), acc[c]);
+        to_pairs<32>(c4, v, (const T *)nullptr);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = __ffma2_rn(v[c], make_float2(w4, w4), acc[c]);
+    }
+
+    // ---- exchange: lane h keeps channels 8h..8h+7 and gets the partner's partial sums for them
+    float2 mine[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float2 keep = h ? acc[4 + c] : acc[c];
+        const float2 send = h ? acc[c] : acc[4 + c];
+        mine[c].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, 1);
+        mine[c].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, 1);
+    }
+
+    // ---- point 8 (i = 2, j = 2): both lanes, 8 channels each
+    {
+        const float2 o = load_offset_pair(po + 16);
+        Point<float> t;
+        locate<float>(q, p0h_, p0w_, 2, 2, o.x, o.y, t);
+        float m = to_math(pm[8]);
+        if (LOGITS) m = expf(m - mx) * inv;
+        const float hm = t.hh * m, lm = t.lh * m;
+        const float w1 = hm * t.hw, w2 = hm * t.lw, w3 = lm * t.hw, w4 = lm * t.lw;
+        const char *r1 = im + (t.h_low * q.W + t.w_low) * sC + 16 * h;
+        const Words<16> c1 = ldg_pred<16>(r1, t.ok1);
+        const Words<16> c2 = ldg_pred<16>(r1 + sC, t.ok2);
+        const Words<16> c3 = ldg_pred<16>(r1 + sW, t.ok3);
+        const Words<16> c4 = ldg_pred<16>(r1 + sW + sC, t.ok4);
+        float2 v[4];
+        to_pairs<16>(c1, v, (const T *)nullptr);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mine[c] = __ffma2_rn(v[c], make_float2(w1, w1), mine[c]);
+        to_pairs<16>(c2, v, (const T *)nullptr);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mine[c] = __ffma2_rn(v[c], make_float2(w2, w2), mine[c]);
+        to_pairs<16>(c3, v, (const T *)nullptr);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mine[c] = __ffma2_rn(v[c], make_float2(w3, w3), mine[c]);
+        to_pairs<16>(c4, v, (const T *)nullptr);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mine[c] = __ffma2_rn(v[c], make_float2(w4, w4), mine[c]);
+    }
+    Words<16> r;
+    from_pairs<16>(mine, r, (const T *)nullptr);
+    if (active) st_words<16>(out + (size_t)pix * q.C + g * 16 + 8 * h, r);
+}
+
+// ===========================================================================
 // backward, vector path.  A = accumulation type of grad_input (float: gin itself for f32
 // storage or the fp32 workspace for 16-bit storage; T: packed 16-bit reductions).
 //
