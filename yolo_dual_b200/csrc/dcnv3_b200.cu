@@ -380,18 +380,26 @@ int backward_launch(const T *in, const T *off, const T *mask, const T *gout, A *
     if constexpr (sizeof(T) <= 4) {
         if (pl.vec) {
             const unsigned n_blocks = blocks_for(pl.total_vec);
-            // selector-guarded launch: about three CTAs per SM that walk the logical blocks, so that a
-            // launch the selector turns into a no-op costs one resident wave, not thousands of CTAs
-            const unsigned per_cta = sel ? (n_blocks + 148u * 3u - 1u) / (148u * 3u) : 1u;
+            // Selector-guarded launch: `per_cta` consecutive logical blocks per CTA, so that a launch the
+            // selector turns into a no-op is a few thousand empty CTAs, not 12 800.  Measured on one box
+            // (step of the common path / P3 backward when the selector picks THIS kernel, us):
+            //   per_cta 1: 575.0 / 432   2: 563.4 / 440   4: 557.6 / 456   8: 556 / 464   32: 553.1 / 514
+            // (fewer, longer CTAs quantise the last wave).  4 is the default; DCNV3_B200_GUARD_PER_CTA overrides.
+            unsigned per_cta = 1u;
+            if (sel) {
+                const char *e = getenv("DCNV3_B200_GUARD_PER_CTA");
+                const int v = e ? atoi(e) : 4;
+                per_cta = v >= 1 && v <= 64 ? (unsigned)v : 4u;
+            }
             const unsigned grid = (n_blocks + per_cta - 1) / per_cta;
             const bool k9 = (q.kh == 3 && q.kw == 3);
 #define LAUNCH_BWD(BPL, KP, LG)                                                                  \
     launch(bwd_vec_kernel<T, A, BPL, KP, LG>, grid, kThreads, 0, st, in, off, mask, gout, acc, goff, \
            gmask, q, pl.vec_per_pix, pl.lanes_per_group, pl.total_vec, sel, per_cta, n_blocks)
-#define LAUNCH_BWD_B(BPL)                      \
-    if (k9 && logits) LAUNCH_BWD(BPL, 9, true); \
-    else if (k9) LAUNCH_BWD(BPL, 9, false);     \
-    else LAUNCH_BWD(BPL, 0, false)
+#define LAUNCH_BWD_B(BPL)                        \
+    if (k9 && logits) { LAUNCH_BWD(BPL, 9, true); } \
+    else if (k9) { LAUNCH_BWD(BPL, 9, false); }     \
+    else { LAUNCH_BWD(BPL, 0, false); }
             if (pl.bpl == 32) { LAUNCH_BWD_B(32); }
             else if (pl.bpl == 8) {
                 if constexpr (sizeof(T) == 2 && sizeof(A) == 4) { LAUNCH_BWD_B(8); }

@@ -548,6 +548,10 @@ bwd_vec_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                T *__restrict__ gmask, const Geo q, const int vec_per_pix,
                const int lanes_per_group, const unsigned total, const int *__restrict__ sel = nullptr,
                const unsigned per_cta = 1, const unsigned n_blocks = 0) {
+    // Wait first, like every kernel of the chain.  (Reading `sel` ahead of the wait and letting unneeded CTAs
+    // leave at once is legal — zero_select_kernel has completed by then — but it lets the NEXT kernel's
+    // thousands of CTAs become resident and sit in their own wait while bwd_imat_kernel is still in its
+    // tail, which slowed the back-to-back step by 20-170 us.  Waiting CTAs are not free.)
     pdl_enter();
     if (sel != nullptr && *sel != 1) return;
     if (per_cta == 1) {
