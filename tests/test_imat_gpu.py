@@ -44,7 +44,7 @@ def _close(got, want, what, rtol=1e-2, atol=2e-3):
                                msg=lambda s: f"{what}: {s}")
 
 
-@pytest.mark.parametrize("fwd", ["vec", "imat", "pts"])
+@pytest.mark.parametrize("fwd", ["vec", "imat", "pts", "win"])
 @pytest.mark.parametrize("dist", ["unit", "ref"])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
 @pytest.mark.parametrize("case", list(CASES))

@@ -177,9 +177,9 @@ bool pdl_on() {
     return !(e && e[0] == '0');
 }
 template <typename... P, typename... A>
-void launch(void (*kernel)(P...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, A... args) {
+void launch(void (*kernel)(P...), dim3 grid, unsigned block, size_t smem, cudaStream_t st, A... args) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
+    cfg.gridDim = grid;
     cfg.blockDim = dim3(block);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -195,13 +195,14 @@ void launch(void (*kernel)(P...), unsigned grid, unsigned block, size_t smem, cu
 // Knobs: DCNV3_B200_FWD / DCNV3_B200_BWD = vec | imat force a family.  Defaults: the backward takes the
 // interpolation-matrix kernel when eligible (16-bit, gc = 16, 3x3 s1 d1, fp32 accumulation), the forward the
 // vector kernel (its imat variant is correct but slower: profiles/r01_imat.md).
-int family_knob(const char *name) {  // 0 default, 1 vec, 2 tile, 3 imat, 4 pts
+int family_knob(const char *name) {  // 0 default, 1 vec, 2 tile, 3 imat, 4 pts, 5 win
     const char *e = getenv(name);
     if (!e) return 0;
     if (!strcmp(e, "vec")) return 1;
     if (!strcmp(e, "tile")) return 2;
     if (!strcmp(e, "imat")) return 3;
     if (!strcmp(e, "pts")) return 4;
+    if (!strcmp(e, "win")) return 5;
     return 0;
 }
 
@@ -265,6 +266,24 @@ int forward_t(const void *in_, const void *off_, const void *mask_, void *out_, 
         const int fam = family_knob("DCNV3_B200_FWD");
         if (fam == 3 && imat_eligible<T>(q, {in_, out_}, off_))
             return launch_fwd_imat<T>(in, off, mask, out, q, logits, st);
+        // Default for the C3-DCN shapes (16-bit, group_channels = 16, 3x3 s1 d1, G % 4 = 0): the forward from a
+        // staged window (imat::fwd_tile_kernel), unless the map wastes more than 40 % of its 8x8 tiles.
+        // DCNV3_B200_FWD=vec forces the vector kernel, =win this one.
+        const long long tiles64 = 64ll * ((q.Ho + 7) / 8) * ((q.Wo + 7) / 8);
+        if ((fam == 5 || (fam == 0 && 10ll * q.Ho * q.Wo >= 6ll * tiles64)) && imat_eligible<T>(q, {in_, out_}, off_) &&
+            !(reinterpret_cast<uintptr_t>(mask_) & 1u) && q.N <= 65535 && (q.Ho + 7) / 8 <= 65535) {
+            const int tiles_y = (q.Ho + 7) / 8, tiles_x = (q.Wo + 7) / 8, GQ = q.G / imat::kWarps;
+            const dim3 grid((unsigned)(tiles_x * GQ), (unsigned)tiles_y, (unsigned)q.N);
+            int rc;
+            if (logits) {
+                if ((rc = set_smem(imat::fwd_tile_kernel<T, true>, imat::kFwinBytes, "cudaFuncSetAttribute(fwd_tile_kernel)"))) return rc;
+                launch(imat::fwd_tile_kernel<T, true>, grid, imat::kFwdTileThreads, imat::kFwinBytes, st, in, off, mask, out, q, GQ);
+            } else {
+                if ((rc = set_smem(imat::fwd_tile_kernel<T, false>, imat::kFwinBytes, "cudaFuncSetAttribute(fwd_tile_kernel)"))) return rc;
+                launch(imat::fwd_tile_kernel<T, false>, grid, imat::kFwdTileThreads, imat::kFwinBytes, st, in, off, mask, out, q, GQ);
+            }
+            return 0;
+        }
         // opt-in (DCNV3_B200_FWD=pts): the point-split kernel — 25 % fewer instructions, measured SLOWER
         // (P3 98.7 vs 82.3 us): a lane's 32-byte LDG.256 costs L1 two passes where the channel-split
         // pair of 16-byte lanes shares one; the forward is bound by L1 wavefronts, not by issue slots

@@ -131,6 +131,12 @@ template <> __device__ __forceinline__ float half_to_float<__nv_bfloat16>(unsign
 template <> __device__ __forceinline__ float half_to_float<__half>(unsigned short h) {
     return __half2float(__ushort_as_half(h));
 }
+// bit pattern of a positive value in the storage dtype (rounded down: a threshold)
+template <typename T> __device__ __forceinline__ uint32_t storage_bits(float v);
+template <> __device__ __forceinline__ uint32_t storage_bits<__nv_bfloat16>(float v) { return __float_as_uint(v) >> 16; }
+template <> __device__ __forceinline__ uint32_t storage_bits<__half>(float v) {
+    return (uint32_t)__half_as_ushort(__float2half_rz(fminf(v, 60000.f)));
+}
 template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
 template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -1071,6 +1077,241 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
             float *d = dst0 + r * row_stride;
             red_add_v4_f32(row_ok && ok0 ? d : gacc, v0.x, v0.y, v0.z, v0.w, row_ok && ok0 && nz0);
             red_add_v4_f32(row_ok && ok1 ? d + 8 * q.C : gacc, v1.x, v1.y, v1.z, v1.w, row_ok && ok1 && nz1);
+        }
+    }
+}
+
+// ===========================================================================
+// forward from a staged window (16-bit storage, group_channels = 16, 3x3 s1 d1): SIMT gathers out of
+// shared memory instead of L1.
+//
+// fwd_vec_kernel is co-limited by instruction issue (77 %) and by L1 wavefronts (74 %): every corner of every
+// point is a 32-byte sector of its own cache line, ~1.9 sectors per L1 wavefront.  Here a CTA stages the
+// 16x16-cell x 64-channel window of an (8x8 tile, 4 groups) once, UNswizzled: a cell is one 128-byte row and
+// the 16-byte chunk of lane (g, h) inside it is always chunk 2g + h.  The eight lanes of a quarter-warp are the
+// four groups x two channel halves of ONE pixel, so whatever cells the four groups sample, their eight chunks
+// fall into eight different bank groups: every LDS.128 is conflict-free (4 wavefronts for 16 slabs instead of
+// ~8.5).  The zero fill outside the map is the reference's per-corner validity, so the lanes carry no
+// validity predicates, no predicated loads and 32-bit addresses: ~40 % fewer instructions per point.
+// Points that leave the window (|offset * scale| >= ~4 px) gather from global memory as the vector kernel does.
+// ===========================================================================
+constexpr int kFwdTileThreads = 256;
+constexpr int kFwin = 20, kFhalo = 6;            // window of the staged forward: 8x8 tile + 6 cells each side
+constexpr int kFwinBytes = kFwin * kFwin * 128;  // 51 200 B: three CTAs per SM
+
+template <typename T>
+__device__ __forceinline__ void fill_window_plain(unsigned char *win, const T *in, const T *img, const Geo &q,
+                                                  int wy0, int wx0, int tid) {
+    // thread = (column slot, 16-byte chunk): slots 0..19 copy one column of the 20 window rows each (warps 5-7
+    // have no column and go straight on); pointer and shared address advance by constants
+    const int ch = tid & 7, col = tid >> 3;
+    if (col >= kFwin) return;
+    const int ix = wx0 + col;
+    const bool col_ok = (unsigned)ix < (unsigned)q.W;
+    const size_t step = (size_t)q.W * q.C;
+    const T *p = img + ((long long)wy0 * q.W + ix) * q.C + ch * 8;
+    uint32_t dst = smem_u32(win) + col * 128 + (ch << 4);
+    int iy = wy0;
+#pragma unroll 4
+    for (int i = 0; i < kFwin; ++i) {
+        const bool ok = col_ok && (unsigned)iy < (unsigned)q.H;
+        cp_async16(dst, ok ? p : in, ok ? 16 : 0);
+        p += step; dst += kFwin * 128; ++iy;
+    }
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ void fma8(float2 (&acc)[4], const uint4 &c, float w) {
+    const uint32_t wd[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = __ffma2_rn(unpack2f<T>(wd[k]), make_float2(w, w), acc[k]);
+}
+
+// one corner of a window-resident point: both 16-byte chunks of the group's slab (own chunk first)
+template <typename T>
+__device__ __forceinline__ void corner16(float2 (&acc)[8], uint32_t a0, uint32_t a1, float w) {
+    const uint4 x0 = lds128(a0), x1 = lds128(a1);
+    const uint32_t w0[4] = {x0.x, x0.y, x0.z, x0.w}, w1[4] = {x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = __ffma2_rn(unpack2f<T>(w0[k]), make_float2(w, w), acc[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[4 + k] = __ffma2_rn(unpack2f<T>(w1[k]), make_float2(w, w), acc[4 + k]);
+}
+
+// The two lanes (h = 0, 1) of a (pixel, group) split the nine POINTS: lane h takes points 4h..4h+3 with all 16
+// channels and both take point 8 with their own 8.  A lane reads its chunk 2g + h first and the partner's
+// chunk 2g + 1 - h second, so in either LDS.128 the eight lanes of a quarter-warp still touch eight different
+// bank groups; one shuffle exchange per pixel merges the halves.  4.5 locates per lane instead of 9.
+// (The same split over L1 — fwd_pts_kernel — lost: there a 32-byte request costs L1 two passes.)
+template <typename T, bool LOGITS>
+__global__ void __launch_bounds__(kFwdTileThreads, 3)
+fwd_tile_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
+                T *__restrict__ out, const Geo q, const int GQ) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    pdl_enter();
+    const int tid = threadIdx.x;
+    // grid = (tiles_x * GQ, tiles_y, N): no divisions by run-time extents except this one
+    TileCoord tc;
+    tc.tx = (int)(blockIdx.x / (unsigned)GQ); tc.gq = (int)(blockIdx.x - (unsigned)tc.tx * (unsigned)GQ);
+    tc.ty = (int)blockIdx.y; tc.n = (int)blockIdx.z;
+    const int wy0 = tc.ty * kTile + (q.half_h - q.ph) - kFhalo;  // input row of window cell (0, 0)
+    const int wx0 = tc.tx * kTile + (q.half_w - q.pw) - kFhalo;
+    const T *img = in + (size_t)tc.n * q.H * q.W * q.C + tc.gq * 64;
+    fill_window_plain<T>(smem, in, img, q, wy0, wx0, tid);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    const PtGeo pg{q.H, q.W, q.scale};
+    const uint32_t win_s = smem_u32(smem);
+    const int sub = tid & 7, h = sub & 1;          // chunk of the cell row: 2 * (group in quad) + channel half
+    const int g = tc.gq * kWarps + (sub >> 1);
+    const uint32_t own16 = (uint32_t)sub << 4, other16 = (uint32_t)(sub ^ 1) << 4;
+    // kernel-grid coordinates of this lane's four whole points p = 4h + k: i = p / 3 (kernel_w), j = p % 3
+    float fi[4], fj[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        fi[k] = h ? (float)((4 + k) / 3) : (float)(k / 3);
+        fj[k] = h ? (float)((4 + k) % 3) : (float)(k % 3);
+    }
+
+    // two pixels per lane (tile rows 0-3 and 4-7); offsets of points 4h..4h+3 and 8, all nine masks
+    uint32_t roff[2][5];
+    float rm[2][9];
+    int oy[2], ox[2];
+    bool valid[2];
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int px = it * 32 + (tid >> 3);
+        oy[it] = tc.ty * kTile + (px >> 3);
+        ox[it] = tc.tx * kTile + (px & 7);
+        valid[it] = oy[it] < q.Ho && ox[it] < q.Wo;
+        const size_t unit = (((size_t)tc.n * q.Ho + oy[it]) * q.Wo + ox[it]) * q.G + g;
+        const uint32_t *po = reinterpret_cast<const uint32_t *>(off) + unit * 9;
+        const unsigned short *pm = reinterpret_cast<const unsigned short *>(mask) + unit * 9;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) roff[it][k] = valid[it] ? __ldg(po + 4 * h + k) : 0u;
+        roff[it][4] = valid[it] ? __ldg(po + 8) : 0u;
+        if (LOGITS) {
+#pragma unroll
+            for (int p = 0; p < 9; ++p) rm[it][p] = valid[it] ? half_to_float<T>(__ldg(pm + p)) : 0.f;
+        } else {  // slots 0-3: this lane's points, slot 8: point 8
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rm[it][k] = valid[it] ? half_to_float<T>(__ldg(pm + 4 * h + k)) : 0.f;
+            rm[it][8] = valid[it] ? half_to_float<T>(__ldg(pm + 8)) : 0.f;
+        }
+    }
+    // Mode of the CTA.  A point that leaves the window costs a divergent trip through global memory, so a
+    // tile whose offsets are large (more than 1 in 16 of its lanes sees an offset coordinate of 5 px or more) runs the vector kernel's body instead: same result, ~the vector
+    // kernel's speed, no dependence on the offset distribution.  Decided per CTA, on the device, no state.
+    // (an offset coordinate with |off * scale| >= 5 px: the window reaches 5 px beyond the 3x3 grid; tested on the packed
+    // storage bits — positive 16-bit floats order like integers)
+    const uint32_t thr = storage_bits<T>(5.f / fabsf(q.scale));
+    uint32_t far = 0u;
+#pragma unroll
+    for (int it = 0; it < 2; ++it)
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const uint32_t a = roff[it][k] & 0x7fff7fffu;
+            far |= (a >= (thr << 16) || (a & 0xffffu) >= thr) ? 1u : 0u;
+        }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const bool cta_far = __syncthreads_count(far != 0u) * 16 > kFwdTileThreads;  // (also the barrier for the window)
+    if (cta_far) {
+#pragma unroll 1
+        for (int it = 0; it < 2; ++it) {
+            if (!valid[it]) continue;
+            VecCoord c;
+            c.pix = (unsigned)(((size_t)tc.n * q.Ho + oy[it]) * q.Wo + ox[it]);
+            c.v = tc.gq * 8 + sub; c.g = g; c.n = tc.n; c.ho = oy[it]; c.wo = ox[it];
+            fwd_vec_body<T, 16, 9, LOGITS>(c, in, off, mask, out, q);
+        }
+        return;
+    }
+
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        // (a pair shares its pixel, so both lanes take the same branch and the shuffle below is safe)
+        if (__ballot_sync(0xffffffffu, valid[it]) == 0u) continue;
+        float p0h_, p0w_;
+        window_origin<float>(q, oy[it], ox[it], p0h_, p0w_);
+        float mk[5];  // masks of points 4h..4h+3 and 8
+        if (LOGITS) {
+            softmax9<T, LOGITS>(rm[it]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mk[k] = h ? rm[it][4 + k] : rm[it][k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mk[k] = rm[it][k];
+        }
+        mk[4] = rm[it][8];
+        float2 acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = make_float2(0.f, 0.f);
+        const T *img_g = img + (sub >> 1) * 16;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            if (k == 4) {  // the four whole points are done: merge the halves, then point 8 on 8 channels
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    acc[c].x += __shfl_xor_sync(0xffffffffu, acc[4 + c].x, 1);
+                    acc[c].y += __shfl_xor_sync(0xffffffffu, acc[4 + c].y, 1);
+                }
+            }
+            const float2 o = unpack2f<T>(roff[it][k]);
+            const LeanPoint t = locate_lean(pg, p0h_, p0w_, k == 4 ? 2.f : fi[k], k == 4 ? 2.f : fj[k], o.x, o.y);
+            const unsigned u = (unsigned)(t.w_low - wx0), v = (unsigned)(t.h_low - wy0);
+            const bool inwin = u <= (unsigned)(kFwin - 2) && v <= (unsigned)(kFwin - 2);
+            const bool fast = t.inside && inwin && valid[it];
+            const float m = fast ? mk[k] : 0.f;
+            const uint32_t a = win_s + (fast ? (v * kFwin + u) * 128u : 0u);
+            const float hh = sub_rn(1.f, t.lh), hw = sub_rn(1.f, t.lw);
+            const float hm = hh * m, lm = t.lh * m;
+            const float w1 = hm * hw, w2 = hm * t.lw, w3 = lm * hw, w4 = lm * t.lw;
+            if (k < 4) {
+                corner16<T>(acc, a + own16, a + other16, w1);
+                corner16<T>(acc, a + own16 + 128, a + other16 + 128, w2);
+                corner16<T>(acc, a + own16 + kFwin * 128, a + other16 + kFwin * 128, w3);
+                corner16<T>(acc, a + own16 + kFwin * 128 + 128, a + other16 + kFwin * 128 + 128, w4);
+            } else {
+                float2 (&lo)[4] = reinterpret_cast<float2 (&)[4]>(acc);
+                fma8<T>(lo, lds128(a + own16), w1);
+                fma8<T>(lo, lds128(a + own16 + 128), w2);
+                fma8<T>(lo, lds128(a + own16 + kFwin * 128), w3);
+                fma8<T>(lo, lds128(a + own16 + kFwin * 128 + 128), w4);
+            }
+            if (t.inside && !inwin && valid[it]) {
+                // rare: the point left the staged window; gather from global memory with the reference's
+                // validity (whole points before the merge: both chunks; point 8: the own chunk).  Inline on
+                // purpose: as a non-inlined function the accumulators live in local memory (72 -> 97 us).
+                Point<float> tt;
+                locate<float>(q, p0h_, p0w_, k == 4 ? 2 : (h ? (4 + k) / 3 : k / 3), k == 4 ? 2 : (h ? (4 + k) % 3 : k % 3), o.x, o.y, tt);
+                const float sm_h = tt.hh * mk[k], sm_l = tt.lh * mk[k];
+                const float w[4] = {sm_h * tt.hw, sm_h * tt.lw, sm_l * tt.hw, sm_l * tt.lw};
+                const bool ok[4] = {tt.ok1, tt.ok2, tt.ok3, tt.ok4};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (!ok[c]) continue;
+                    const T *src = img_g + ((size_t)(tt.h_low + (c >> 1)) * q.W + (tt.w_low + (c & 1))) * q.C;
+                    float2 (&lo)[4] = reinterpret_cast<float2 (&)[4]>(acc);
+                    fma8<T>(lo, __ldg(reinterpret_cast<const uint4 *>(src + 8 * h)), w[c]);
+                    if (k < 4) {
+                        float2 (&hi)[4] = reinterpret_cast<float2 (&)[4]>(acc[4]);
+                        fma8<T>(hi, __ldg(reinterpret_cast<const uint4 *>(src + 8 * (h ^ 1))), w[c]);
+                    }
+                }
+            }
+        }
+        if (valid[it]) {
+            const size_t pix = ((size_t)tc.n * q.Ho + oy[it]) * q.Wo + ox[it];
+            uint4 r;
+            r.x = pack2<T>(acc[0].x, acc[0].y); r.y = pack2<T>(acc[1].x, acc[1].y);
+            r.z = pack2<T>(acc[2].x, acc[2].y); r.w = pack2<T>(acc[3].x, acc[3].y);
+            *reinterpret_cast<uint4 *>(out + pix * q.C + g * 16 + h * 8) = r;
         }
     }
 }

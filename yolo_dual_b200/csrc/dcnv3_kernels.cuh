@@ -142,16 +142,11 @@ __device__ __forceinline__ void softmax_stats(const T *pm, int P, float &mx, flo
 // ===========================================================================
 // forward, vector path: one lane owns BPL bytes of channels of one (n, ho, wo, g)
 // ===========================================================================
+// one lane's work: BPL bytes of channels (vector c.v of pixel c.pix, group c.g), all points
 template <typename T, int BPL, int KP, bool LOGITS>
-__global__ void __launch_bounds__(kThreads)
-fwd_vec_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
-               T *__restrict__ out, const Geo q, const int vec_per_pix,
-               const int lanes_per_group, const unsigned total) {
+__device__ __forceinline__ void fwd_vec_body(const VecCoord &c, const T *__restrict__ in, const T *__restrict__ off,
+                                             const T *__restrict__ mask, T *__restrict__ out, const Geo &q) {
     constexpr int CH = Lane<T, BPL>::CH, NP = Lane<T, BPL>::NP;
-    pdl_enter();
-    const unsigned idx = blockIdx.x * (unsigned)kThreads + threadIdx.x;
-    if (idx >= total) return;
-    const VecCoord c = decode_vec(idx, q, vec_per_pix, lanes_per_group);
 
     float p0h_, p0w_;
     window_origin<float>(q, c.ho, c.wo, p0h_, p0w_);
@@ -207,6 +202,18 @@ fwd_vec_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     Words<BPL> r;
     from_pairs<BPL>(acc, r, (const T *)nullptr);
     st_words<BPL>(out + (size_t)c.pix * q.C + c.v * CH, r);
+}
+
+template <typename T, int BPL, int KP, bool LOGITS>
+__global__ void __launch_bounds__(kThreads)
+fwd_vec_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
+               T *__restrict__ out, const Geo q, const int vec_per_pix,
+               const int lanes_per_group, const unsigned total) {
+    pdl_enter();
+    const unsigned idx = blockIdx.x * (unsigned)kThreads + threadIdx.x;
+    if (idx >= total) return;
+    const VecCoord c = decode_vec(idx, q, vec_per_pix, lanes_per_group);
+    fwd_vec_body<T, BPL, KP, LOGITS>(c, in, off, mask, out, q);
 }
 
 // ===========================================================================
