@@ -252,7 +252,7 @@ def time_e2e(wl, steps, warmup, dist):
     DCNv3Function.apply + autograd; every step copies its inputs from pinned host memory and writes
     every result (output + three grads per site) back to pinned host memory.  Copies in, kernels and
     copies out run on three streams (PCIe is full duplex), three steps in flight."""
-    from yolo_dual_b200.host import HostPipeline, HostSite
+    from yolo_dual_b200.host import HostPipeline, HostSite, pack_sites
     from yolo_dual_b200.ops_dcnv3.functions import set_grad_accum
     set_grad_accum("opmath" if wl.accum == 0 else "storage")
     sites = []
@@ -261,6 +261,7 @@ def time_e2e(wl, steps, warmup, dist):
         hs = HostSite(*(t.cpu().pin_memory() for t in (b.input, b.offset, b.mask, b.grad_out)),
                       args=(3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0))
         sites.append(hs.alloc_outputs(tuple(b.output.shape)))
+    sites = pack_sites(sites)  # one pinned arena per direction: one copy each way per step
     h2d = sum(s.h2d_bytes for s in sites)
     d2h = sum(s.d2h_bytes for s in sites)
     pipe = HostPipeline(wl.dev, depth=3, fused_softmax=bool(wl.logits))
@@ -509,7 +510,7 @@ def main():
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / a.e2e_steps,
                "steps": a.e2e_steps,
                "api": "yolo_dual_b200.host.HostPipeline -> DCNv3Function.apply + autograd on pinned host tensors; "
-                      "H2D of input/offset/mask/grad_out and D2H of output + 3 grads every step, copies and kernels "
+                      "H2D of input/offset/mask/grad_out and D2H of output + 3 grads every step (one pinned arena per direction), copies and kernels "
                       "on three streams, three steps in flight"}
     seg_res = None
     if not a.no_seg:

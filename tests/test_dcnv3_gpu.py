@@ -511,9 +511,10 @@ def test_seg_model_train_step(cfg_name):
 # ------------------------------------------------------------------------------------------
 # 11. host-buffer front: overlapped copies must not change the results
 # ------------------------------------------------------------------------------------------
-def test_host_pipeline_matches_direct_calls(fn):
+@pytest.mark.parametrize("packed", [False, True], ids=["separate_buffers", "one_arena_per_direction"])
+def test_host_pipeline_matches_direct_calls(fn, packed):
     from oracle.dcnv3_oracle import make_inputs
-    from yolo_dual_b200.host import HostPipeline, HostSite
+    from yolo_dual_b200.host import HostPipeline, HostSite, pack_sites
     shapes = [(2, 20, 24, 4, 16), (2, 10, 12, 8, 16)]
     sites, want = [], []
     for i, (N, H, W, G, gc) in enumerate(shapes):
@@ -522,8 +523,10 @@ def test_host_pipeline_matches_direct_calls(fn):
         sites.append(HostSite(x.pin_memory(), off.pin_memory(), m.pin_memory(), go.pin_memory(), args=args)
                      .alloc_outputs((N, H, W, G * gc)))
         want.append(run_cuda(fn, x, off, m, go, args))
+    if packed:
+        sites = pack_sites(sites)
     pipe = HostPipeline(DEV)
-    for _ in range(5):  # several steps in flight reuse the two staging slots
+    for _ in range(5):  # several steps in flight reuse the staging slots
         t = pipe.submit(sites)
     pipe.wait(t)
     pipe.drain()
