@@ -127,7 +127,8 @@ def main():
                     vec = gc % (16 // e) == 0 and (gc // (16 // e)) & (gc // (16 // e) - 1) == 0 and gc // (16 // e) <= 32
                     name = {torch.float32: "fp32", torch.float16: "fp16", torch.bfloat16: "bf16"}[dtype]
                     fg, bg = fwd_b / res[0] / 1e3, bwd_b / res[1] / 1e3
-                    print(f"| {C} | {G} | {gc} | {HW}x{HW} | {name} | {'vec' if vec else '(generic)'} | {res[0]:.1f} | "
+                    win = e == 2 and gc == 16 and G % 4 == 0  # staged-window forward + interpolation-matrix backward
+                    print(f"| {C} | {G} | {gc} | {HW}x{HW} | {name} | {'win/imat' if win else 'vec' if vec else '(generic)'} | {res[0]:.1f} | "
                           f"{fg:.0f} | {100 * fg / peak:.1f} | {res[1]:.1f} | {bg:.0f} | {100 * bg / peak:.1f} |", flush=True)
                     del sets
                     torch.cuda.empty_cache()
