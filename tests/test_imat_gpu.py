@@ -163,3 +163,29 @@ def test_imat_bf16_gradient_range(mode, pixel_oracle, monkeypatch):
         # (window rows above the large half's reach) must not be garbage: absolute error stays below 2^-24 max
         gi, wi = got[0].double(), want[0].double()
         assert float((gi - wi).abs().max()) <= 2.0 ** -8 * float(wi.abs().max())
+
+
+@pytest.mark.parametrize("fwd", ["win", "vec"])
+def test_forward_non_finite_input_stays_local(fwd, pixel_oracle, monkeypatch):
+    """A closed sampling point (outside the map) contributes nothing — it must not multiply some unrelated
+    staged cell by a zero weight: with an Inf in the input that would turn 0 * Inf into NaN far away from the
+    pixels that really sample it.  The staged-window forward parks closed points on zero cells."""
+    from oracle.dcnv3_oracle import make_inputs
+    from yolo_dual_b200.ops_dcnv3.functions import DCNv3Function
+    monkeypatch.setenv("DCNV3_B200_FWD", fwd)
+    N, H, W, G, gc = 1, 24, 24, 4, 16
+    args = (3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0)
+    x, off, m, _ = make_inputs(N, H, W, G, gc, 3, 3, 1, 1, 1, 1, 1, 1, dist="unit", seed=21)
+    x[0, 2, 2, :] = float("inf")      # = window cell (0, 0) of tile (1, 1)
+    off = off.view(N, H, W, G, 9, 2).clone()
+    off[..., 0, :] = 100.0            # point 0 of every (pixel, group) leaves the map: gate closed
+    off = off.view(N, H, W, G * 18)
+    dtype = torch.bfloat16
+    xr, offr, mr = (t.to(dtype).float() for t in (x, off, m))
+    want = pixel_oracle.forward(xr, offr, mr, *args)
+    xs, os_, ms = (t.to(DEV, dtype).contiguous() for t in (x, off, m))
+    got = DCNv3Function.apply(xs, os_, ms, *args, 256).float().cpu()
+    fin_w, fin_g = torch.isfinite(want), torch.isfinite(got)
+    assert fin_w.float().mean() > 0.9            # the Inf reaches only the pixels around (2, 2)
+    assert torch.equal(fin_w, fin_g)
+    torch.testing.assert_close(got[fin_g], want[fin_w], rtol=1e-2, atol=2e-2)

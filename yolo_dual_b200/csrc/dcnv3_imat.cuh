@@ -1097,7 +1097,9 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
 // ===========================================================================
 constexpr int kFwdTileThreads = 256;
 constexpr int kFwin = 20, kFhalo = 6;            // window of the staged forward: 8x8 tile + 6 cells each side
-constexpr int kFwinBytes = kFwin * kFwin * 128;  // 51 200 B: three CTAs per SM
+constexpr int kFwinCells = kFwin * kFwin;
+constexpr int kFzeroCells = kFwin + 2;            // zero cells behind the window: where a closed point's four corners read
+constexpr int kFwinBytes = (kFwinCells + kFzeroCells) * 128;  // 54 016 B: three CTAs per SM
 
 template <typename T>
 __device__ __forceinline__ void fill_window_plain(unsigned char *win, const T *in, const T *img, const Geo &q,
@@ -1165,6 +1167,7 @@ fwd_tile_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
     const T *img = in + (size_t)tc.n * q.H * q.W * q.C + tc.gq * 64;
     fill_window_plain<T>(smem, in, img, q, wy0, wx0, tid);
     asm volatile("cp.async.commit_group;" ::: "memory");
+    if (tid < kFzeroCells * 8) reinterpret_cast<uint4 *>(smem + kFwinCells * 128)[tid] = make_uint4(0u, 0u, 0u, 0u);
 
     const PtGeo pg{q.H, q.W, q.scale};
     const uint32_t win_s = smem_u32(smem);
@@ -1268,7 +1271,7 @@ fwd_tile_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
             const bool inwin = u <= (unsigned)(kFwin - 2) && v <= (unsigned)(kFwin - 2);
             const bool fast = t.inside && inwin && valid[it];
             const float m = fast ? mk[k] : 0.f;
-            const uint32_t a = win_s + (fast ? (v * kFwin + u) * 128u : 0u);
+            const uint32_t a = win_s + (fast ? v * kFwin + u : (unsigned)kFwinCells) * 128u;  // closed point: the zero cells (0 * Inf would be NaN)
             const float hh = sub_rn(1.f, t.lh), hw = sub_rn(1.f, t.lw);
             const float hm = hh * m, lm = t.lh * m;
             const float w1 = hm * hw, w2 = hm * t.lw, w3 = lm * hw, w4 = lm * t.lw;
