@@ -159,6 +159,11 @@ __device__ __forceinline__ void red_add_v4_f32(float *p, float a, float b, float
                  "f"(c), "f"(d), "r"((int)pred)
                  : "memory");
 }
+__device__ __forceinline__ void red_add_v2_f32(float *p, float a, float b, bool pred = true) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t"
+                 "@q red.global.add.v2.f32 [%0], {%1, %2};\n\t}" ::"l"(p), "f"(a), "f"(b), "r"((int)pred)
+                 : "memory");
+}
 __device__ __forceinline__ void red_add_v4_f16x2(__half *p, const uint4 &v, bool pred = true) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
                  "@q red.global.add.noftz.v4.f16x2 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p), "r"(v.x),

@@ -1041,9 +1041,38 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
         __syncwarp();
     }
 
-    // ---- flush, per warp (no CTA barrier): the group's window goes through the warp's own Wm buffer as
-    // [256 cells][16 ch] fp32 (16-byte chunks swizzled by 2*((cell >> 1) & 1): conflict-free both ways),
-    // then out as 64-byte-contiguous vector reductions; cells that received nothing are skipped
+    // ---- flush, per warp (no CTA barrier)
+#ifdef DCNV3_IMAT_FLUSH_DIRECT
+    // A/B variant (-DDCNV3_IMAT_FLUSH_DIRECT), measured SLOWER: straight from the mma fragments — (c0, c1) of a
+    // fragment are two consecutive channels of one cell, the four lanes of a quad cover one 32-byte sector, each
+    // REDG.F32x2 instruction carries 8 sectors.  It saves the detour through shared memory (11 % of the kernel's
+    // shared wavefronts, 8 % of its instructions) and loses more on the reduction path: twice the reduction
+    // instructions at 32 instead of 64 contiguous bytes (2.46 vs 1.83 port clocks per sector,
+    // profiles/r01_red_egress_microbench.md): P3 backward 251.4 vs 233.1 us on one box.
+    {
+        const float unscale = __uint_as_float((uint32_t)max(e_ref, 1) << 23);  // 2^(e_ref - 127), bf16 storage only
+        const int ix0 = wx0 + gID, ix1 = ix0 + 8;
+        const bool ok0 = (unsigned)ix0 < (unsigned)q.W, ok1 = (unsigned)ix1 < (unsigned)q.W;
+        const long long row_stride = (long long)q.W * q.C;
+        float *d0 = gacc_g + ((long long)wy0 * q.W + ix0) * q.C + 2 * tq;
+#pragma unroll
+        for (int r = 0; r < kWin; ++r) {
+            const bool row_ok = (unsigned)(wy0 + r) < (unsigned)q.H;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                float v0 = gw[r][nt][0], v1 = gw[r][nt][1], v2 = gw[r][nt][2], v3 = gw[r][nt][3];
+                if constexpr (kScaled) { v0 *= unscale; v1 *= unscale; v2 *= unscale; v3 *= unscale; }
+                const bool nz0 = ((__float_as_uint(v0) | __float_as_uint(v1)) << 1) != 0u;
+                const bool nz1 = ((__float_as_uint(v2) | __float_as_uint(v3)) << 1) != 0u;
+                red_add_v2_f32(row_ok && ok0 ? d0 + 8 * nt : gacc, v0, v1, row_ok && ok0 && nz0);
+                red_add_v2_f32(row_ok && ok1 ? d0 + 8 * nt + 8 * q.C : gacc, v2, v3, row_ok && ok1 && nz1);
+            }
+            d0 += row_stride;
+        }
+    }
+#else
+    // through the warp's own Wm buffer as [256 cells][16 ch] fp32 (16-byte chunks swizzled by 2*((cell >> 1) & 1):
+    // conflict-free both ways), then out as 64-byte-contiguous vector reductions; cells that received nothing are skipped
     {
         float *GW = Wm;
 #pragma unroll
@@ -1079,6 +1108,7 @@ bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
             red_add_v4_f32(row_ok && ok1 ? d + 8 * q.C : gacc, v1.x, v1.y, v1.z, v1.w, row_ok && ok1 && nz1);
         }
     }
+#endif
 }
 
 // ===========================================================================
