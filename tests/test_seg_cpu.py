@@ -151,3 +151,33 @@ def test_data_parallel_step_world2_gloo(tmp_path):
             continue
         torch.testing.assert_close(r0["grads"][k], p.grad, rtol=1e-4, atol=1e-6, msg=lambda m: f"{k}: {m}")
     torch.testing.assert_close((r0["loss"] + r1["loss"]) / 2, (sum(losses) / 2).detach(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("cfg", [YOLOV5_SEG, YOLOV8_SEG], ids=["v5", "v8"])
+def test_deferred_upsample_is_the_reference_order(cfg):
+    """The pointwise tail (1x1 Conv + BN(train) + SiLU, channel Softmax) commutes with the last nearest Upsample:
+    outputs and gradients equal the reference's layer order; `state_dict` keys are the same."""
+    torch.manual_seed(0)
+    a = SegModel(cfg, dcn="none", img_size=(64, 64), defer_upsample=True).double().train()
+    b = SegModel(cfg, dcn="none", img_size=(64, 64), defer_upsample=False).double().train()
+    assert a._deferred is not None and b._deferred is None
+    assert list(a.state_dict()) == list(b.state_dict())
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(2, 3, 64, 64, dtype=torch.double)
+    ya, yb = a(x), b(x)
+    assert ya.shape == yb.shape == (2, 12, 64, 64)
+    torch.testing.assert_close(ya, yb, rtol=1e-10, atol=1e-12)
+    w = torch.randn_like(ya)
+    (ya * w).sum().backward()
+    (yb * w).sum().backward()
+    for (n, p), q in zip(a.named_parameters(), b.parameters()):
+        assert (p.grad is None) == (q.grad is None), n
+        if p.grad is not None:
+            torch.testing.assert_close(p.grad, q.grad, rtol=1e-8, atol=1e-10 * float(q.grad.abs().max()) + 1e-14)
+    # running_mean identical; running_var differs only by BatchNorm's unbiased factor n/(n-1) in the tail's BN
+    sa, sb = a.state_dict(), b.state_dict()
+    for k in sa:
+        if k.endswith("running_mean"):
+            torch.testing.assert_close(sa[k], sb[k], rtol=1e-9, atol=1e-12)
+    a.eval(), b.eval()
+    torch.testing.assert_close(a(x), b(x), rtol=2e-3, atol=1e-6)

@@ -172,7 +172,13 @@ class SegModel(nn.Module):
 
     def __init__(self, cfg: Dict = YOLOV5_SEG, num_classes: Optional[int] = None, dcn: str = "dcnv3",
                  dcn_group: Optional[int] = None, fused_softmax: bool = False, outer_residual: bool = False,
-                 img_size: Sequence[int] = (640, 640)):
+                 img_size: Sequence[int] = (640, 640), defer_upsample: bool = True):
+        """defer_upsample: run the pointwise tail of the head (1x1 Conv + BN + SiLU, channel Softmax) BEFORE the last
+        nearest Upsample instead of after it.  Every one of those ops commutes with pixel replication — the batch
+        statistics of a replicated map are those of the map — so outputs and gradients are the reference's, while
+        the 64-channel 640x640 activation (839 MB in bf16 at batch 16) and the BN / SiLU / Softmax passes over it are
+        never materialised.  Only BatchNorm's unbiased-variance factor n/(n-1) in `running_var` sees the smaller n
+        (relative 2e-6).  Layer indices, parameter names and `state_dict` are unchanged."""
         super().__init__()
         if dcn not in ("dcnv3", "none"):
             raise ValueError("dcn must be 'dcnv3' or 'none'")
@@ -198,7 +204,34 @@ class SegModel(nn.Module):
             self.layers.append(mod)
             self.froms.append(frm)
             chs.append(c2)
+        self._deferred = self._find_deferrable_upsample() if defer_upsample else None
         self._initialize_weights()
+
+    def _find_deferrable_upsample(self) -> Optional[int]:
+        """Index of the last nearest Upsample if everything after it is pointwise and reads only its predecessor."""
+        n = len(self.layers)
+        ups = [i for i, m in enumerate(self.layers) if isinstance(m, nn.Upsample)]
+        if not ups:
+            return None
+        i = ups[-1]
+        m = self.layers[i]
+        if m.mode != "nearest" or float(m.scale_factor) != int(m.scale_factor) or i == n - 1:
+            return None
+        for j in range(i + 1, n):
+            if self.froms[j] != -1:
+                return None
+            t = self.layers[j]
+            if isinstance(t, Conv):
+                c = t.conv
+                if c.kernel_size != (1, 1) or c.stride != (1, 1) or c.padding != (0, 0):
+                    return None
+            elif not (isinstance(t, nn.Softmax) and t.dim == 1):
+                return None
+        for j, frm in enumerate(self.froms):  # nobody else may read the upsampled map
+            for f in (frm if isinstance(frm, list) else [frm]):
+                if f != -1 and (f if f >= 0 else j + f) >= i and j > i:
+                    return None
+        return i
 
     def _make(self, name, c1, args):
         if name == "Conv":
@@ -241,12 +274,16 @@ class SegModel(nn.Module):
 
     def forward(self, x):
         outs: List[torch.Tensor] = []
-        for layer, frm in zip(self.layers, self.froms):
-            if isinstance(frm, list):
+        for i, (layer, frm) in enumerate(zip(self.layers, self.froms)):
+            if i == self._deferred:
+                pass  # replicated after the pointwise tail instead (see __init__)
+            elif isinstance(frm, list):
                 x = layer([outs[f] for f in frm])
             else:
                 x = layer(x if not outs else outs[frm])
             outs.append(x)
+        if self._deferred is not None:
+            x = self.layers[self._deferred](x)
         if list(x.shape[2:]) != self.img_size:
             x = F.interpolate(x, size=self.img_size, mode="bilinear", align_corners=False)
         return x
