@@ -156,3 +156,24 @@ def test_function_signature_matches_reference():
     fwd = getattr(fwd, "__wrapped__", fwd)
     assert list(inspect.signature(fwd).parameters) == want
     assert list(inspect.signature(DCNv3Function.symbolic).parameters) == ["g"] + want[1:]
+
+
+def test_segloss_library_exports_its_header():
+    from yolo_dual_b200 import _segloss
+    from yolo_dual_b200.build import build_segloss
+    build_segloss()
+    lib = _segloss.load()
+    hdr = open(os.path.join(ROOT, "include", "segloss_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(segloss_b200_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_segloss.SYMBOLS)
+    v = int(re.search(r"#define SEGLOSS_B200_VERSION (\d+)", hdr).group(1))
+    assert lib.segloss_b200_version() == v
+    # argument validation happens before any device is touched; no CPU path behind it
+    assert lib.segloss_b200_forward(None, None, None, None, 1, 12, 4, 4, 1, None) == -2
+    assert lib.segloss_b200_forward(1, 1, 1, 1, 1, 17, 4, 4, 1, None) == -1
+    assert lib.segloss_b200_forward(1, 1, 1, 1, 1, 12, 4, 4, 1, None) == -3
+    assert b"no CPU path" in lib.segloss_b200_last_error()
+    with pytest.raises(NotImplementedError):
+        _segloss.FusedSegLoss.apply(torch.zeros(1, 12, 4, 4), torch.zeros(1, 4, 4, dtype=torch.long),
+                                    torch.ones(12), 1)

@@ -181,3 +181,25 @@ def test_deferred_upsample_is_the_reference_order(cfg):
             torch.testing.assert_close(sa[k], sb[k], rtol=1e-9, atol=1e-12)
     a.eval(), b.eval()
     torch.testing.assert_close(a(x), b(x), rtol=2e-3, atol=1e-6)
+
+
+def test_lowres_output_and_scaled_loss_on_cpu():
+    """lowres=True hands out the map before the deferred Upsample; the unfused loss replicates it itself."""
+    torch.manual_seed(0)
+    m = SegModel(YOLOV5_SEG, dcn="none", img_size=(64, 64)).eval()
+    x = torch.randn(1, 3, 64, 64)
+    full = m(x)
+    low, scale = m(x, lowres=True)
+    assert scale == 4 and low.shape == (1, 12, 16, 16)
+    torch.testing.assert_close(F.interpolate(low, scale_factor=4.0, mode="nearest"), full)
+    lab = torch.randint(0, 12, (1, 64, 64))
+    crit = SegmentationLoss(12, class_weights=CAMVID_CLASS_WEIGHTS)
+    torch.testing.assert_close(crit(low, lab, scale)[0], crit(full, lab)[0])
+    m8 = SegModel(YOLOV8_SEG, dcn="none", img_size=(64, 64)).eval()
+    low8, s8 = m8(x, lowres=True)
+    assert s8 == 2 and low8.shape == (1, 12, 32, 32)
+    torch.testing.assert_close(F.interpolate(low8, scale_factor=2.0, mode="nearest"), m8(x))
+    m8.img_size = [96, 96]                      # output needs the final bilinear resize: nothing to skip
+    low8, s8 = m8(x, lowres=True)
+    assert s8 == 1 and low8.shape == (1, 12, 96, 96)
+    torch.testing.assert_close(low8, m8(x))

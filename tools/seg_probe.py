@@ -29,9 +29,9 @@ def phases():
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     ev[0].record()
     with torch.autocast("cuda", dtype=torch.bfloat16):
-        pred = model(imgs)
+        pred, scale = model(imgs, lowres=True)
     ev[1].record()
-    loss, _ = crit(pred, lab)
+    loss, _ = crit(pred, lab, scale)
     ev[2].record()
     opt.zero_grad(set_to_none=True)
     loss.backward()
@@ -45,6 +45,10 @@ ts = [phases()[0] for _ in range(5)][-1]
 print("phases ms: model fwd %.2f, loss fwd %.2f, backward %.2f, optimizer %.2f" % tuple(ts))
 pred = phases()[1]
 print("pred", pred.dtype, tuple(pred.shape), pred.stride(), "deferred upsample:", model._deferred)
+with torch.autocast("cuda", dtype=torch.bfloat16):
+    t = torch.randn(2, 8, 4, 4, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    print("autocast dtypes: nearest", torch.nn.Upsample(scale_factor=2.0)(t).dtype,
+          "bilinear", torch.nn.functional.interpolate(t, size=(8, 8), mode="bilinear").dtype)
 for sync in (True, False):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(10):

@@ -31,6 +31,11 @@ NVCC_FLAGS = [
 ]
 
 
+# second, small library: the fused CE + Dice loss of the seg trainers (include/segloss_b200.h)
+SEGLOSS_LIB = os.path.join(CSRC, "libsegloss_b200.so")
+SEGLOSS_DEPS = [os.path.join(CSRC, "segloss_b200.cu"), os.path.join(ROOT, "include", "segloss_b200.h")]
+
+
 def _nvcc():
     for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -47,11 +52,8 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
-        return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+def _run_nvcc(out: str, sources, verbose: bool):
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + list(sources)
     env = dict(os.environ)
     env.pop("CC", None)   # the image exports a gcc wrapper nvcc should not pick up
     env.pop("CXX", None)
@@ -60,6 +62,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(r.stdout)
     if r.returncode:
         raise RuntimeError("nvcc failed:\n" + r.stdout[-4000:])
+
+
+def build_segloss(force: bool = False, verbose: bool = False) -> str:
+    if force or not os.path.exists(SEGLOSS_LIB) or \
+            any(os.path.getmtime(d) > os.path.getmtime(SEGLOSS_LIB) for d in SEGLOSS_DEPS):
+        _run_nvcc(SEGLOSS_LIB, SEGLOSS_DEPS[:1], verbose)
+    return SEGLOSS_LIB
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    build_segloss(force, verbose)
+    if not force and not _stale():
+        return LIB
+    _run_nvcc(LIB, [os.path.join(CSRC, s) for s in SOURCES], verbose)
     return LIB
 
 

@@ -135,6 +135,24 @@ class SPPF(nn.Module):
         return self.cv2(torch.cat([x, y1, y2, self.m(y2)], 1))
 
 
+def _resize_in_own_dtype(fn, x, **kw):
+    """CUDA autocast runs the upsample_* ops in float32 whatever comes in, and everything downstream of one
+    (torch.cat with bf16 neighbours, the copies in front of the next convolution) then moves 4-byte elements.
+    Resizing in the tensor's own 16-bit dtype gives the same numbers: nearest replication is exact, and the bilinear
+    kernels interpolate in float and round once — the rounding the next convolution's autocast cast would apply."""
+    if x.is_cuda and torch.is_autocast_enabled():
+        with torch.autocast("cuda", enabled=False):
+            return fn(x, **kw)
+    return fn(x, **kw)
+
+
+class Upsample(nn.Upsample):
+    """nn.Upsample (the layer tables' 'nn.Upsample' / 'Upsample') that keeps its input's dtype under autocast."""
+
+    def forward(self, x):
+        return _resize_in_own_dtype(super().forward, x)
+
+
 class Concat(nn.Module):
     """Concatenate after resizing every input to the first one's H x W
     (seg_diceloss_yolov5.py:484-507)."""
@@ -145,8 +163,8 @@ class Concat(nn.Module):
 
     def forward(self, xs: Sequence[torch.Tensor]):
         size = xs[0].shape[2:]
-        xs = [x if x.shape[2:] == size else F.interpolate(x, size=size, mode="bilinear", align_corners=False)
-              for x in xs]
+        xs = [x if x.shape[2:] == size else
+              _resize_in_own_dtype(F.interpolate, x, size=size, mode="bilinear", align_corners=False) for x in xs]
         return torch.cat(xs, self.d)
 
 
@@ -254,7 +272,7 @@ class SegModel(nn.Module):
         if name in ("Upsample", "nn.Upsample"):
             scale = float(args[1]) if len(args) > 1 and args[1] is not None else 2.0
             mode = args[2] if len(args) > 2 else "nearest"
-            return nn.Upsample(scale_factor=scale, mode=mode), c1
+            return Upsample(scale_factor=scale, mode=mode), c1
         if name == "Concat":
             return Concat(*args), c1
         if name == "nn.Softmax":
@@ -272,7 +290,9 @@ class SegModel(nn.Module):
                 nn.init.constant_(m.weight, 1)
                 nn.init.constant_(m.bias, 0)
 
-    def forward(self, x):
+    def forward(self, x, lowres: bool = False):
+        """lowres=True returns `(pred, scale)`: the output before the deferred nearest Upsample and its factor
+        (scale 1 and the full-size output when nothing is deferred) for `SegmentationLoss(pred, target, scale)`."""
         outs: List[torch.Tensor] = []
         for i, (layer, frm) in enumerate(zip(self.layers, self.froms)):
             if i == self._deferred:
@@ -283,7 +303,13 @@ class SegModel(nn.Module):
                 x = layer(x if not outs else outs[frm])
             outs.append(x)
         if self._deferred is not None:
+            scale = int(self.layers[self._deferred].scale_factor)
+            if lowres and [x.shape[2] * scale, x.shape[3] * scale] == self.img_size:
+                return x, scale
             x = self.layers[self._deferred](x)
+        if lowres:
+            return (x, 1) if list(x.shape[2:]) == self.img_size else \
+                (F.interpolate(x, size=self.img_size, mode="bilinear", align_corners=False), 1)
         if list(x.shape[2:]) != self.img_size:
             x = F.interpolate(x, size=self.img_size, mode="bilinear", align_corners=False)
         return x
@@ -298,16 +324,37 @@ class SegModel(nn.Module):
 # loss: CE(class weights) + 0.5 * weighted Dice on softmax(pred)   (seg_diceloss_yolov5.py:693-750)
 # ---------------------------------------------------------------------------------------------
 class SegmentationLoss(nn.Module):
-    def __init__(self, num_classes: int = 12, label_smoothing: float = 0.0, class_weights=None):
+    """`fused`: None = the fused CUDA kernels (yolo_dual_b200/csrc/segloss_b200.cu) whenever they apply (CUDA tensors,
+    label_smoothing 0, at most 16 classes), True = require them, False = the reference's chain of torch ops.
+    `scale`: `pred` is the model's output before its last nearest Upsample (`SegModel(x, lowres=True)`)."""
+    accepts_lowres = True
+
+    def __init__(self, num_classes: int = 12, label_smoothing: float = 0.0, class_weights=None,
+                 fused: Optional[bool] = None):
         super().__init__()
         self.num_classes = num_classes
         w = torch.ones(num_classes) if class_weights is None else torch.as_tensor(class_weights, dtype=torch.float32)
         self.register_buffer("class_weights", w.float())
         self.label_smoothing = label_smoothing
+        self.fused = fused
 
-    def forward(self, pred: torch.Tensor, target: torch.Tensor):
+    def _use_fused(self, pred: torch.Tensor) -> bool:
+        from ._segloss import MAX_CLASSES
+        ok = pred.is_cuda and self.label_smoothing == 0.0 and pred.size(1) <= MAX_CLASSES
+        if self.fused and not ok:
+            raise RuntimeError("fused=True needs CUDA tensors, label_smoothing 0 and at most 16 classes")
+        return ok and self.fused is not False
+
+    def forward(self, pred: torch.Tensor, target: torch.Tensor, scale: int = 1):
         if pred.size(0) != target.size(0):
             raise ValueError(f"batch mismatch: {pred.size(0)} vs {target.size(0)}")
+        full = (pred.shape[2] * scale, pred.shape[3] * scale)
+        if self._use_fused(pred) and tuple(target.shape[1:]) == full:
+            from ._segloss import FusedSegLoss
+            total, ce, dice = FusedSegLoss.apply(pred.float(), target, self.class_weights, int(scale))
+            return total, (total.detach(), ce, dice)
+        if scale != 1:
+            pred = F.interpolate(pred, scale_factor=float(scale), mode="nearest")
         if pred.shape[2:] != target.shape[1:]:
             target = F.interpolate(target.unsqueeze(1).float(), size=pred.shape[2:], mode="nearest").squeeze(1).long()
         pred = pred.float()
@@ -367,13 +414,20 @@ def wrap_ddp(model: nn.Module, device=None):
     return DDP(model, device_ids=ids, static_graph=True)
 
 
+def forward_loss(model, criterion, imgs, labels, autocast_dtype=None):
+    """model forward (optional autocast) + criterion.  When both sides can, the model stops before its deferred
+    nearest Upsample and the loss reads the low-resolution map against the full-resolution labels."""
+    lowres = getattr(criterion, "accepts_lowres", False) and \
+        getattr(getattr(model, "module", model), "_deferred", None) is not None
+    with torch.autocast(imgs.device.type, dtype=autocast_dtype, enabled=autocast_dtype is not None):
+        pred = model(imgs, lowres=True) if lowres else model(imgs)
+    return criterion(pred[0], labels, pred[1]) if lowres else criterion(pred, labels)
+
+
 def train_step(model, criterion, optimizer, imgs, labels, autocast_dtype=None):
     """One optimizer step of the reference hot loop (seg_diceloss_yolov5.py:1073-1103) without
     logging: forward (optional autocast) -> CE+Dice -> backward (DDP all-reduces) -> SGD step."""
-    dev_type = imgs.device.type
-    with torch.autocast(dev_type, dtype=autocast_dtype, enabled=autocast_dtype is not None):
-        pred = model(imgs)
-    loss, parts = criterion(pred, labels)
+    loss, parts = forward_loss(model, criterion, imgs, labels, autocast_dtype)
     optimizer.zero_grad(set_to_none=True)
     loss.backward()
     optimizer.step()

@@ -26,7 +26,7 @@ from typing import Optional
 import torch
 from torch import nn
 
-from .seg import smart_optimizer, wrap_ddp
+from .seg import forward_loss, smart_optimizer, wrap_ddp
 
 HYP = dict(lr0=0.01, lrf=0.2, momentum=0.937, weight_decay=0.0005, label_smoothing=0.0)
 NOMINAL_BATCH = 64
@@ -96,9 +96,7 @@ class Trainer:
         boundary = (self._i + 1) % self.accumulate == 0 or last_of_epoch
         sync = nullcontext() if boundary or not hasattr(self.model, "no_sync") else self.model.no_sync()
         with sync:
-            with torch.autocast(imgs.device.type, dtype=self.autocast_dtype, enabled=self.autocast_dtype is not None):
-                pred = self.model(imgs)
-            loss, parts = self.criterion(pred, labels)
+            loss, parts = forward_loss(self.model, self.criterion, imgs, labels, self.autocast_dtype)
             (self.scaler.scale(loss) if self.scaler else loss).backward()
         if boundary:
             if self.scaler:
