@@ -177,3 +177,26 @@ def test_segloss_library_exports_its_header():
     with pytest.raises(NotImplementedError):
         _segloss.FusedSegLoss.apply(torch.zeros(1, 12, 4, 4), torch.zeros(1, 4, 4, dtype=torch.long),
                                     torch.ones(12), 1)
+
+
+def test_bnact_library_exports_its_header():
+    from yolo_dual_b200 import _bnact
+    from yolo_dual_b200.build import build_bnact
+    build_bnact()
+    lib = _bnact.load()
+    hdr = open(os.path.join(ROOT, "include", "bnact_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(bnact_b200_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_bnact.SYMBOLS)
+    assert lib.bnact_b200_version() == int(re.search(r"#define BNACT_B200_VERSION (\d+)", hdr).group(1))
+    assert [lib.bnact_b200_supported(2, c) for c in (8, 64, 1024, 2048, 4096, 12, 24, 0)] == [1, 1, 1, 1, 0, 0, 0, 0]
+    assert [lib.bnact_b200_supported(0, c) for c in (4, 64, 1024, 2048, 6)] == [1, 1, 1, 0, 0]
+    assert lib.bnact_b200_partial_floats(2, 16 * 80 * 80, 128) % (2 * 128) == 0
+    assert lib.bnact_b200_forward(None, None, None, None, None, None, None, None, 2, 100, 64, 1e-3, 0.03, 1, None) == -2
+    assert lib.bnact_b200_forward(1, 1, 1, 1, None, None, 1, 1, 2, 100, 12, 1e-3, 0.03, 1, None) == -1
+    assert lib.bnact_b200_forward(1, 1, 1, 1, None, None, 1, 1, 2, 100, 64, 1e-3, 0.03, 1, None) == -3
+    # on a CPU tensor the Conv block never reaches the fused call
+    from yolo_dual_b200.ops_dcnv3.modules.conv import Conv
+    m = Conv(8, 16, 1).train()
+    assert not _bnact.usable(torch.zeros(2, 16, 4, 4), m.bn, m.act)
+    assert m(torch.zeros(2, 8, 4, 4)).shape == (2, 16, 4, 4)

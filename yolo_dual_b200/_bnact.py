@@ -1,0 +1,115 @@
+"""ctypes binding of libbnact_b200.so (include/bnact_b200.h) and the autograd front of the fused
+training-mode BatchNorm2d + SiLU used by the `Conv` block.  No fallback behind the fused call: a missing
+library raises; `usable()` only decides whether a given call is one the kernels are written for."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+from torch import nn
+
+from .build import BNACT_LIB
+
+SYMBOLS = ("bnact_b200_version", "bnact_b200_last_error", "bnact_b200_supported", "bnact_b200_partial_floats",
+           "bnact_b200_forward", "bnact_b200_backward")
+_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(BNACT_LIB):
+        raise ImportError(f"{BNACT_LIB} is missing: build it with `python -m yolo_dual_b200.build`")
+    lib = ctypes.CDLL(BNACT_LIB)
+    for s in SYMBOLS:
+        if not hasattr(lib, s):
+            raise ImportError(f"{BNACT_LIB} does not export {s}")
+    vp, ip, i64, fl = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+    lib.bnact_b200_version.restype = ip
+    lib.bnact_b200_last_error.restype = ctypes.c_char_p
+    lib.bnact_b200_supported.argtypes = [ip, ip]
+    lib.bnact_b200_partial_floats.argtypes = [ip, i64, ip]
+    lib.bnact_b200_partial_floats.restype = ctypes.c_size_t
+    lib.bnact_b200_forward.argtypes = [vp] * 8 + [ip, i64, ip, fl, fl, ip, vp]
+    lib.bnact_b200_backward.argtypes = [vp] * 10 + [ip, i64, ip, ip, vp]
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc:
+        raise RuntimeError(f"{what}: {'argument' if rc < 0 else 'CUDA'} error {rc}: "
+                           f"{load().bnact_b200_last_error().decode('utf-8', 'replace')}")
+
+
+def enabled() -> bool:
+    return os.environ.get("YOLO_DUAL_B200_FUSED_BN", "1") != "0"
+
+
+def usable(y: torch.Tensor, bn: nn.Module, act: nn.Module) -> bool:
+    """True when `act(bn(y))` is a call the fused kernels cover: CUDA, training-mode plain BatchNorm2d with affine
+    parameters and a fixed momentum, SiLU or no activation, NHWC-contiguous y with a supported channel count."""
+    if not (y.is_cuda and bn.training and enabled()):
+        return False
+    if type(bn) is not nn.BatchNorm2d or not bn.affine or bn.momentum is None:
+        return False
+    if not isinstance(act, (nn.SiLU, nn.Identity)):
+        return False
+    if y.dim() != 4 or y.dtype not in _DTYPES or y.numel() // y.size(1) < 2:
+        return False
+    if bn.weight.dtype != torch.float32 or not y.is_contiguous(memory_format=torch.channels_last):
+        return False
+    return bool(load().bnact_b200_supported(_DTYPES[y.dtype], y.size(1)))
+
+
+class FusedBNAct(torch.autograd.Function):
+    """z = act(batch_norm(x; batch statistics)) for NHWC-contiguous x; updates the running statistics in place."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum, silu):
+        n, c, h, w = x.shape
+        m = n * h * w
+        dt = _DTYPES[x.dtype]
+        lib = load()
+        z = torch.empty_like(x)                                   # keeps the NHWC strides
+        save = torch.empty(4 * c, dtype=torch.float32, device=x.device)
+        partial = torch.empty(lib.bnact_b200_partial_floats(dt, m, c), dtype=torch.float32, device=x.device)
+        with torch.cuda.device_of(x):
+            _check(lib.bnact_b200_forward(
+                x.data_ptr(), z.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                running_mean.data_ptr() if running_mean is not None else None,
+                running_var.data_ptr() if running_var is not None else None,
+                save.data_ptr(), partial.data_ptr(), dt, m, c, float(eps), float(momentum), int(silu),
+                torch.cuda.current_stream().cuda_stream), "bnact_b200_forward")
+        ctx.save_for_backward(x, gamma, beta, save)
+        ctx.silu = int(silu)
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        x, gamma, beta, save = ctx.saved_tensors
+        n, c, h, w = x.shape
+        m = n * h * w
+        dt = _DTYPES[x.dtype]
+        lib = load()
+        gz = gz.to(x.dtype).contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_like(x)
+        small = torch.empty(4 * c, dtype=torch.float32, device=x.device)   # dgamma, dbeta, coef[2]
+        partial = torch.empty(lib.bnact_b200_partial_floats(dt, m, c), dtype=torch.float32, device=x.device)
+        with torch.cuda.device_of(x):
+            _check(lib.bnact_b200_backward(
+                x.data_ptr(), gz.data_ptr(), dx.data_ptr(), gamma.data_ptr(), beta.data_ptr(), save.data_ptr(),
+                small.data_ptr(), small[c:].data_ptr(), small[2 * c:].data_ptr(), partial.data_ptr(), dt, m, c,
+                ctx.silu, torch.cuda.current_stream().cuda_stream), "bnact_b200_backward")
+        return dx, small[:c], small[c:2 * c], None, None, None, None, None
+
+
+def bn_act(y: torch.Tensor, bn: nn.BatchNorm2d, act: nn.Module) -> torch.Tensor:
+    """act(bn(y)) through the fused kernels (callers check `usable` first)."""
+    if bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    rm, rv = (bn.running_mean, bn.running_var) if bn.track_running_stats else (None, None)
+    return FusedBNAct.apply(y, bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum, isinstance(act, nn.SiLU))

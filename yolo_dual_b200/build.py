@@ -36,6 +36,11 @@ SEGLOSS_LIB = os.path.join(CSRC, "libsegloss_b200.so")
 SEGLOSS_DEPS = [os.path.join(CSRC, "segloss_b200.cu"), os.path.join(ROOT, "include", "segloss_b200.h")]
 
 
+# third: fused training-mode BatchNorm2d + SiLU of the Conv block (include/bnact_b200.h)
+BNACT_LIB = os.path.join(CSRC, "libbnact_b200.so")
+BNACT_DEPS = [os.path.join(CSRC, "bnact_b200.cu"), os.path.join(ROOT, "include", "bnact_b200.h")]
+
+
 def _nvcc():
     for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -71,8 +76,16 @@ def build_segloss(force: bool = False, verbose: bool = False) -> str:
     return SEGLOSS_LIB
 
 
+def build_bnact(force: bool = False, verbose: bool = False) -> str:
+    if force or not os.path.exists(BNACT_LIB) or \
+            any(os.path.getmtime(d) > os.path.getmtime(BNACT_LIB) for d in BNACT_DEPS):
+        _run_nvcc(BNACT_LIB, BNACT_DEPS[:1], verbose)
+    return BNACT_LIB
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     build_segloss(force, verbose)
+    build_bnact(force, verbose)
     if not force and not _stale():
         return LIB
     _run_nvcc(LIB, [os.path.join(CSRC, s) for s in SOURCES], verbose)

@@ -31,7 +31,12 @@ class Conv(nn.Module):
             self.act = act if isinstance(act, nn.Module) else nn.Identity()
 
     def forward(self, x):
-        return self.act(self.bn(self.conv(x)))
+        y = self.conv(x)
+        if y.is_cuda and self.training:
+            from ... import _bnact   # fused batch-statistics BatchNorm + SiLU (csrc/bnact_b200.cu) where it applies
+            if _bnact.usable(y, self.bn, self.act):
+                return _bnact.bn_act(y, self.bn, self.act)
+        return self.act(self.bn(y))
 
     def forward_fuse(self, x):  # after conv+bn folding
         return self.act(self.conv(x))
