@@ -200,3 +200,22 @@ def test_bnact_library_exports_its_header():
     m = Conv(8, 16, 1).train()
     assert not _bnact.usable(torch.zeros(2, 16, 4, 4), m.bn, m.act)
     assert m(torch.zeros(2, 8, 4, 4)).shape == (2, 16, 4, 4)
+
+
+def test_resize_library_exports_its_header():
+    from yolo_dual_b200 import _resize
+    from yolo_dual_b200.build import build_resize
+    build_resize()
+    lib = _resize.load()
+    hdr = open(os.path.join(ROOT, "include", "resize_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(resize_b200_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_resize.SYMBOLS)
+    assert lib.resize_b200_version() == int(re.search(r"#define RESIZE_B200_VERSION (\d+)", hdr).group(1))
+    assert lib.resize_b200_supported(2, 64, 10, 10, 20, 20, 0) == 1
+    assert lib.resize_b200_supported(2, 64, 10, 10, 25, 20, 0) == 0          # nearest: integer factors only
+    assert lib.resize_b200_supported(2, 64, 10, 10, 25, 7, 1) == 1
+    assert lib.resize_b200_supported(2, 12, 10, 10, 20, 20, 1) == 0          # 12 bf16 channels: not whole vectors
+    assert lib.resize_b200_forward(None, None, 2, 1, 4, 4, 8, 8, 8, 0, None) == -2
+    assert lib.resize_b200_forward(1, 1, 2, 1, 4, 4, 8, 8, 8, 0, None) == -3
+    assert not _resize.usable(torch.zeros(1, 8, 4, 4), (8, 8), "nearest")   # CPU tensors stay with torch

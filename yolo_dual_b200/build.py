@@ -41,6 +41,11 @@ BNACT_LIB = os.path.join(CSRC, "libbnact_b200.so")
 BNACT_DEPS = [os.path.join(CSRC, "bnact_b200.cu"), os.path.join(ROOT, "include", "bnact_b200.h")]
 
 
+# fourth: NHWC nearest / bilinear resize of the seg heads (include/resize_b200.h)
+RESIZE_LIB = os.path.join(CSRC, "libresize_b200.so")
+RESIZE_DEPS = [os.path.join(CSRC, "resize_b200.cu"), os.path.join(ROOT, "include", "resize_b200.h")]
+
+
 def _nvcc():
     for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -83,9 +88,17 @@ def build_bnact(force: bool = False, verbose: bool = False) -> str:
     return BNACT_LIB
 
 
+def build_resize(force: bool = False, verbose: bool = False) -> str:
+    if force or not os.path.exists(RESIZE_LIB) or \
+            any(os.path.getmtime(d) > os.path.getmtime(RESIZE_LIB) for d in RESIZE_DEPS):
+        _run_nvcc(RESIZE_LIB, RESIZE_DEPS[:1], verbose)
+    return RESIZE_LIB
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     build_segloss(force, verbose)
     build_bnact(force, verbose)
+    build_resize(force, verbose)
     if not force and not _stale():
         return LIB
     _run_nvcc(LIB, [os.path.join(CSRC, s) for s in SOURCES], verbose)

@@ -135,22 +135,35 @@ class SPPF(nn.Module):
         return self.cv2(torch.cat([x, y1, y2, self.m(y2)], 1))
 
 
-def _resize_in_own_dtype(fn, x, **kw):
-    """CUDA autocast runs the upsample_* ops in float32 whatever comes in, and everything downstream of one
-    (torch.cat with bf16 neighbours, the copies in front of the next convolution) then moves 4-byte elements.
-    Resizing in the tensor's own 16-bit dtype gives the same numbers: nearest replication is exact, and the bilinear
-    kernels interpolate in float and round once — the rounding the next convolution's autocast cast would apply."""
-    if x.is_cuda and torch.is_autocast_enabled():
-        with torch.autocast("cuda", enabled=False):
-            return fn(x, **kw)
-    return fn(x, **kw)
+def _resize(x: torch.Tensor, size, mode: str) -> torch.Tensor:
+    """F.interpolate(x, size, mode) ('nearest' | 'bilinear' with align_corners=False).
+
+    NHWC-contiguous CUDA activations go through the repo's own kernels (csrc/resize_b200.cu: same index
+    arithmetic as ATen, gather backward).  Otherwise torch — but in the tensor's own dtype: CUDA autocast runs the
+    upsample_* ops in float32 whatever comes in, and everything downstream of one (torch.cat with bf16 neighbours,
+    the copies in front of the next convolution) then moves 4-byte elements.  Same numbers either way: nearest
+    replication is exact, and the bilinear kernels interpolate in float and round once — the rounding the next
+    convolution's autocast cast would apply."""
+    kw = {} if mode == "nearest" else {"align_corners": False}
+    if x.is_cuda:
+        from . import _resize as native
+        if native.usable(x, size, mode):
+            return native.resize(x, size, mode)
+        if torch.is_autocast_enabled():
+            with torch.autocast("cuda", enabled=False):
+                return F.interpolate(x, size=tuple(size), mode=mode, **kw)
+    return F.interpolate(x, size=tuple(size), mode=mode, **kw)
 
 
 class Upsample(nn.Upsample):
-    """nn.Upsample (the layer tables' 'nn.Upsample' / 'Upsample') that keeps its input's dtype under autocast."""
+    """nn.Upsample (the layer tables' 'nn.Upsample' / 'Upsample'): integer-factor nearest replication through
+    `_resize`; any other configuration is nn.Upsample itself."""
 
     def forward(self, x):
-        return _resize_in_own_dtype(super().forward, x)
+        s = self.scale_factor
+        if self.mode == "nearest" and s is not None and not isinstance(s, (tuple, list)) and float(s) == int(s):
+            return _resize(x, (x.shape[2] * int(s), x.shape[3] * int(s)), "nearest")
+        return super().forward(x)
 
 
 class Concat(nn.Module):
@@ -163,8 +176,7 @@ class Concat(nn.Module):
 
     def forward(self, xs: Sequence[torch.Tensor]):
         size = xs[0].shape[2:]
-        xs = [x if x.shape[2:] == size else
-              _resize_in_own_dtype(F.interpolate, x, size=size, mode="bilinear", align_corners=False) for x in xs]
+        xs = [x if x.shape[2:] == size else _resize(x, size, "bilinear") for x in xs]
         return torch.cat(xs, self.d)
 
 
