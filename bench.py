@@ -306,17 +306,49 @@ def time_seg(dev, dist, world, steps, warmup, batch, model_name, channels_last=T
     g = torch.Generator().manual_seed(1 + (dist.get_rank() if dist is not None else 0))
     imgs_h = torch.randn(batch, 3, 640, 640, generator=g).pin_memory()
     lab_h = torch.randint(0, 12, (batch, 640, 640), generator=g).pin_memory()
+    # the data-loader side of the loop: batch k+1 is uploaded on a copy stream while step k computes (two device
+    # slots), and the loss of step k is read back into pinned memory and looked at one step later
+    copy_st = torch.cuda.Stream(device=dev)
+    slots = [(torch.empty(batch, 3, 640, 640, device=dev), torch.empty(batch, 640, 640, dtype=torch.int64, device=dev))
+             for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    loss_h = torch.zeros(2, dtype=torch.float32).pin_memory()
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    state = {"k": 0, "last": float("nan")}
+
+    def upload(k):
+        with torch.cuda.stream(copy_st):
+            copy_st.wait_event(freed[k % 2])
+            slots[k % 2][0].copy_(imgs_h, non_blocking=True)
+            slots[k % 2][1].copy_(lab_h, non_blocking=True)
+            ready[k % 2].record(copy_st)
+
+    for ev in freed:
+        ev.record()
+    upload(0)
 
     def one():
-        imgs = imgs_h.to(dev, non_blocking=True)
+        k = state["k"]
+        upload(k + 1)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ready[k % 2])
+        imgs, lab = slots[k % 2]
         if channels_last:
             imgs = imgs.contiguous(memory_format=torch.channels_last)
-        lab = lab_h.to(dev, non_blocking=True)
         loss, _ = seg.train_step(ddp, crit, opt, imgs, lab, autocast_dtype=torch.bfloat16)
-        return float(loss)  # D2H: the step's result
+        freed[k % 2].record(cur)
+        loss_h[k % 2].copy_(loss, non_blocking=True)   # D2H: the step's result
+        loss_ev[k % 2].record(cur)
+        if k:
+            loss_ev[(k - 1) % 2].synchronize()
+            state["last"] = float(loss_h[(k - 1) % 2])
+        state["k"] = k + 1
+        return state["last"]
 
     for _ in range(warmup):
         last = one()
+    torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -326,6 +358,7 @@ def time_seg(dev, dist, world, steps, warmup, batch, model_name, channels_last=T
         last = one()
     e1.record()
     torch.cuda.synchronize()
+    last = float(loss_h[(state["k"] - 1) % 2])
     ms = e0.elapsed_time(e1)
     if dist is not None:
         dist.barrier()
@@ -339,6 +372,10 @@ def time_seg(dev, dist, world, steps, warmup, batch, model_name, channels_last=T
             "memory_format": "channels_last" if channels_last else "contiguous",
             "optimizer": "SGD nesterov 3 groups", "params": n_params, "loss_last": last,
             "h2d_bytes_per_step": imgs_h.numel() * 4 + lab_h.numel() * 8, "d2h_bytes_per_step": 4,
+            "input_pipeline": "pinned host batch uploaded every step on a copy stream, one step ahead; loss read back "
+                              "into pinned memory every step and inspected one step later",
+            "fused": "deferred last Upsample, fused CE+Dice loss, fused BN+SiLU, NHWC resize kernels (this repo's "
+                     "segloss_b200 / bnact_b200 / resize_b200)",
             "data_parallel": f"DDP x{world} (NCCL all-reduce of {n_params * 4 / 1e6:.1f} MB fp32 grads)" if world > 1 else "single GPU"}
 
 
@@ -451,7 +488,9 @@ def main():
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-seg", action="store_true")
     ap.add_argument("--seg-steps", type=int, default=10)
-    ap.add_argument("--seg-batch", type=int, default=16)
+    ap.add_argument("--seg-batch", type=int, default=16, help="images per GPU (weak scaling)")
+    ap.add_argument("--seg-global-batch", type=int, default=0,
+                    help="fixed global batch split over the GPUs (strong scaling, BASELINE configs[3]: 64)")
     ap.add_argument("--seg-model", default="yolov5seg", choices=["yolov5seg", "yolov8seg"])
     ap.add_argument("--seg-nchw", action="store_true", help="keep NCHW activations in the seg model")
     a = ap.parse_args()
@@ -517,7 +556,9 @@ def main():
         del wl
         torch.cuda.empty_cache()
         try:
-            seg_res = time_seg(dev, dist, world, a.seg_steps, 3, a.seg_batch, a.seg_model, not a.seg_nchw)
+            seg_batch = a.seg_global_batch // world if a.seg_global_batch else a.seg_batch
+            seg_res = time_seg(dev, dist, world, a.seg_steps, 3, seg_batch, a.seg_model, not a.seg_nchw)
+            seg_res["scaling"] = "strong (global batch fixed)" if a.seg_global_batch else "weak (batch per GPU fixed)"
         except Exception as ex:
             if world > 1:
                 raise  # a rank must not leave a collective half-done
