@@ -6,13 +6,23 @@ sys.path.insert(0, ROOT)
 import torch
 from yolo_dual_b200 import seg
 
-dev = torch.device("cuda:0")
+import torch.distributed as dist
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+torch.cuda.set_device(dev)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+    if rank:
+        sys.stdout = open(os.devnull, "w")
 name = sys.argv[1] if len(sys.argv) > 1 else "yolov5seg"
 cfg = {"yolov5seg": seg.YOLOV5_SEG, "yolov8seg": seg.YOLOV8_SEG}[name]
 torch.manual_seed(0)
 torch.backends.cudnn.benchmark = True
 model = seg.SegModel(cfg, dcn="dcnv3").to(dev).to(memory_format=torch.channels_last)
 crit = seg.SegmentationLoss(12, class_weights=seg.CAMVID_CLASS_WEIGHTS).to(dev)
+net = model
+model = seg.wrap_ddp(model, dev)
 opt = seg.smart_optimizer(model)
 model.train()
 imgs = torch.randn(16, 3, 640, 640, device=dev).contiguous(memory_format=torch.channels_last)
@@ -44,7 +54,7 @@ def phases():
 ts = [phases()[0] for _ in range(5)][-1]
 print("phases ms: model fwd %.2f, loss fwd %.2f, backward %.2f, optimizer %.2f" % tuple(ts))
 pred = phases()[1]
-print("pred", pred.dtype, tuple(pred.shape), pred.stride(), "deferred upsample:", model._deferred)
+print("pred", pred.dtype, tuple(pred.shape), pred.stride(), "deferred upsample:", net._deferred, "world", world)
 with torch.autocast("cuda", dtype=torch.bfloat16):
     t = torch.randn(2, 8, 4, 4, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
     print("autocast dtypes: nearest", torch.nn.Upsample(scale_factor=2.0)(t).dtype,

@@ -423,7 +423,7 @@ def wrap_ddp(model: nn.Module, device=None):
         return model
     from torch.nn.parallel import DistributedDataParallel as DDP
     ids = [device.index] if device is not None and device.type == "cuda" else None
-    return DDP(model, device_ids=ids, static_graph=True)
+    return DDP(model, device_ids=ids, static_graph=True, gradient_as_bucket_view=True)  # grads live in the buckets
 
 
 def forward_loss(model, criterion, imgs, labels, autocast_dtype=None):
