@@ -12,7 +12,8 @@
 namespace {
 
 constexpr int THREADS = 256;
-constexpr int UNROLL = 4;
+constexpr int UNROLL = 4;        // 16-byte loads in flight per thread in the apply kernel
+constexpr int UNROLL_STATS = 8;  // ... in the statistics kernel (no stores, few registers)
 constexpr int MAX_BLOCKS = 148 * 4;
 constexpr int FIN_CH = 32, FIN_LANES = 32;   // finalize: a block sums the partials of 32 channels with 32 lanes each
 thread_local char g_err[256] = "";
@@ -120,12 +121,12 @@ stats_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int64_t M
 #pragma unroll
     for (int i = 0; i < N; ++i) s[i] = q[i] = 0.f;
     int64_t r = g / CV;
-    for (; r + (UNROLL - 1) * rs < M; r += UNROLL * rs) {
-        uint4 v[UNROLL];
+    for (; r + (UNROLL_STATS - 1) * rs < M; r += UNROLL_STATS * rs) {
+        uint4 v[UNROLL_STATS];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) v[u] = __ldg(x + (r + u * rs) * CV + cv);
+        for (int u = 0; u < UNROLL_STATS; ++u) v[u] = __ldg(x + (r + u * rs) * CV + cv);
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
+        for (int u = 0; u < UNROLL_STATS; ++u) {
             float f[N];
             Vec<T>::unpack(v[u], f);
 #pragma unroll
@@ -237,7 +238,7 @@ bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gz, con
     load_consts<N>(beta, cv * N, be);
 #pragma unroll
     for (int i = 0; i < N; ++i) a[i] = b[i] = 0.f;
-    constexpr int U = 2;
+    constexpr int U = 4;
     int64_t r = g / CV;
     for (; r + (U - 1) * rs < M; r += U * rs) {
         uint4 vx[U], vg[U];
@@ -302,7 +303,7 @@ bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gz, uint
     load_consts<N>(beta, cv * N, be);
     load_consts<N>(coef, cv * N, k1);
     load_consts<N>(coef + C, cv * N, k2);
-    constexpr int U = 2;
+    constexpr int U = 4;
     int64_t r = g / CV;
     for (; r < M; r += U * rs) {
         uint4 vx[U], vg[U];
