@@ -74,6 +74,13 @@ template <> struct Vec<__half> {
     }
 };
 
+// 16-byte read-only streaming load (ld.global.nc), kept in program order by asm volatile
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
 template <int N>
 __device__ __forceinline__ void load_consts(const float* __restrict__ p, int c0, float (&f)[N]) {
 #pragma unroll
@@ -124,7 +131,7 @@ stats_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int64_t M
     for (; r + (UNROLL_STATS - 1) * rs < M; r += UNROLL_STATS * rs) {
         uint4 v[UNROLL_STATS];
 #pragma unroll
-        for (int u = 0; u < UNROLL_STATS; ++u) v[u] = __ldg(x + (r + u * rs) * CV + cv);
+        for (int u = 0; u < UNROLL_STATS; ++u) v[u] = ldg_stream(x + (r + u * rs) * CV + cv);
 #pragma unroll
         for (int u = 0; u < UNROLL_STATS; ++u) {
             float f[N];
@@ -203,7 +210,7 @@ apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ z, const float* __
     for (; r + (UNROLL - 1) * rs < M; r += UNROLL * rs) {
         uint4 v[UNROLL];
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u) v[u] = __ldg(x + (r + u * rs) * CV + cv);
+        for (int u = 0; u < UNROLL; ++u) v[u] = ldg_stream(x + (r + u * rs) * CV + cv);
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             float f[N];
@@ -240,35 +247,40 @@ bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gz, con
     for (int i = 0; i < N; ++i) a[i] = b[i] = 0.f;
     constexpr int U = 4;
     int64_t r = g / CV;
-    for (; r + (U - 1) * rs < M; r += U * rs) {
-        uint4 vx[U], vg[U];
+    uint4 cx[U], cg[U], nx[U], ng[U];                         // software pipeline as in stats_kernel
+    const uint4 zero = make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int u = 0; u < U; ++u) { vx[u] = __ldg(x + (r + u * rs) * CV + cv); vg[u] = __ldg(gz + (r + u * rs) * CV + cv); }
+    for (int u = 0; u < U; ++u) {
+        const bool in = r + u * rs < M;
+        cx[u] = in ? ldg_stream(x + (r + u * rs) * CV + cv) : zero;
+        cg[u] = in ? ldg_stream(gz + (r + u * rs) * CV + cv) : zero;
+    }
+    while (r < M) {
+        const int64_t rn = r + U * rs;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            float f[N], gzz[N];
-            Vec<T>::unpack(vx[u], f);
-            Vec<T>::unpack(vg[u], gzz);
+            const bool in = rn + u * rs < M;
+            nx[u] = in ? ldg_stream(x + (rn + u * rs) * CV + cv) : zero;
+            ng[u] = in ? ldg_stream(gz + (rn + u * rs) * CV + cv) : zero;
+        }
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const float d = f[i] - mean[i];
-                const float gy = SILU ? gzz[i] * dsilu_f(fmaf(d, sc[i], be[i])) : gzz[i];
-                a[i] += gy;
-                b[i] = fmaf(gy, d, b[i]);
+        for (int u = 0; u < U; ++u) {
+            if (r + u * rs < M) {
+                float f[N], gzz[N];
+                Vec<T>::unpack(cx[u], f);
+                Vec<T>::unpack(cg[u], gzz);
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const float d = f[i] - mean[i];
+                    const float gy = SILU ? gzz[i] * dsilu_f(fmaf(d, sc[i], be[i])) : gzz[i];
+                    a[i] += gy;
+                    b[i] = fmaf(gy, d, b[i]);
+                }
             }
         }
-    }
-    for (; r < M; r += rs) {
-        float f[N], gzz[N];
-        Vec<T>::unpack(__ldg(x + r * CV + cv), f);
-        Vec<T>::unpack(__ldg(gz + r * CV + cv), gzz);
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const float d = f[i] - mean[i];
-            const float gy = SILU ? gzz[i] * dsilu_f(fmaf(d, sc[i], be[i])) : gzz[i];
-            a[i] += gy;
-            b[i] = fmaf(gy, d, b[i]);
-        }
+        for (int u = 0; u < U; ++u) { cx[u] = nx[u]; cg[u] = ng[u]; }
+        r = rn;
     }
     block_partials<N>(a, b, CV, C, partial);
 }
