@@ -1,0 +1,307 @@
+"""YOLOv5 detection models from the reference's yaml layer tables, with `C3_DCNV3` in the module set.
+
+SURVEY §8 (f) rank 4: the reference builds its detection models with `parse_model`
+(/root/reference/models/yolo.py:296-390), whose module set knows `C3_DCN` (torchvision DeformConv2d) but not the
+DCNv3 blocks; the paste-in notes (`models/ops_dcnv3/common and yolo.py:40-43`) ask the user to register `C3_DCNV3`
+by hand and warn that the constructor's CPU stride probe cannot run the CUDA-only op.  This module is that
+registration as importable code:
+
+  * `build_layers(cfg, ch)`  — the yaml grammar `[from, number, module, args]` with depth / width multiples
+    (`parse_model`, yolo.py:296-390), over the modules the DCN yamls use; channel bookkeeping identical
+    (`make_divisible(c2 * gw, 8)`, repeats folded into C3-type blocks);
+  * strides are derived from the layer table (product of convolution strides over nearest-Upsample factors along the
+    `from` graph) instead of a 256x256 CPU forward (yolo.py:192-195) — DCNv3 has no CPU path;
+  * `Detect` (yolo.py:38-87): same raw training output and the same box decoding at inference;
+  * `DetectionModel` (yolo.py:165-262): `model` (nn.Sequential, so checkpoint keys are `model.<i>....`), `save`,
+    `stride`, `names`, Detect bias initialisation, YOLOv5's BatchNorm eps / momentum;
+  * `YOLOV5N_DCNV3`: `models/backbone/yolov5n-DCN.yaml` with its three `C3_DCN` slots as `C3_DCNV3`
+    (`dcn="none"` builds the plain `C3` there — the stock yolov5n — for A/B runs and CPU tests).
+"""
+from __future__ import annotations
+
+import math
+from copy import deepcopy
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+
+from .blocks import C2f_DCNV3, C3_DCNV3
+from .ops_dcnv3.modules.conv import Conv
+
+_ANCHORS = [[10, 13, 16, 30, 33, 23], [30, 61, 62, 45, 59, 119], [116, 90, 156, 198, 373, 326]]
+YOLOV5N_DCNV3: Dict = {  # models/backbone/yolov5n-DCN.yaml, C3_DCN -> C3_DCNV3
+    "nc": 80, "depth_multiple": 0.33, "width_multiple": 0.25, "anchors": _ANCHORS,
+    "backbone": [
+        [-1, 1, "Conv", [64, 6, 2, 2]], [-1, 1, "Conv", [128, 3, 2]], [-1, 3, "C3", [128]],
+        [-1, 1, "Conv", [256, 3, 2]], [-1, 6, "C3_DCNV3", [256]],
+        [-1, 1, "Conv", [512, 3, 2]], [-1, 9, "C3_DCNV3", [512]],
+        [-1, 1, "Conv", [1024, 3, 2]], [-1, 3, "C3_DCNV3", [1024]], [-1, 1, "SPPF", [1024, 5]],
+    ],
+    "head": [
+        [-1, 1, "Conv", [512, 1, 1]], [-1, 1, "nn.Upsample", [None, 2, "nearest"]], [[-1, 6], 1, "Concat", [1]],
+        [-1, 3, "C3", [512, False]],
+        [-1, 1, "Conv", [256, 1, 1]], [-1, 1, "nn.Upsample", [None, 2, "nearest"]], [[-1, 4], 1, "Concat", [1]],
+        [-1, 3, "C3", [256, False]],
+        [-1, 1, "Conv", [256, 3, 2]], [[-1, 14], 1, "Concat", [1]], [-1, 3, "C3", [512, False]],
+        [-1, 1, "Conv", [512, 3, 2]], [[-1, 10], 1, "Concat", [1]], [-1, 3, "C3", [1024, False]],
+        [[17, 20, 23], 1, "Detect", ["nc", "anchors"]],
+    ],
+}
+
+
+def make_divisible(x, divisor):
+    """Smallest multiple of `divisor` that is >= x (utils/general.py make_divisible)."""
+    return math.ceil(x / divisor) * divisor
+
+
+# ---------------------------------------------------------------------------------------------
+# blocks of models/common.py that the DCN yamls use (inner-residual Bottleneck, unlike the seg scripts' C3)
+# ---------------------------------------------------------------------------------------------
+class Bottleneck(nn.Module):
+    """models/common.py Bottleneck: 1x1 -> 3x3, residual when shapes allow."""
+
+    def __init__(self, c1, c2, shortcut=True, g=1, e=0.5):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c_, c2, 3, 1, g=g)
+        self.add = shortcut and c1 == c2
+
+    def forward(self, x):
+        y = self.cv2(self.cv1(x))
+        return x + y if self.add else y
+
+
+class C3(nn.Module):
+    """models/common.py:161-172."""
+
+    def __init__(self, c1, c2, n=1, shortcut=True, g=1, e=0.5):
+        super().__init__()
+        c_ = int(c2 * e)
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c1, c_, 1, 1)
+        self.cv3 = Conv(2 * c_, c2, 1)
+        self.m = nn.Sequential(*(Bottleneck(c_, c_, shortcut, g, e=1.0) for _ in range(n)))
+
+    def forward(self, x):
+        return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), 1))
+
+
+class SPPF(nn.Module):
+    """models/common.py SPPF: three chained 5x5 max-pools."""
+
+    def __init__(self, c1, c2, k=5):
+        super().__init__()
+        c_ = c1 // 2
+        self.cv1 = Conv(c1, c_, 1, 1)
+        self.cv2 = Conv(c_ * 4, c2, 1, 1)
+        self.m = nn.MaxPool2d(kernel_size=k, stride=1, padding=k // 2)
+
+    def forward(self, x):
+        x = self.cv1(x)
+        y1 = self.m(x)
+        y2 = self.m(y1)
+        return self.cv2(torch.cat((x, y1, y2, self.m(y2)), 1))
+
+
+class Concat(nn.Module):
+    """models/common.py Concat (no resizing: the detection yamls only join equal-sized maps)."""
+
+    def __init__(self, dimension=1):
+        super().__init__()
+        self.d = dimension
+
+    def forward(self, xs: Sequence[torch.Tensor]):
+        return torch.cat(list(xs), self.d)
+
+
+class Detect(nn.Module):
+    """YOLOv5 detection head (models/yolo.py:38-87).
+
+    training: list over levels of raw `[bs, na, ny, nx, no]`; eval: `(decoded [bs, sum(na*ny*nx), no], raw list)`
+    with `xy = (2 sigmoid - 0.5 + grid) * stride`, `wh = (2 sigmoid)^2 * anchor * stride`."""
+    export = False
+    dynamic = False
+
+    def __init__(self, nc=80, anchors=(), ch=(), inplace=True):
+        super().__init__()
+        self.nc, self.no = nc, nc + 5
+        self.nl, self.na = len(anchors), len(anchors[0]) // 2
+        self.register_buffer("anchors", torch.tensor(anchors).float().view(self.nl, -1, 2))
+        self.register_buffer("stride", torch.zeros(self.nl), persistent=False)
+        self.m = nn.ModuleList(nn.Conv2d(c, self.no * self.na, 1) for c in ch)
+        self.inplace = inplace
+        self._grids: List[Optional[Tuple[torch.Tensor, torch.Tensor]]] = [None] * self.nl
+
+    def _grid(self, i, nx, ny, like: torch.Tensor):
+        cached = self._grids[i]
+        if self.dynamic or cached is None or cached[0].shape[2:4] != (ny, nx) or cached[0].device != like.device:
+            d, t = like.device, self.anchors.dtype
+            yv, xv = torch.meshgrid(torch.arange(ny, device=d, dtype=t), torch.arange(nx, device=d, dtype=t),
+                                    indexing="ij")
+            shape = (1, self.na, ny, nx, 2)
+            grid = torch.stack((xv, yv), 2).expand(shape) - 0.5
+            anchor = (self.anchors[i].to(d) * self.stride[i].to(d)).view(1, self.na, 1, 1, 2).expand(shape)
+            cached = self._grids[i] = (grid, anchor)
+        return cached
+
+    def forward(self, xs: List[torch.Tensor]):
+        raw, decoded = [], []
+        for i, x in enumerate(xs):
+            x = self.m[i](x)
+            bs, _, ny, nx = x.shape
+            x = x.view(bs, self.na, self.no, ny, nx).permute(0, 1, 3, 4, 2).contiguous()
+            raw.append(x)
+            if not self.training:
+                grid, anchor = self._grid(i, nx, ny, x)
+                xy, wh, conf = x.sigmoid().split((2, 2, self.nc + 1), 4)
+                xy = (xy * 2 + grid) * self.stride[i]
+                wh = (wh * 2) ** 2 * anchor
+                decoded.append(torch.cat((xy, wh, conf), 4).view(bs, self.na * nx * ny, self.no))
+        if self.training:
+            return raw
+        return (torch.cat(decoded, 1),) if self.export else (torch.cat(decoded, 1), raw)
+
+
+# ---------------------------------------------------------------------------------------------
+# the yaml grammar
+# ---------------------------------------------------------------------------------------------
+_WIDTH_SCALED = {"Conv": Conv, "C3": C3, "SPPF": SPPF, "C3_DCNV3": C3_DCNV3, "C2f_DCNV3": C2f_DCNV3}
+_REPEAT_INSIDE = {"C3", "C3_DCNV3", "C2f_DCNV3"}     # blocks that take the repeat count as an argument
+_ALIASES = {"C3_DCN": "C3_DCNV3", "C2f_DCN": "C2f_DCNV3", "Upsample": "nn.Upsample"}
+
+
+def build_layers(cfg: Dict, ch: Sequence[int] = (3,), dcn: str = "dcnv3", dcn_group: Optional[int] = None,
+                 fused_softmax: bool = False):
+    """Layer table -> (nn.Sequential, sorted save list, output channels per layer, stride per layer).
+
+    Mirrors `parse_model` (models/yolo.py:296-390) for the modules above.  `dcn="none"` builds `C3` in the DCN
+    slots; `C3_DCN` / `C2f_DCN` in a table are read as the DCNv3 blocks (the torchvision-DCNv2 block of the
+    reference is outside this repo's scope)."""
+    if dcn not in ("dcnv3", "none"):
+        raise ValueError("dcn must be 'dcnv3' or 'none'")
+    cfg = deepcopy(cfg)
+    anchors, nc = cfg["anchors"], cfg["nc"]
+    gd, gw = cfg.get("depth_multiple", 1.0), cfg.get("width_multiple", 1.0)
+    na = len(anchors[0]) // 2 if isinstance(anchors, list) else anchors
+    no = na * (nc + 5)
+    chans: List[int] = list(ch)
+    strides: List[float] = []
+    layers, save = [], []
+    c2 = chans[-1]
+
+    def src_stride(f):
+        return 1.0 if not strides else strides[f]
+
+    for i, (f, n, name, args) in enumerate(cfg["backbone"] + cfg["head"]):
+        name = _ALIASES.get(name, name)
+        args = [{"nc": nc, "anchors": anchors}.get(a, a) if isinstance(a, str) else a for a in args]
+        args = [None if a == "None" else a for a in args]
+        n = max(round(n * gd), 1) if n > 1 else n
+        if name in _WIDTH_SCALED:
+            c1, c2 = chans[f], args[0]
+            if c2 != no:
+                c2 = make_divisible(c2 * gw, 8)
+            rest = list(args[1:])
+            if name in _REPEAT_INSIDE:
+                kind = name
+                if name.endswith("DCNV3") and dcn == "none":
+                    kind = "C3"
+                    if name.startswith("C2f"):
+                        raise NotImplementedError("dcn='none' is only defined for the C3 slots of the detection yamls")
+                if kind == "C3":
+                    make = lambda c1=c1, c2=c2, n=n, rest=rest: C3(c1, c2, n, *rest)
+                else:
+                    make = lambda c1=c1, c2=c2, n=n, rest=rest, kind=kind: _WIDTH_SCALED[kind](
+                        c1, c2, n, *rest, dcn_group=dcn_group, fused_softmax=fused_softmax)
+                n = 1
+            else:
+                make = lambda c1=c1, c2=c2, rest=rest, name=name: _WIDTH_SCALED[name](c1, c2, *rest)
+            mod = make()
+            s = src_stride(f) * (mod.conv.stride[0] if name == "Conv" else 1)
+        elif name == "nn.Upsample":
+            scale = args[1] if len(args) > 1 and args[1] is not None else 2
+            mode = args[2] if len(args) > 2 else "nearest"
+            from .seg import Upsample     # integer-factor nearest replication through resize_b200 on NHWC activations
+            make = lambda scale=scale, mode=mode: Upsample(scale_factor=float(scale), mode=mode)
+            mod, c2, s = make(), chans[f], src_stride(f) / float(scale)
+        elif name == "Concat":
+            make = lambda args=args: Concat(*args)
+            mod, c2 = make(), sum(chans[x] for x in f)
+            s = src_stride(f[0])
+            if any(src_stride(x) != s for x in f):
+                raise ValueError(f"layer {i}: Concat joins maps of different strides {[src_stride(x) for x in f]}")
+        elif name == "Detect":
+            a = args[1]
+            if isinstance(a, int):
+                a = [list(range(a * 2))] * len(f)
+            make = None
+            mod = Detect(args[0], a, [chans[x] for x in f])
+            mod.stride.copy_(torch.tensor([src_stride(x) for x in f]))
+            c2, s = chans[f[0]], src_stride(f[0])
+        else:
+            raise NotImplementedError(f"layer {i}: module {name!r} is not in this module set")
+        if n > 1:                                    # `number` independent instances in sequence (yolo.py:376)
+            mod = nn.Sequential(*([mod] + [make() for _ in range(n - 1)]))
+        mod.i, mod.f, mod.type = i, f, name
+        save.extend(x % i for x in ([f] if isinstance(f, int) else f) if x != -1)
+        layers.append(mod)
+        if i == 0:
+            chans, strides = [], []
+        chans.append(c2)
+        strides.append(s)
+    return nn.Sequential(*layers), sorted(set(save)), chans, strides
+
+
+class DetectionModel(nn.Module):
+    """models/yolo.py:165-262 over `build_layers` (no CPU stride probe; see module docstring)."""
+
+    def __init__(self, cfg: Dict = YOLOV5N_DCNV3, ch: int = 3, nc: Optional[int] = None, dcn: str = "dcnv3",
+                 dcn_group: Optional[int] = None, fused_softmax: bool = False):
+        super().__init__()
+        self.yaml = deepcopy(cfg)
+        if nc and nc != self.yaml["nc"]:
+            self.yaml["nc"] = nc
+        self.model, self.save, self.channels, self.layer_strides = build_layers(
+            self.yaml, [ch], dcn=dcn, dcn_group=dcn_group, fused_softmax=fused_softmax)
+        self.names = [str(i) for i in range(self.yaml["nc"])]
+        head = self.model[-1]
+        if isinstance(head, Detect):
+            self._order_anchors(head)
+            head.anchors /= head.stride.view(-1, 1, 1)      # anchors in grid units, as the loss expects
+            self.stride = head.stride.clone()
+            self._initialize_biases()
+        for m in self.modules():                            # utils/torch_utils.py:212-221
+            if type(m) is nn.BatchNorm2d:
+                m.eps, m.momentum = 1e-3, 0.03
+
+    @staticmethod
+    def _order_anchors(head: Detect):
+        """utils/autoanchor.py:19-26: anchor areas must grow with the strides."""
+        area = head.anchors.prod(-1).mean(-1).view(-1)
+        da, ds = area[-1] - area[0], head.stride[-1] - head.stride[0]
+        if da and da.sign() != ds.sign():
+            head.anchors[:] = head.anchors.flip(0)
+
+    def _initialize_biases(self):
+        """yolo.py:253-261: objectness prior of 8 objects per 640 px image, class prior 0.6 / nc."""
+        head = self.model[-1]
+        for conv, s in zip(head.m, head.stride):
+            b = conv.bias.detach().view(head.na, -1).clone()
+            b[:, 4] += math.log(8 / (640 / float(s)) ** 2)
+            b[:, 5:5 + head.nc] += math.log(0.6 / (head.nc - 0.99999))
+            conv.bias = nn.Parameter(b.view(-1), requires_grad=True)
+
+    def forward(self, x):
+        outs: List[Optional[torch.Tensor]] = []
+        for m in self.model:
+            if m.f != -1:
+                x = outs[m.f] if isinstance(m.f, int) else [x if j == -1 else outs[j] for j in m.f]
+            x = m(x)
+            outs.append(x if m.i in self.save else None)
+        return x
+
+    def dcn_sites(self):
+        from .ops_dcnv3.modules import DCNv3
+        return [(n, m) for n, m in self.named_modules() if isinstance(m, DCNv3)]
