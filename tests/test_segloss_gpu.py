@@ -64,12 +64,20 @@ def test_fused_loss_argument_errors():
                                                  torch.zeros(1, 4, 4, dtype=torch.long, device=DEV))
 
 
-def test_lowres_train_path_equals_full_resolution_path():
+@pytest.fixture
+def no_tf32():
+    """Whole-model fp32 comparison: keep convolutions and matmuls in fp32 for the test, then restore."""
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_lowres_train_path_equals_full_resolution_path(no_tf32):
     """SegModel(x, lowres=True) + fused loss with scale == full-size output + the reference's unfused loss:
     same loss, same parameter gradients (bf16 autocast: compare in fp32 without autocast)."""
     torch.manual_seed(0)
-    torch.backends.cudnn.allow_tf32 = False          # whole-model fp32 comparison: keep the convolutions in fp32
-    torch.backends.cuda.matmul.allow_tf32 = False
     m = SegModel(YOLOV5_SEG, dcn="dcnv3", img_size=(128, 128)).to(DEV).train()
     x = torch.randn(2, 3, 128, 128, device=DEV)
     lab = torch.randint(0, 12, (2, 128, 128), device=DEV)
