@@ -160,7 +160,7 @@ class Workload:
         self.lib = _lib.load()
         self._lib = _lib
         self.dev, self.dtype, self.sites = dev, dtype, sites
-        self.accum = {"opmath": _lib.ACC_OPMATH, "storage": _lib.ACC_STORAGE}[accum]
+        self.accum = {"opmath": _lib.ACC_OPMATH, "storage": _lib.ACC_STORAGE, "tile": _lib.ACC_TILE}[accum]
         self.logits = int(fused_softmax)
         self.sets = []
         for r in range(N_BUFFER_SETS):
@@ -173,7 +173,7 @@ class Workload:
         # zero_select_kernel + bwd_imat_kernel + bwd_vec_kernel (returns at once unless the selector picked
         # it) + cast_ws_kernel; with a family forced by DCNV3_B200_BWD: backward kernel + cast (+ a driver memset).
         forced = os.environ.get("DCNV3_B200_BWD") in ("vec", "imat", "tile")
-        bwd = (2 if forced else 4) if (lowp and accum == "opmath") else 1
+        bwd = (2 if forced else 4) if (lowp and accum == "opmath") else 1  # 'tile': bwd_win_kernel (+ a driver memset)
         self.launches_per_step = len(sites) * (1 + bwd)
 
     def fwd(self, b, st):
@@ -254,7 +254,7 @@ def time_e2e(wl, steps, warmup, dist):
     copies out run on three streams (PCIe is full duplex), three steps in flight."""
     from yolo_dual_b200.host import HostPipeline, HostSite, pack_sites
     from yolo_dual_b200.ops_dcnv3.functions import set_grad_accum
-    set_grad_accum("opmath" if wl.accum == 0 else "storage")
+    set_grad_accum({0: "opmath", 1: "storage", 2: "tile"}[wl.accum])
     sites = []
     for b in wl.sets[0]:
         N, H, W, G, gc = SITES[b.name]
@@ -480,7 +480,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--sites", default="P3,P4,P5")
-    ap.add_argument("--grad-accum", default="opmath", choices=["opmath", "storage"])
+    ap.add_argument("--grad-accum", default="tile", choices=["tile", "opmath", "storage"])
     ap.add_argument("--fused-softmax", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

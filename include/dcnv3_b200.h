@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define DCNV3_B200_VERSION 100 /* 0.1.0 */
+#define DCNV3_B200_VERSION 200 /* 0.2.0 */
 
 /* storage dtypes (op-math is float for F32/F16/BF16, double for F64 — as
  * at::opmath_type in dcnv3_im2col_cuda.cuh:30) */
@@ -68,10 +68,20 @@ enum {
  *   ACC_OPMATH  accumulate in an fp32 workspace, round once at the end
  *               (what the reference does, dcnv3_cuda.cu:126-133,168-170);
  *   ACC_STORAGE packed 16-bit vector reductions straight into grad_input
- *               (no workspace, less traffic, one rounding per contribution). */
+ *               (no workspace, less traffic, one rounding per contribution);
+ *   ACC_TILE    one kernel, no workspace: the contributions of an 8x8 tile of
+ *               output pixels are summed in fp32 on the SM and the tile's window
+ *               leaves as packed 16-bit vector reductions, so a cell of grad_input
+ *               sees at most four roundings (one per tile window that reaches it)
+ *               instead of one (ACC_OPMATH) or ~36 (ACC_STORAGE).  Sampling points
+ *               further than 3 px from their kernel-grid position leave the window
+ *               and are reduced one by one like ACC_STORAGE.  Shapes the tile kernel
+ *               does not take (group_channels != 16, kernel != 3x3 s1 d1, group % 4)
+ *               run as ACC_OPMATH and need its workspace. */
 enum {
     DCNV3_B200_ACC_OPMATH = 0,
-    DCNV3_B200_ACC_STORAGE = 1
+    DCNV3_B200_ACC_STORAGE = 1,
+    DCNV3_B200_ACC_TILE = 2
 };
 
 /* error codes */
@@ -99,6 +109,10 @@ typedef struct dcnv3_b200_geometry {
 } dcnv3_b200_geometry;
 
 int dcnv3_b200_version(void);
+
+/* The library reads its DCNV3_B200_* tuning knobs from the environment once per process; this
+ * re-reads them (for tests that switch kernel families in-process).  Not for production use. */
+void dcnv3_b200_reload_knobs(void);
 const char *dcnv3_b200_last_error(void);
 
 /* Ho/Wo of dcnv3_cuda.cu:40-45.  Returns EINVAL if the geometry is not valid. */

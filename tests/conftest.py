@@ -36,3 +36,39 @@ def pytest_collection_modifyitems(config, items):
 def pixel_oracle():
     from oracle.dcnv3_oracle import PixelOracle
     return PixelOracle()
+
+
+def _reload_knobs():
+    """The library caches its DCNV3_B200_* environment knobs on first use (no getenv on the hot path);
+    tests that switch kernel families in-process make it read them again."""
+    try:
+        from yolo_dual_b200 import _lib
+        _lib.reload_knobs()
+    except Exception:
+        pass
+
+
+@pytest.fixture(autouse=True)
+def _fresh_knobs():
+    # runs before every test, after the previous test's monkeypatch was undone: back to the real environment
+    _reload_knobs()
+    yield
+
+
+@pytest.fixture
+def monkeypatch(monkeypatch):
+    """pytest's monkeypatch, with setenv / delenv of a DCNV3_B200_* name followed by a knob reload."""
+    set_, del_ = monkeypatch.setenv, monkeypatch.delenv
+
+    def setenv(name, value, *a, **k):
+        set_(name, value, *a, **k)
+        if name.startswith("DCNV3_B200_"):
+            _reload_knobs()
+
+    def delenv(name, *a, **k):
+        del_(name, *a, **k)
+        if name.startswith("DCNV3_B200_"):
+            _reload_knobs()
+
+    monkeypatch.setenv, monkeypatch.delenv = setenv, delenv
+    return monkeypatch

@@ -19,6 +19,7 @@ for label, dist, sc in (("s0", "unit", 0.0), ("s1", "unit", 1.0), ("s1.1", "unit
     res = []
     for fam in ("vec", "win"):
         os.environ["DCNV3_B200_FWD"] = fam
+        _lib.reload_knobs()
         def step(i):
             x, off, m = sets[i % 4]
             assert lib.dcnv3_b200_forward(x.data_ptr(), off.data_ptr(), m.data_ptr(), out.data_ptr(), _lib.BF16, ctypes.byref(geo), 0, st) == 0

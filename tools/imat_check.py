@@ -14,6 +14,7 @@ import torch  # noqa: E402
 
 from oracle.dcnv3_oracle import PixelOracle, make_inputs  # noqa: E402
 from yolo_dual_b200.ops_dcnv3.functions import DCNv3Function, DCNv3SoftmaxFunction  # noqa: E402
+from yolo_dual_b200 import _lib as _lib_mod  # noqa: E402
 
 DEV = "cuda:0"
 DIST = os.environ.get("IMAT_DIST", "unit")
@@ -24,6 +25,7 @@ def run(fn, x, off, m, go, args, dtype, env):
     for k in ("DCNV3_B200_FWD", "DCNV3_B200_BWD"):
         os.environ.pop(k, None)
     os.environ.update(env)
+    _lib_mod.reload_knobs()  # the library caches its knobs
     xs, os_, ms = (t.to(DEV, dtype).contiguous().requires_grad_(True) for t in (x, off, m))
     out = fn.apply(xs, os_, ms, *args, 256)
     res = [out.detach().float().cpu()]
@@ -119,6 +121,7 @@ def timing(do_bwd):
             else:
                 os.environ["DCNV3_B200_FWD"] = fam
                 os.environ["DCNV3_B200_BWD"] = fam
+            _lib_mod.reload_knobs()
             res = {}
             for what in (("fwd", "bwd") if do_bwd else ("fwd",)):
                 def step(i):

@@ -18,6 +18,8 @@ from yolo_dual_b200.ops_dcnv3.functions import DCNv3Function, DCNv3SoftmaxFuncti
 
 
 def run(shape, dtype, fn=DCNv3Function):
+    from yolo_dual_b200 import _lib
+    _lib.reload_knobs()  # the library caches its DCNV3_B200_* knobs; main() switches them between runs
     N, H, W, G, gc, k, s, pad = shape
     args = (k, k, s, s, pad, pad, 1, 1, G, gc, 1.0)
     x, off, m, go = make_inputs(N, H, W, G, gc, k, k, s, s, pad, pad, 1, 1, dist="unit", seed=1)

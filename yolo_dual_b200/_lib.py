@@ -11,10 +11,11 @@ import os
 from .build import LIB
 
 F32, F16, BF16, F64 = 0, 1, 2, 3
-ACC_OPMATH, ACC_STORAGE = 0, 1
+ACC_OPMATH, ACC_STORAGE, ACC_TILE = 0, 1, 2
 
 SYMBOLS = (
     "dcnv3_b200_version",
+    "dcnv3_b200_reload_knobs",
     "dcnv3_b200_last_error",
     "dcnv3_b200_output_size",
     "dcnv3_b200_forward",
@@ -49,6 +50,8 @@ def load() -> ctypes.CDLL:
     vp, ip, gp = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(Geometry)
     lib.dcnv3_b200_version.restype = ip
     lib.dcnv3_b200_last_error.restype = ctypes.c_char_p
+    lib.dcnv3_b200_reload_knobs.restype = None
+    lib.dcnv3_b200_reload_knobs.argtypes = []
     lib.dcnv3_b200_output_size.argtypes = [gp, ctypes.POINTER(ip), ctypes.POINTER(ip)]
     lib.dcnv3_b200_forward.argtypes = [vp, vp, vp, vp, ip, gp, ip, vp]
     lib.dcnv3_b200_backward_workspace_bytes.argtypes = [ip, gp, ip]
@@ -57,6 +60,11 @@ def load() -> ctypes.CDLL:
     lib.dcnv3_b200_debug_indices.argtypes = [vp, vp, vp, ip, gp, vp]
     _lib = lib
     return lib
+
+
+def reload_knobs() -> None:
+    """Re-read the DCNV3_B200_* environment knobs (the library caches them on first use).  Tests only."""
+    load().dcnv3_b200_reload_knobs()
 
 
 def last_error() -> str:

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libdcnv3_b200.so")
 SOURCES = ["dcnv3_b200.cu"]
-HEADERS = ["dcnv3_common.cuh", "dcnv3_kernels.cuh", "dcnv3_bwd_tile.cuh", "dcnv3_imat.cuh", os.path.join(ROOT, "include", "dcnv3_b200.h")]
+HEADERS = ["dcnv3_common.cuh", "dcnv3_kernels.cuh", "dcnv3_bwd_tile.cuh", "dcnv3_imat.cuh", "dcnv3_win.cuh", os.path.join(ROOT, "include", "dcnv3_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

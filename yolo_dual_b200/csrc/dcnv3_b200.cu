@@ -11,11 +11,14 @@
 #include <cstdlib>
 #include <cmath>
 #include <cstring>
+#include <atomic>
+#include <mutex>
 #include <initializer_list>
 
 #include "dcnv3_kernels.cuh"
 #include "dcnv3_bwd_tile.cuh"
 #include "dcnv3_imat.cuh"
+#include "dcnv3_win.cuh"
 
 using namespace dcnv3;
 
@@ -117,12 +120,54 @@ struct Plan {
 
 bool aligned_to(const void *p, int a) { return (reinterpret_cast<uintptr_t>(p) & (uintptr_t)(a - 1)) == 0; }
 
-// Tuning knob: DCNV3_B200_BPL=16|32 forces the bytes-per-lane of the vector path.
-int forced_bpl() {
-    const char *e = getenv("DCNV3_B200_BPL");
-    const int v = e ? atoi(e) : 0;
-    return (v == 8 || v == 16 || v == 32) ? v : 0;
+// Tuning knobs (environment, all optional).  Read ONCE per process — the hot path must not call getenv — and
+// cached; dcnv3_b200_reload_knobs() (test-only entry point) reads them again.
+//   DCNV3_B200_BPL=8|16|32          bytes of channels per lane of the vector kernels
+//   DCNV3_B200_PDL=0                no programmatic dependent launch
+//   DCNV3_B200_FWD=vec|imat|pts|win forward kernel family
+//   DCNV3_B200_BWD=vec|tile|imat|win backward kernel family (ACC_OPMATH: vec|tile|imat; ACC_TILE: win, or vec = ACC_STORAGE path)
+//   DCNV3_B200_TILE="R,warps"       halo / warps of the experimental privatised backward
+//   DCNV3_B200_GUARD_PER_CTA=n      logical blocks per CTA of the selector-guarded vector backward
+struct Knobs {
+    int bpl = 0;
+    bool pdl = true;
+    int fwd = 0, bwd = 0;  // 0 default, 1 vec, 2 tile, 3 imat, 4 pts, 5 win
+    int tile_R = 2, tile_warps = 4;
+    unsigned guard_per_cta = 4;
+};
+Knobs g_knobs;
+std::atomic<bool> g_knobs_ready{false};
+std::mutex g_knobs_mu;
+
+int family_of(const char *e) {
+    if (!e) return 0;
+    if (!strcmp(e, "vec")) return 1;
+    if (!strcmp(e, "tile")) return 2;
+    if (!strcmp(e, "imat")) return 3;
+    if (!strcmp(e, "pts")) return 4;
+    if (!strcmp(e, "win")) return 5;
+    return 0;
 }
+void read_knobs() {
+    Knobs k;
+    if (const char *e = getenv("DCNV3_B200_BPL")) { const int v = atoi(e); k.bpl = (v == 8 || v == 16 || v == 32) ? v : 0; }
+    if (const char *e = getenv("DCNV3_B200_PDL")) k.pdl = e[0] != '0';
+    k.fwd = family_of(getenv("DCNV3_B200_FWD"));
+    k.bwd = family_of(getenv("DCNV3_B200_BWD"));
+    if (const char *e = getenv("DCNV3_B200_TILE")) {
+        int c, d;
+        if (sscanf(e, "%d,%d", &c, &d) == 2 && c >= 0 && c <= 8 && d >= 1 && d <= 4) { k.tile_R = c; k.tile_warps = d; }
+    }
+    if (const char *e = getenv("DCNV3_B200_GUARD_PER_CTA")) { const int v = atoi(e); k.guard_per_cta = v >= 1 && v <= 64 ? (unsigned)v : 4u; }
+    std::lock_guard<std::mutex> lk(g_knobs_mu);
+    g_knobs = k;
+    g_knobs_ready.store(true, std::memory_order_release);
+}
+inline const Knobs &knobs() {
+    if (!g_knobs_ready.load(std::memory_order_acquire)) read_knobs();
+    return g_knobs;
+}
+int forced_bpl() { return knobs().bpl; }
 
 // Can this call take the vector kernels, and with how many bytes per lane?
 // `ptrs` are the channel-vector tensors (input, output / grad_output): they must be aligned to
@@ -172,10 +217,7 @@ unsigned blocks_for(size_t threads) { return (unsigned)((threads + kThreads - 1)
 // Launch with programmatic stream serialization (the kernel may be scheduled while its predecessor on
 // the stream drains; it calls pdl_enter() before touching memory, dcnv3_common.cuh).  DCNV3_B200_PDL=0
 // turns the attribute off (plain stream order).  Errors surface through cudaGetLastError in finish().
-bool pdl_on() {
-    const char *e = getenv("DCNV3_B200_PDL");
-    return !(e && e[0] == '0');
-}
+bool pdl_on() { return knobs().pdl; }
 template <typename... P, typename... A>
 void launch(void (*kernel)(P...), dim3 grid, unsigned block, size_t smem, cudaStream_t st, A... args) {
     cudaLaunchConfig_t cfg{};
@@ -195,17 +237,6 @@ void launch(void (*kernel)(P...), dim3 grid, unsigned block, size_t smem, cudaSt
 // Knobs: DCNV3_B200_FWD / DCNV3_B200_BWD = vec | imat force a family.  Defaults: the backward takes the
 // interpolation-matrix kernel when eligible (16-bit, gc = 16, 3x3 s1 d1, fp32 accumulation), the forward the
 // vector kernel (its imat variant is correct but slower: profiles/r01_imat.md).
-int family_knob(const char *name) {  // 0 default, 1 vec, 2 tile, 3 imat, 4 pts, 5 win
-    const char *e = getenv(name);
-    if (!e) return 0;
-    if (!strcmp(e, "vec")) return 1;
-    if (!strcmp(e, "tile")) return 2;
-    if (!strcmp(e, "imat")) return 3;
-    if (!strcmp(e, "pts")) return 4;
-    if (!strcmp(e, "win")) return 5;
-    return 0;
-}
-
 template <typename T>
 bool imat_eligible(const Geo &q, std::initializer_list<const void *> vec_ptrs, const void *off) {
     if (sizeof(T) != 2) return false;
@@ -217,9 +248,28 @@ bool imat_eligible(const Geo &q, std::initializer_list<const void *> vec_ptrs, c
     return blocks > 0 && blocks < (1ull << 31);
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device), not once per launch
 template <typename K> int set_smem(K kernel, int bytes, const char *what) {
+    static std::mutex mu;
+    static struct { const void *fn; unsigned long long devs; } seen[64];
+    static int n_seen = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const void *fn = reinterpret_cast<const void *>(kernel);
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (int i = 0; i < n_seen; ++i)
+            if (seen[i].fn == fn && dev < 64 && ((seen[i].devs >> dev) & 1ull)) return 0;
+    }
     const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return cuda_fail(e, what);
+    if (dev < 64) {
+        std::lock_guard<std::mutex> lk(mu);
+        int i = 0;
+        for (; i < n_seen; ++i) if (seen[i].fn == fn) break;
+        if (i == n_seen && n_seen < 64) { seen[n_seen].fn = fn; seen[n_seen].devs = 0; ++n_seen; }
+        if (i < 64) seen[i].devs |= 1ull << dev;
+    }
     return 0;
 }
 
@@ -254,6 +304,39 @@ int launch_bwd_imat(const T *in, const T *off, const T *mask, const T *gout, flo
     return 0;
 }
 
+// ------------------------------------------------ single-kernel window backward (ACC_TILE)
+bool win_geometry(const Geo &q) {
+    return q.gc == 16 && q.G % win::kGrp == 0 && q.kh == 3 && q.kw == 3 && q.sh == 1 && q.sw == 1 && q.dh == 1 && q.dw == 1;
+}
+template <typename T>
+bool win_eligible(const Geo &q, const void *in, const void *off, const void *mask, const void *gout, const void *gin,
+                  const void *goff, const void *gmask) {
+    if (sizeof(T) != 2 || !win_geometry(q)) return false;
+    if (!aligned16(in) || !aligned16(gout) || !aligned16(gin)) return false;
+    if ((reinterpret_cast<uintptr_t>(off) & 3u) || (reinterpret_cast<uintptr_t>(goff) & 3u) ||
+        (reinterpret_cast<uintptr_t>(mask) & 1u) || (reinterpret_cast<uintptr_t>(gmask) & 1u)) return false;
+    const unsigned long long blocks = (unsigned long long)q.N * ((q.Ho + 7) / 8) * ((q.Wo + 7) / 8) * (q.G / win::kGrp);
+    if (blocks == 0 || blocks >= (1ull << 31)) return false;
+    // the far-tile fallback indexes (pixel, 8-channel vector) lanes with 32 bits
+    return (unsigned long long)q.N * q.Ho * q.Wo * (q.C / 8) < (1ull << 31);
+}
+
+template <typename T>
+int launch_bwd_win(const T *in, const T *off, const T *mask, const T *gout, T *gin, T *goff, T *gmask,
+                   const Geo &q, bool logits, cudaStream_t st) {
+    const int tiles_y = (q.Ho + 7) / 8, tiles_x = (q.Wo + 7) / 8, GQ = q.G / win::kGrp;
+    const unsigned grid = (unsigned)((size_t)q.N * tiles_y * tiles_x * GQ);
+    int rc;
+    if (logits) {
+        if ((rc = set_smem(win::bwd_win_kernel<T, true>, win::kSmemB, "cudaFuncSetAttribute(bwd_win_kernel)"))) return rc;
+        launch(win::bwd_win_kernel<T, true>, grid, win::kThreadsW, win::kSmemB, st, in, off, mask, gout, gin, goff, gmask, q, GQ);
+    } else {
+        if ((rc = set_smem(win::bwd_win_kernel<T, false>, win::kSmemB, "cudaFuncSetAttribute(bwd_win_kernel)"))) return rc;
+        launch(win::bwd_win_kernel<T, false>, grid, win::kThreadsW, win::kSmemB, st, in, off, mask, gout, gin, goff, gmask, q, GQ);
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------ forward
 template <typename T>
 int forward_t(const void *in_, const void *off_, const void *mask_, void *out_, const Geo &q,
@@ -263,7 +346,7 @@ int forward_t(const void *in_, const void *off_, const void *mask_, void *out_, 
     const size_t n_pix = (size_t)q.N * q.Ho * q.Wo;
     if (n_pix == 0) return 0;
     if constexpr (sizeof(T) == 2) {
-        const int fam = family_knob("DCNV3_B200_FWD");
+        const int fam = knobs().fwd;
         if (fam == 3 && imat_eligible<T>(q, {in_, out_}, off_))
             return launch_fwd_imat<T>(in, off, mask, out, q, logits, st);
         // Default for the C3-DCN shapes (16-bit, group_channels = 16, 3x3 s1 d1, G % 4 = 0): the forward from a
@@ -326,14 +409,9 @@ int forward_t(const void *in_, const void *off_, const void *mask_, void *out_, 
 // ------------------------------------------------ privatised backward (tile)
 // Knobs: DCNV3_B200_BWD=tile selects this family, DCNV3_B200_TILE="R,warps" its halo / warps per CTA.
 struct TileKnobs { int force; int R, warps; };
-TileKnobs tile_knobs() {  // read per call (getenv is ~100 ns) so tests can switch paths in-process
-    TileKnobs t{0, 2, 4};
-    if (const char *e = getenv("DCNV3_B200_BWD")) t.force = !strcmp(e, "vec") ? 1 : (!strcmp(e, "tile") ? 2 : 0);
-    if (const char *e = getenv("DCNV3_B200_TILE")) {
-        int c, d;
-        if (sscanf(e, "%d,%d", &c, &d) == 2 && c >= 0 && c <= 8 && d >= 1 && d <= 4) { t.R = c; t.warps = d; }
-    }
-    return t;
+TileKnobs tile_knobs() {
+    const Knobs &k = knobs();
+    return TileKnobs{k.bwd == 1 ? 1 : (k.bwd == 2 ? 2 : 0), k.tile_R, k.tile_warps};
 }
 
 template <typename T>
@@ -405,11 +483,7 @@ int backward_launch(const T *in, const T *off, const T *mask, const T *gout, A *
             //   per_cta 1: 575.0 / 432   2: 563.4 / 440   4: 557.6 / 456   8: 556 / 464   32: 553.1 / 514
             // (fewer, longer CTAs quantise the last wave).  4 is the default; DCNV3_B200_GUARD_PER_CTA overrides.
             unsigned per_cta = 1u;
-            if (sel) {
-                const char *e = getenv("DCNV3_B200_GUARD_PER_CTA");
-                const int v = e ? atoi(e) : 4;
-                per_cta = v >= 1 && v <= 64 ? (unsigned)v : 4u;
-            }
+            if (sel) per_cta = knobs().guard_per_cta;
             const unsigned grid = (n_blocks + per_cta - 1) / per_cta;
             const bool k9 = (q.kh == 3 && q.kw == 3);
 #define LAUNCH_BWD(BPL, KP, LG)                                                                  \
@@ -459,6 +533,22 @@ int backward_t(const void *in_, const void *off_, const void *mask_, const void 
     if (n_in == 0) return 0;
     cudaError_t e;
     constexpr bool lowp = sizeof(T) == 2;
+    if constexpr (lowp) {
+        // ACC_TILE (default of the Python front): one kernel, fp32 sums per tile window, 16-bit reductions across
+        // tiles, no workspace.  Shapes it does not take fall through to ACC_OPMATH (which needs the workspace).
+        if (grad_accum == DCNV3_B200_ACC_TILE) {
+            const int fam = knobs().bwd;
+            if ((fam == 0 || fam == 5) && win_eligible<T>(q, in_, off_, mask_, gout_, gin_, goff_, gmask_)) {
+                if ((e = cudaMemsetAsync(gin, 0, n_in * sizeof(T), st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_input)");
+                if (n_pix == 0) return 0;
+                return launch_bwd_win<T>(in, off, mask, gout, gin, goff, gmask, q, logits, st);
+            }
+            if (win_geometry(q) && (!ws || ws_bytes == 0))
+                return fail(DCNV3_B200_EALIGN, "ACC_TILE needs 16-byte aligned input / grad_output / grad_input (4-byte offset / "
+                                               "grad_offset); pass an ACC_OPMATH workspace to fall back");
+            grad_accum = DCNV3_B200_ACC_OPMATH;
+        }
+    }
     if (lowp && grad_accum == DCNV3_B200_ACC_OPMATH) {
         // reference semantics (dcnv3_cuda.cu:126-133,168-170): fp32 accumulation, one rounding
         const size_t acc_bytes = (n_in * sizeof(float) + 255) & ~(size_t)255;
@@ -484,7 +574,7 @@ int backward_t(const void *in_, const void *off_, const void *mask_, const void 
                 // Default for eligible shapes: a 2 K-sample look at the offsets picks the family on
                 // the device (imat::select_kernel); both kernels are launched, one returns at once.
                 // DCNV3_B200_BWD=vec|imat forces one (no selector).
-                const int fam = family_knob("DCNV3_B200_BWD");
+                const int fam = knobs().bwd;
                 if (!tiled && (fam == 0 || fam == 3) && imat_eligible<T>(q, {in_, gout_, ws}, off_) &&
                     !(reinterpret_cast<uintptr_t>(goff_) & 3u)) {
                     const Plan pl = plan_vec<T>(q, n_pix, logits, {in_, gout_}, off_, sizeof(float), true);
@@ -544,6 +634,8 @@ extern "C" {
 
 int dcnv3_b200_version(void) { return DCNV3_B200_VERSION; }
 
+void dcnv3_b200_reload_knobs(void) { read_knobs(); }
+
 const char *dcnv3_b200_last_error(void) { return g_err; }
 
 int dcnv3_b200_output_size(const dcnv3_b200_geometry *geo, int *Ho, int *Wo) {
@@ -582,7 +674,10 @@ int dcnv3_b200_forward(const void *input, const void *offset, const void *mask, 
 size_t dcnv3_b200_backward_workspace_bytes(int dtype, const dcnv3_b200_geometry *geo, int grad_accum) {
     Geo q;
     if (make_geo(geo, q)) return 0;
-    if (dtype_size(dtype) == 2 && grad_accum == DCNV3_B200_ACC_OPMATH)
+    const bool tile_takes_it = grad_accum == DCNV3_B200_ACC_TILE && win_geometry(q) && knobs().bwd != 1 &&
+                               knobs().bwd != 2 && knobs().bwd != 3;
+    if (dtype_size(dtype) == 2 && !tile_takes_it &&
+        (grad_accum == DCNV3_B200_ACC_OPMATH || grad_accum == DCNV3_B200_ACC_TILE))
         return (((size_t)q.N * q.H * q.W * q.C * sizeof(float) + 255) & ~(size_t)255) + 256;
     return 0;
 }
@@ -598,7 +693,7 @@ int dcnv3_b200_backward(const void *input, const void *offset, const void *mask,
     if (rc) return rc;
     if (!dtype_size(dtype)) return fail(DCNV3_B200_EINVAL, "unknown dtype %d", dtype);
     if (mask_is_logits != 0 && mask_is_logits != 1) return fail(DCNV3_B200_EINVAL, "mask_is_logits must be 0 or 1");
-    if (grad_accum != DCNV3_B200_ACC_OPMATH && grad_accum != DCNV3_B200_ACC_STORAGE)
+    if (grad_accum != DCNV3_B200_ACC_OPMATH && grad_accum != DCNV3_B200_ACC_STORAGE && grad_accum != DCNV3_B200_ACC_TILE)
         return fail(DCNV3_B200_EINVAL, "unknown grad_accum %d", grad_accum);
     if (q.N == 0) return 0;
     if (!input || !offset || !mask || !grad_output || !grad_input || !grad_offset || !grad_mask)

@@ -158,6 +158,40 @@ template <> __device__ __forceinline__ uint32_t add2<__half>(uint32_t a, uint32_
     return *reinterpret_cast<const uint32_t *>(&r);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// mixed-precision FMA (PTX ISA 8.6, sm_100+): d = a * b + c with 16-bit a, b and fp32 c, d.  The product of two
+// 16-bit values is exact in fp32, so a dot of storage values is an fp32-accumulated exact dot.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T> struct Mix;
+template <> struct Mix<__nv_bfloat16> {
+    // s0 += x.lo * g.lo ; s1 += x.hi * g.hi
+    static __device__ __forceinline__ void dot2(float &s0, float &s1, uint32_t x, uint32_t g) {
+        asm("{\n\t.reg .b16 xl, xh, gl, gh;\n\tmov.b32 {xl, xh}, %2;\n\tmov.b32 {gl, gh}, %3;\n\t"
+            "fma.rn.f32.bf16 %0, xl, gl, %0;\n\tfma.rn.f32.bf16 %1, xh, gh, %1;\n\t}"
+            : "+f"(s0), "+f"(s1) : "r"(x), "r"(g));
+    }
+    // a0 += x.lo * w ; a1 += x.hi * w   (w: 16-bit weight in the low half of a register)
+    static __device__ __forceinline__ void axpy2(float &a0, float &a1, uint32_t x, uint32_t w) {
+        asm("{\n\t.reg .b16 xl, xh, wl, wh;\n\tmov.b32 {xl, xh}, %2;\n\tmov.b32 {wl, wh}, %3;\n\t"
+            "fma.rn.f32.bf16 %0, xl, wl, %0;\n\tfma.rn.f32.bf16 %1, xh, wl, %1;\n\t}"
+            : "+f"(a0), "+f"(a1) : "r"(x), "r"(w));
+    }
+    static __device__ __forceinline__ uint32_t weight(float w) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(w)); }
+};
+template <> struct Mix<__half> {
+    static __device__ __forceinline__ void dot2(float &s0, float &s1, uint32_t x, uint32_t g) {
+        asm("{\n\t.reg .b16 xl, xh, gl, gh;\n\tmov.b32 {xl, xh}, %2;\n\tmov.b32 {gl, gh}, %3;\n\t"
+            "fma.rn.f32.f16 %0, xl, gl, %0;\n\tfma.rn.f32.f16 %1, xh, gh, %1;\n\t}"
+            : "+f"(s0), "+f"(s1) : "r"(x), "r"(g));
+    }
+    static __device__ __forceinline__ void axpy2(float &a0, float &a1, uint32_t x, uint32_t w) {
+        asm("{\n\t.reg .b16 xl, xh, wl, wh;\n\tmov.b32 {xl, xh}, %2;\n\tmov.b32 {wl, wh}, %3;\n\t"
+            "fma.rn.f32.f16 %0, xl, wl, %0;\n\tfma.rn.f32.f16 %1, xh, wl, %1;\n\t}"
+            : "+f"(a0), "+f"(a1) : "r"(x), "r"(w));
+    }
+    static __device__ __forceinline__ uint32_t weight(float w) { return (uint32_t)__half_as_ushort(__float2half_rn(w)); }
+};
+
 // 16-byte chunk swizzle of the window: chunk' = chunk ^ key(cell); 8 consecutive cells of a
 // sub-window row (also across its 12-cell wrap into the next row) get 8 distinct keys.
 __device__ __forceinline__ int win_key(int cell) { return ((cell & 15) + 4 * (cell >> 4)) & 7; }
@@ -1158,8 +1192,16 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return v;
 }
 
+// acc += w * (8 storage values): mixed-precision FMAs (FHFMA) straight on the halves of the loaded registers, fp32
+// accumulation; `w` is the corner weight rounded to the storage dtype (Mix<T>::weight)
 template <typename T>
-__device__ __forceinline__ void fma8(float2 (&acc)[4], const uint4 &c, float w) {
+__device__ __forceinline__ void fma8(float2 (&acc)[4], const uint4 &c, uint32_t w) {
+    Mix<T>::axpy2(acc[0].x, acc[0].y, c.x, w); Mix<T>::axpy2(acc[1].x, acc[1].y, c.y, w);
+    Mix<T>::axpy2(acc[2].x, acc[2].y, c.z, w); Mix<T>::axpy2(acc[3].x, acc[3].y, c.w, w);
+}
+// fp32-weight variant (unpack + FFMA2) for the rare gathers from global memory
+template <typename T>
+__device__ __forceinline__ void fma8f(float2 (&acc)[4], const uint4 &c, float w) {
     const uint32_t wd[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) acc[k] = __ffma2_rn(unpack2f<T>(wd[k]), make_float2(w, w), acc[k]);
@@ -1167,13 +1209,12 @@ __device__ __forceinline__ void fma8(float2 (&acc)[4], const uint4 &c, float w) 
 
 // one corner of a window-resident point: both 16-byte chunks of the group's slab (own chunk first)
 template <typename T>
-__device__ __forceinline__ void corner16(float2 (&acc)[8], uint32_t a0, uint32_t a1, float w) {
+__device__ __forceinline__ void corner16(float2 (&acc)[8], uint32_t a0, uint32_t a1, uint32_t w) {
     const uint4 x0 = lds128(a0), x1 = lds128(a1);
-    const uint32_t w0[4] = {x0.x, x0.y, x0.z, x0.w}, w1[4] = {x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) acc[k] = __ffma2_rn(unpack2f<T>(w0[k]), make_float2(w, w), acc[k]);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) acc[4 + k] = __ffma2_rn(unpack2f<T>(w1[k]), make_float2(w, w), acc[4 + k]);
+    Mix<T>::axpy2(acc[0].x, acc[0].y, x0.x, w); Mix<T>::axpy2(acc[1].x, acc[1].y, x0.y, w);
+    Mix<T>::axpy2(acc[2].x, acc[2].y, x0.z, w); Mix<T>::axpy2(acc[3].x, acc[3].y, x0.w, w);
+    Mix<T>::axpy2(acc[4].x, acc[4].y, x1.x, w); Mix<T>::axpy2(acc[5].x, acc[5].y, x1.y, w);
+    Mix<T>::axpy2(acc[6].x, acc[6].y, x1.z, w); Mix<T>::axpy2(acc[7].x, acc[7].y, x1.w, w);
 }
 
 // The two lanes (h = 0, 1) of a (pixel, group) split the nine POINTS: lane h takes points 4h..4h+3 with all 16
@@ -1304,7 +1345,8 @@ fwd_tile_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
             const uint32_t a = win_s + (fast ? v * kFwin + u : (unsigned)kFwinCells) * 128u;  // closed point: the zero cells (0 * Inf would be NaN)
             const float hh = sub_rn(1.f, t.lh), hw = sub_rn(1.f, t.lw);
             const float hm = hh * m, lm = t.lh * m;
-            const float w1 = hm * hw, w2 = hm * t.lw, w3 = lm * hw, w4 = lm * t.lw;
+            // corner weights rounded to the storage dtype (2^-9 / 2^-11 relative): operands of the mixed-precision FMAs
+            const uint32_t w1 = Mix<T>::weight(hm * hw), w2 = Mix<T>::weight(hm * t.lw), w3 = Mix<T>::weight(lm * hw), w4 = Mix<T>::weight(lm * t.lw);
             if (k < 4) {
                 corner16<T>(acc, a + own16, a + other16, w1);
                 corner16<T>(acc, a + own16 + 128, a + other16 + 128, w2);
@@ -1331,10 +1373,10 @@ fwd_tile_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
                     if (!ok[c]) continue;
                     const T *src = img_g + ((size_t)(tt.h_low + (c >> 1)) * q.W + (tt.w_low + (c & 1))) * q.C;
                     float2 (&lo)[4] = reinterpret_cast<float2 (&)[4]>(acc);
-                    fma8<T>(lo, __ldg(reinterpret_cast<const uint4 *>(src + 8 * h)), w[c]);
+                    fma8f<T>(lo, __ldg(reinterpret_cast<const uint4 *>(src + 8 * h)), w[c]);
                     if (k < 4) {
                         float2 (&hi)[4] = reinterpret_cast<float2 (&)[4]>(acc[4]);
-                        fma8<T>(hi, __ldg(reinterpret_cast<const uint4 *>(src + 8 * (h ^ 1))), w[c]);
+                        fma8f<T>(hi, __ldg(reinterpret_cast<const uint4 *>(src + 8 * (h ^ 1))), w[c]);
                     }
                 }
             }

@@ -416,22 +416,18 @@ __device__ __forceinline__ void load_go_chunk(const T *p, float (&g)[CPQ]) {
     }
 }
 
+// One lane's work: BPL bytes of channels (vector c.v of pixel c.pix, group c.g), all points.  `active` false:
+// the lane only takes part in the shuffles (its coordinates must still be valid ones).
 template <typename T, typename A, int BPL, int KP, bool LOGITS>
 __device__ __forceinline__ void
-bwd_vec_body(const unsigned block, const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
-             const T *__restrict__ gout, A *__restrict__ gin, T *__restrict__ goff,
-             T *__restrict__ gmask, const Geo &q, const int vec_per_pix,
-             const int lanes_per_group, const unsigned total) {
+bwd_vec_lane(const VecCoord &c, const int lane_in_group, const bool active, const T *__restrict__ in,
+             const T *__restrict__ off, const T *__restrict__ mask, const T *__restrict__ gout, A *__restrict__ gin,
+             T *__restrict__ goff, T *__restrict__ gmask, const Geo &q, const int lanes_per_group) {
     static_assert(!LOGITS || KP > 0, "fused softmax in the vector path needs a compile-time P");
     constexpr int CH = Lane<T, BPL>::CH, NP = Lane<T, BPL>::NP;
     constexpr int CPQ = RedChunk<A>::CPQ;                 // channels per 16-byte reduction
     constexpr int R = CH * (int)sizeof(A) / 16;           // reductions per corner per lane
     static_assert(R >= 1, "a lane must own at least one 16-byte reduction chunk");
-    unsigned idx = block * (unsigned)kThreads + threadIdx.x;
-    const bool active = idx < total;  // tail lanes stay for the shuffles
-    if (!active) idx = total - 1;
-    const VecCoord c = decode_vec(idx, q, vec_per_pix, lanes_per_group);
-    const int lane_in_group = c.v - c.g * lanes_per_group;
 
     float p0h_, p0w_;
     window_origin<float>(q, c.ho, c.wo, p0h_, p0w_);
@@ -543,6 +539,20 @@ bwd_vec_body(const unsigned block, const T *__restrict__ in, const T *__restrict
 #pragma unroll
         for (int k = 0; k < (KP ? KP : 1); ++k) d_m[k] = from_math<T>(prob[k] * (gm[k] - dot));
     }
+}
+
+template <typename T, typename A, int BPL, int KP, bool LOGITS>
+__device__ __forceinline__ void
+bwd_vec_body(const unsigned block, const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
+             const T *__restrict__ gout, A *__restrict__ gin, T *__restrict__ goff,
+             T *__restrict__ gmask, const Geo &q, const int vec_per_pix,
+             const int lanes_per_group, const unsigned total) {
+    unsigned idx = block * (unsigned)kThreads + threadIdx.x;
+    const bool active = idx < total;  // tail lanes stay for the shuffles
+    if (!active) idx = total - 1;
+    const VecCoord c = decode_vec(idx, q, vec_per_pix, lanes_per_group);
+    bwd_vec_lane<T, A, BPL, KP, LOGITS>(c, c.v - c.g * lanes_per_group, active, in, off, mask, gout, gin, goff, gmask,
+                                        q, lanes_per_group);
 }
 
 // `per_cta` consecutive logical blocks per CTA (1 except for the selector-guarded launch, where a

@@ -12,8 +12,10 @@ Deliberate differences, all documented in DESIGN.md:
     src/cuda/dcnv3_cuda.cu:69,147);
   * ``im2col_step`` keeps its position and the reference's divisibility check
     (dcnv3_cuda.cu:46-49) but the whole batch is always one launch;
-  * 16-bit gradients come back in the storage dtype after fp32 accumulation
-    (same as dcnv3_cuda.cu:126-133,168-170) unless ``set_grad_accum('storage')``;
+  * 16-bit gradients come back in the storage dtype; grad_input is summed in fp32 per tile of output
+    pixels and across tiles in the storage dtype (``set_grad_accum('tile')``, the default), or in an fp32
+    workspace with one rounding (``'opmath'``, what dcnv3_cuda.cu:126-133,168-170 does), or per contribution
+    in the storage dtype (``'storage'``);
   * ``DCNv3SoftmaxFunction`` is the same op with the softmax over the sampling
     points fused in (``mask`` carries logits).
 
@@ -39,16 +41,18 @@ _DTYPES = {
     torch.float64: _lib.F64,
 }
 
-_GRAD_ACCUM = {"opmath": _lib.ACC_OPMATH, "storage": _lib.ACC_STORAGE}
-_grad_accum = _GRAD_ACCUM[os.environ.get("DCNV3_B200_GRAD_ACCUM", "opmath")]
+_GRAD_ACCUM = {"opmath": _lib.ACC_OPMATH, "storage": _lib.ACC_STORAGE, "tile": _lib.ACC_TILE}
+_grad_accum = _GRAD_ACCUM[os.environ.get("DCNV3_B200_GRAD_ACCUM", "tile")]
 
 
 def set_grad_accum(mode: str) -> None:
-    """How grad_input is accumulated for fp16/bf16 storage.
+    """How grad_input is accumulated for fp16/bf16 storage (include/dcnv3_b200.h).
 
-    'opmath'  (default) fp32 workspace, rounded once — the reference's semantics;
-    'storage' packed 16-bit vector reductions straight into grad_input (faster, one
-              rounding per contribution)."""
+    'tile'    (default) one kernel, no workspace: fp32 sums per 8x8 tile of output pixels on the SM, the tile's
+              window leaves as packed 16-bit reductions -> at most four roundings per element (rtol 1e-2 bar);
+              shapes the tile kernel does not take (group_channels != 16, not 3x3 s1 d1) run as 'opmath';
+    'opmath'  fp32 workspace, rounded once — the reference's semantics (dcnv3_cuda.cu:126-133,168-170);
+    'storage' packed 16-bit vector reductions per contribution straight into grad_input (~36 roundings)."""
     global _grad_accum
     _grad_accum = _GRAD_ACCUM[mode]
 
@@ -145,13 +149,16 @@ def _backward(ctx, logits, grad_output):
         grad_input = torch.empty_like(input)
         grad_offset = torch.empty_like(offset)
         grad_mask = torch.empty_like(mask)
-        ws_bytes = lib.dcnv3_b200_backward_workspace_bytes(dt, ctypes.byref(geo), _grad_accum)
+        accum = _grad_accum
+        if accum == _lib.ACC_TILE and ((input.data_ptr() | grad_output.data_ptr()) & 15 or offset.data_ptr() & 3):
+            accum = _lib.ACC_OPMATH  # views at odd byte offsets: the tile kernel needs 16-byte channel vectors
+        ws_bytes = lib.dcnv3_b200_backward_workspace_bytes(dt, ctypes.byref(geo), accum)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=input.device) if ws_bytes else None
         rc = lib.dcnv3_b200_backward(
             input.data_ptr(), offset.data_ptr(), mask.data_ptr(), grad_output.data_ptr(),
             grad_input.data_ptr(), grad_offset.data_ptr(), grad_mask.data_ptr(),
             ws.data_ptr() if ws is not None else None, ws_bytes, dt, ctypes.byref(geo),
-            int(logits), _grad_accum, _stream(input.device))
+            int(logits), accum, _stream(input.device))
     _lib.check(rc, "dcnv3_b200_backward")
     return (grad_input, grad_offset, grad_mask,
             None, None, None, None, None, None, None, None, None, None, None, None)
