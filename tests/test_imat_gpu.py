@@ -19,6 +19,17 @@ pytestmark = pytest.mark.gpu
 
 DEV = "cuda:0"
 
+
+@pytest.fixture(autouse=True)
+def _reference_accumulation():
+    """This module checks the reference's own 16-bit semantics (fp32 accumulation of grad_input, one rounding:
+    grad_accum 'opmath') and the explicit 'storage' opt-in; the default 'tile' mode has its own module, test_win_gpu.py."""
+    from yolo_dual_b200.ops_dcnv3.functions import get_grad_accum, set_grad_accum
+    prev = get_grad_accum()
+    set_grad_accum("opmath")
+    yield
+    set_grad_accum(prev)
+
 CASES = {
     "cfg1_G4": ((2, 80, 80, 4, 16), dict()),
     "partial_tiles_G8": ((2, 21, 19, 8, 16), dict()),

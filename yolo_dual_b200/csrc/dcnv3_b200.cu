@@ -306,7 +306,7 @@ int launch_bwd_imat(const T *in, const T *off, const T *mask, const T *gout, flo
 
 // ------------------------------------------------ single-kernel window backward (ACC_TILE)
 bool win_geometry(const Geo &q) {
-    return q.gc == 16 && q.G % win::kGrp == 0 && q.kh == 3 && q.kw == 3 && q.sh == 1 && q.sw == 1 && q.dh == 1 && q.dw == 1;
+    return q.gc == 16 && q.G % imat::kWarps == 0 && q.kh == 3 && q.kw == 3 && q.sh == 1 && q.sw == 1 && q.dh == 1 && q.dw == 1;
 }
 template <typename T>
 bool win_eligible(const Geo &q, const void *in, const void *off, const void *mask, const void *gout, const void *gin,
@@ -315,24 +315,25 @@ bool win_eligible(const Geo &q, const void *in, const void *off, const void *mas
     if (!aligned16(in) || !aligned16(gout) || !aligned16(gin)) return false;
     if ((reinterpret_cast<uintptr_t>(off) & 3u) || (reinterpret_cast<uintptr_t>(goff) & 3u) ||
         (reinterpret_cast<uintptr_t>(mask) & 1u) || (reinterpret_cast<uintptr_t>(gmask) & 1u)) return false;
-    const unsigned long long blocks = (unsigned long long)q.N * ((q.Ho + 7) / 8) * ((q.Wo + 7) / 8) * (q.G / win::kGrp);
-    if (blocks == 0 || blocks >= (1ull << 31)) return false;
-    // the far-tile fallback indexes (pixel, 8-channel vector) lanes with 32 bits
+    const unsigned long long blocks = (unsigned long long)q.N * ((q.Ho + 3) / 4) * ((q.Wo + 7) / 8) * (q.G / imat::kWarps);
+    if (blocks == 0 || blocks >= (1ull << 30)) return false;
+    // the far-band fallback indexes (pixel, 8-channel vector) lanes with 32 bits
     return (unsigned long long)q.N * q.Ho * q.Wo * (q.C / 8) < (1ull << 31);
 }
 
+// one launch: CTA 2u = grad_offset / grad_mask of unit u, CTA 2u + 1 = its grad_input (dcnv3_win.cuh)
 template <typename T>
 int launch_bwd_win(const T *in, const T *off, const T *mask, const T *gout, T *gin, T *goff, T *gmask,
                    const Geo &q, bool logits, cudaStream_t st) {
-    const int tiles_y = (q.Ho + 7) / 8, tiles_x = (q.Wo + 7) / 8, GQ = q.G / win::kGrp;
-    const unsigned grid = (unsigned)((size_t)q.N * tiles_y * tiles_x * GQ);
+    const int tiles_x = (q.Wo + 7) / 8, bands_y = (q.Ho + 3) / 4, GQ = q.G / imat::kWarps;
+    const unsigned grid = 2u * (unsigned)((size_t)q.N * bands_y * tiles_x * GQ);
     int rc;
     if (logits) {
         if ((rc = set_smem(win::bwd_win_kernel<T, true>, win::kSmemB, "cudaFuncSetAttribute(bwd_win_kernel)"))) return rc;
-        launch(win::bwd_win_kernel<T, true>, grid, win::kThreadsW, win::kSmemB, st, in, off, mask, gout, gin, goff, gmask, q, GQ);
+        launch(win::bwd_win_kernel<T, true>, grid, win::kThreadsW, win::kSmemB, st, in, off, mask, gout, gin, goff, gmask, q, GQ, tiles_x, bands_y);
     } else {
         if ((rc = set_smem(win::bwd_win_kernel<T, false>, win::kSmemB, "cudaFuncSetAttribute(bwd_win_kernel)"))) return rc;
-        launch(win::bwd_win_kernel<T, false>, grid, win::kThreadsW, win::kSmemB, st, in, off, mask, gout, gin, goff, gmask, q, GQ);
+        launch(win::bwd_win_kernel<T, false>, grid, win::kThreadsW, win::kSmemB, st, in, off, mask, gout, gin, goff, gmask, q, GQ, tiles_x, bands_y);
     }
     return 0;
 }

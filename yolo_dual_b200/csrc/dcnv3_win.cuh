@@ -1,30 +1,31 @@
-// dcnv3_b200 — single-kernel backward from a staged window (16-bit storage, group_channels = 16, 3x3 s1 d1).
+// dcnv3_b200 — round-2 default backward for 16-bit storage, group_channels = 16, 3x3 s1 d1 (ACC_TILE): two lean kernels
+// instead of the four-launch chain zero_select -> bwd_imat -> guarded bwd_vec -> cast (no fp32 workspace, no selector
+// kernel, no cast).  A fused single kernel was built first and measured (profiles/r02_bwd_kernel_history.md): window +
+// interpolation matrix + grad_output need 90 KB of shared memory per CTA, i.e. two CTAs = 16 warps per SM, and the
+// phases (gather/dots -> barrier -> tensor cores -> flush) serialise: 195 us at P3 with the issue slots 46 % busy.
+// Split, each half fits three CTAs per SM and overlaps with the other under programmatic dependent launch:
 //
-// Round-2 replacement for the four-launch chain zero_select -> bwd_imat -> guarded bwd_vec -> cast:
-// one kernel, no fp32 workspace, no selector kernel, no cast.  grad_input accumulation mode ACC_TILE.
-//
-//   * a CTA (256 threads) owns an 8x8 tile of output pixels of one image and 4 groups (64 channels); the 16x16-cell
-//     input window the tile reaches with |offset * scale| < 3 px is staged once in shared memory (cp.async, zero
-//     fill outside the map = the reference's per-corner validity, dcnv3_im2col_cuda.cuh:57-75), UNswizzled: a
-//     cell is one 128-byte row and lane (g, h) always reads 16-byte chunk 2g + h first, so the eight lanes of a
-//     pixel hit eight different bank groups whatever cells its four groups sample (conflict-free LDS.128);
-//   * the two lanes (h = 0, 1) of a (pixel, group) split the nine POINTS (4 + 4 whole points with all 16 channels,
-//     the ninth by channel halves).  The four corner dots d_k = sum_c go[c] * x_k[c] of a point are EXACT
-//     mixed-precision FMAs (PTX fma.rn.f32.bf16 / .f16 -> FHFMA: 16-bit operands straight from the halves of the
-//     loaded registers, fp32 accumulation, no unpack instructions), and give
-//         grad_mask   = sum_k w_k d_k                                            (cuh:144)
+//   win::bwd_dots_kernel     grad_offset / grad_mask.  The forward's structure: a CTA stages the 20x20-cell x 64-channel
+//     window of an (8x8 tile, 4 groups) once (cp.async, zero fill outside the map = the reference's per-corner
+//     validity, dcnv3_im2col_cuda.cuh:57-75), unswizzled, so that the eight lanes of a pixel (4 groups x 2 halves) hit
+//     eight different bank groups whatever cells they sample (conflict-free LDS.128).  The two lanes of a (pixel,
+//     group) split the nine POINTS; the four corner dots d_k = sum_c go[c] * x_k[c] of a point are EXACT mixed-precision
+//     FMAs (PTX fma.rn.f32.bf16 / .f16 -> FHFMA: 16-bit operands straight from the halves of the loaded registers,
+//     fp32 accumulation, no unpack instructions) and give
+//         grad_mask   = sum_k w_k d_k                                                            (cuh:144)
 //         grad_offset = scale * m * (hh (d2 - d1) + lh (d4 - d3), hw (d3 - d1) + lw (d4 - d2))   (cuh:114-139,145-146)
-//     written straight from the lane (a pixel's 4 groups x 9 points are 144 contiguous bytes);
-//   * grad_input: the lane adds w_k * m as packed 16-bit pairs into its pixel's private row of the interpolation
-//     matrix Wm[pixel][12 band rows][16 window columns] in fp16 (the two lanes of a pixel own the
-//     rows of even / odd parity, one shuffle exchange, no atomics), and the tensor cores expand it:
-//         GW[cell][ch] += sum_pixel Wm[pixel][cell] * go[pixel][ch]      mma.sync m16n8k16, fp32 accumulators
-//     in registers over the tile's two 4-row bands; the window leaves the SM once as packed 16-bit vector
-//     reductions (red.global.add.noftz.v4.bf16x2 / .f16x2) straight into the zero-filled grad_input: a cell sees
-//     at most four per-tile partial sums (each summed in fp32), i.e. at most four roundings.
-//   * a band whose offsets are large (> 1 lane in 4 with an offset coordinate of 3 px or more) runs the vector
-//     kernel's lane body instead (bwd_vec_lane, packed 16-bit reductions per contribution); a single point
-//     that leaves the window takes bwd_point_slow (global gathers, reductions for that point only).
+//   win::bwd_scatter_kernel  grad_input.  A CTA owns a 4-row x 8-column band of output pixels and 4 groups and needs no
+//     window: a lane adds w_k * m as packed fp16 pairs into its pixel's private row of the interpolation matrix
+//     Wm[pixel][12 band rows][16 window columns] (the two lanes of a pixel own the rows of even / odd parity, one
+//     shuffle exchange, no atomics) and the tensor cores expand it:
+//         GW[cell][ch] = sum_pixel Wm[pixel][cell] * go[pixel][ch]       mma.sync m16n8k16, fp32 accumulators
+//     then the band's 12x16-cell window leaves the SM once as packed 16-bit vector reductions
+//     (red.global.add.noftz.v4.bf16x2 / .f16x2) into the zero-filled grad_input: every partial is an fp32 sum of all
+//     the band's contributions to that cell, and a cell sees at most six of them.
+//   A band whose offsets are large (more than 1 lane in 4 with an offset coordinate of 3 px or more) is skipped by
+//   the dots kernel and runs the vector family's lane body in the scatter kernel (bwd_vec_lane: all three gradients,
+//   packed 16-bit reductions per contribution); a single point that leaves the window takes a per-point slow path
+//   in each kernel (global gathers for the dots, reductions for that point only).
 //
 // Location arithmetic is the shared locate() sequence (locate_lean: same operations in the same order), so the
 // integer contract is unchanged.  Reference semantics: dcnv3_col2im_gpu_kernel_* :278-839 + dcnv3_col2im_bilinear :82-147.
@@ -42,18 +43,22 @@ using imat::PtGeo;
 using imat::TileCoord;
 
 constexpr int kThreadsW = 256;
-constexpr int kGrp = 2;                                  // groups per CTA (32 channels)
-constexpr int kCellB = kGrp * 32;                        // 64 B per window cell
-constexpr int kWinW = 16;                                // window cells per edge: tile + 2 * 4
-constexpr int kWinB = kWinW * kWinW * kCellB;            // 16 384 B
+constexpr int kWinW = 16;                                // window columns the band's interpolation matrix spans: 8 + 2 * 4
 constexpr int kBandRows = 12;                            // window rows a 4-row band of pixels reaches
 constexpr int kRowB = kBandRows * kWinW * 2 + 16;        // 400 B per (pixel, group): +16 B skew (ldmatrix rows on distinct banks)
-constexpr int kGrpB = 32 * kRowB + 16;                   // 12 816 B per (band, group): +16 B so the blocks' rows start on different banks
-constexpr int kWmB = 2 * kGrp * kGrpB;                   // 51 264 B: [band][group][32 pixels]
-constexpr int kGoRowB = 48;                              // grad_output rows of the tile: 32 B + 16 B skew
-constexpr int kGoGrpB = 64 * kGoRowB;
-constexpr int kGoB = kGrp * kGoGrpB;                     // 6 144 B
-constexpr int kSmemB = kWinB + kWmB + kGoB;              // 73 792 B: three CTAs per SM
+constexpr int kGrpB = 32 * kRowB + 16;                   // 12 816 B per group: +16 B so the groups' rows start on different banks
+constexpr int kWmB = kWarps * kGrpB;                     // 51 264 B: [group][32 pixels]
+constexpr int kGoRowB = 48;                              // grad_output rows of the band: 32 B + 16 B skew
+constexpr int kGoGrpB = 32 * kGoRowB;
+constexpr int kGoB = kWarps * kGoGrpB;                   // 6 144 B
+constexpr int kScatB = kWmB + kGoB;                      // 57 408 B: three CTAs per SM
+constexpr int kDwinB = kBandRows * kWinW * 128;          // dots role: the band's 12x16-cell x 64-channel window, 24 576 B
+constexpr int kSmemB = kScatB > kDwinB ? kScatB : kDwinB;
+#ifndef DCNV3_WIN_PREFETCH_UNITS
+#define DCNV3_WIN_PREFETCH_UNITS 320
+#endif
+constexpr unsigned kPrefetchUnits = DCNV3_WIN_PREFETCH_UNITS;  // L2 prefetch distance in units (~2/3 of a wave of 444 CTAs apart... see bwd_win_kernel)
+constexpr int kFarLanes = kThreadsW / 4;                 // a band is "far" when more lanes than this see a >= 3 px offset
 static_assert(kWmB % 16 == 0 && kGrpB % 16 == 0 && kRowB % 16 == 0, "ldmatrix rows are 16-byte aligned");
 
 using imat::Mix;
@@ -107,26 +112,6 @@ __device__ __forceinline__ float corner_dot8(uint32_t a_own, const uint4 &g_own)
     return s0 + s1;
 }
 
-// Stage the 16x16-cell x 32-channel input window of (tile, group pair), unswizzled; zero outside the map.
-// 256 threads: thread = (row quarter, column, 16-byte chunk), four window rows each.
-template <typename T>
-__device__ __forceinline__ void fill_window16(unsigned char *win, const T *in, const T *img, const Geo &q,
-                                              int wy0, int wx0, int tid) {
-    const int ch = tid & 3, col = (tid >> 2) & 15, r0 = (tid >> 6) * 4;
-    const int ix = wx0 + col;
-    const bool col_ok = (unsigned)ix < (unsigned)q.W;
-    const size_t step = (size_t)q.W * q.C;
-    const T *p = img + ((long long)(wy0 + r0) * q.W + ix) * q.C + ch * 8;
-    uint32_t dst = imat::smem_u32(win) + (r0 * kWinW + col) * kCellB + (ch << 4);
-    int iy = wy0 + r0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const bool ok = col_ok && (unsigned)iy < (unsigned)q.H;
-        imat::cp_async16(dst, ok ? p : in, ok ? 16 : 0);
-        p += step; dst += kWinW * kCellB; ++iy;
-    }
-}
-
 // packed 16-bit pair (two adjacent window columns of one band row) += into the pixel's Wm row.  Element e = band
 // row * 16 + column (column <= 14).  An odd column straddles two words; the second store is predicated so that a
 // lane never writes a word of a row it does not own (rows of the other parity belong to the partner lane).
@@ -158,20 +143,17 @@ __device__ __forceinline__ float dot_chunk(const uint4 &x, const uint4 &g) {
     return s0 + s1;
 }
 
-// A point that lies inside the map but leaves the band's window (|offset * scale| >= 3 px): the corner dots come
-// from global memory with the reference's per-corner validity and the point's grad_input contributions go out
-// right here as packed 16-bit vector reductions.  `img_c` / `gin_c` point at the first channel of chunk a, chunk b is
-// `delta_b` elements away; the dots always cover both chunks, the reductions chunk a (nred = 1: point 8, whose two
-// lanes reduce one half each) or both (nred = 2: a whole point).  Rare, non-inlined.
+// ---- slow paths (rare: |offset * scale| >= 3 px resp. 5 px; non-inlined) ---------------------------------------
+// Corner dots of a point outside the staged window: global gathers with the reference's per-corner validity.  `img_c`
+// points at the first channel of chunk a of the group's slab, chunk b is `delta_b` elements away.
 template <typename T>
-__device__ __noinline__ float4 bwd_point_slow(const PtGeo pg, const float p0h_, const float p0w_, const int i, const int j,
-                                              const uint32_t offw, const float m, const uint4 ga, const uint4 gb,
-                                              const int nred, const T *img_c, T *gin_c, const int delta_b, const int C) {
+__device__ __noinline__ float4 dots_point_slow(const PtGeo pg, const float p0h_, const float p0w_, const int i, const int j,
+                                               const uint32_t offw, const uint4 ga, const uint4 gb, const T *img_c,
+                                               const int delta_b, const int C) {
     const Geo q = imat::geo_of(pg);
     const float2 o = imat::unpack2f<T>(offw);
     Point<float> t;
     locate<float>(q, p0h_, p0w_, i, j, o.x, o.y, t);
-    const float w[4] = {t.hh * t.hw, t.hh * t.lw, t.lh * t.hw, t.lh * t.lw};
     const bool ok[4] = {t.ok1, t.ok2, t.ok3, t.ok4};
     float d[4];
 #pragma unroll 1
@@ -179,75 +161,130 @@ __device__ __noinline__ float4 bwd_point_slow(const PtGeo pg, const float p0h_, 
         d[k] = 0.f;
         if (!ok[k]) continue;
         const size_t e = ((size_t)(t.h_low + (k >> 1)) * q.W + (t.w_low + (k & 1))) * C;
-        const float wm = w[k] * m;
         const uint4 xa = __ldg(reinterpret_cast<const uint4 *>(img_c + e));
-        float acc = dot_chunk<T>(xa, ga);
-        red_add_v4<T>(gin_c + e, scale_chunk<T>(ga, wm), true);
         const uint4 xb = __ldg(reinterpret_cast<const uint4 *>(img_c + e + delta_b));
-        acc += dot_chunk<T>(xb, gb);
-        if (nred == 2) red_add_v4<T>(gin_c + e + delta_b, scale_chunk<T>(gb, wm), true);
-        d[k] = acc;
+        d[k] = dot_chunk<T>(xa, ga) + dot_chunk<T>(xb, gb);
     }
     return make_float4(d[0], d[1], d[2], d[3]);
 }
 
-// The vector family's lane body for one (pixel, 8 channels): used by a band whose offsets are large.
+// grad_input contributions of a point outside the band's window: packed 16-bit vector reductions, chunk a of the
+// group's slab (nred = 1: point 8, whose two lanes reduce one half each) or both chunks (nred = 2: a whole point).
+template <typename T>
+__device__ __noinline__ void scatter_point_slow(const PtGeo pg, const float p0h_, const float p0w_, const int i, const int j,
+                                                const uint32_t offw, const float m, const uint4 ga, const T *go_b,
+                                                const int nred, T *gin_c, const int delta_b, const int C) {
+    const Geo q = imat::geo_of(pg);
+    const float2 o = imat::unpack2f<T>(offw);
+    Point<float> t;
+    locate<float>(q, p0h_, p0w_, i, j, o.x, o.y, t);
+    const float w[4] = {t.hh * t.hw, t.hh * t.lw, t.lh * t.hw, t.lh * t.lw};
+    const bool ok[4] = {t.ok1, t.ok2, t.ok3, t.ok4};
+    uint4 gb = make_uint4(0u, 0u, 0u, 0u);
+    if (nred == 2) gb = __ldg(reinterpret_cast<const uint4 *>(go_b));
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        if (!ok[k]) continue;
+        const size_t e = ((size_t)(t.h_low + (k >> 1)) * q.W + (t.w_low + (k & 1))) * C;
+        const float wm = w[k] * m;
+        red_add_v4<T>(gin_c + e, scale_chunk<T>(ga, wm), true);
+        if (nred == 2) red_add_v4<T>(gin_c + e + delta_b, scale_chunk<T>(gb, wm), true);
+    }
+}
+
+// The vector family's lane body for one (pixel, 8 channels): all three gradients of a band whose offsets are large.
 template <typename T, bool LOGITS>
 __device__ __noinline__ void bwd_far_lane(const VecCoord c, const int h, const bool active, const T *in, const T *off,
                                           const T *mask, const T *gout, T *gin, T *goff, T *gmask, const Geo q) {
     bwd_vec_lane<T, T, 16, 9, LOGITS>(c, h, active, in, off, mask, gout, gin, goff, gmask, q, 2);
 }
 
-template <int V> struct IntC {  // compile-time band index (std::integral_constant's conversion is a host function)
-    __device__ constexpr operator int() const { return V; }
-};
+// Does this lane see an offset coordinate of 3 px or more among its five points?  (packed storage bits: positive
+// 16-bit floats order like integers.)  Both kernels count these lanes per band with the same code on the same data.
+template <typename T>
+__device__ __forceinline__ bool lane_far(const uint32_t (&roff)[5], float scale) {
+    const uint32_t thr = imat::storage_bits<T>(3.f / fabsf(scale));
+    uint32_t far = 0u;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const uint32_t a = roff[k] & 0x7fff7fffu;
+        far |= (a >= (thr << 16) || (a & 0xffffu) >= thr) ? 1u : 0u;
+    }
+    return far != 0u;
+}
 
 __device__ __forceinline__ uint32_t sel4(const uint32_t (&a)[4], int idx) {
     const uint32_t lo = (idx & 1) ? a[1] : a[0], hi = (idx & 1) ? a[3] : a[2];
     return (idx & 2) ? hi : lo;
 }
 
+// kernel-grid coordinates of a lane's point slot k: points 4h + k (k < 4) and 8 (k = 4); i = p / 3 (kernel_w), j = p % 3
+__device__ __forceinline__ int slot_i(int k, int h) { return k == 4 ? 2 : (h ? (4 + k) / 3 : k / 3); }
+__device__ __forceinline__ int slot_j(int k, int h) { return k == 4 ? 2 : (h ? (4 + k) % 3 : k % 3); }
+
+// ===========================================================================================================
+// One launch, two kinds of CTA.  Unit u = (image, 4-row band, 8-column tile, group quad); CTA 2u computes the
+// unit's grad_offset / grad_mask ("dots" role: needs the 12x16-cell window, 24 KB), CTA 2u + 1 its grad_input
+// ("scatter" role: interpolation matrix + grad_output, 57 KB).  The two roles stress different pipes (FMA / issue
+// versus shared-memory wavefronts) and neighbours in blockIdx order land on the same SM three at a time.
+// ===========================================================================================================
+__device__ __forceinline__ void stmatrix_x4(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+
 template <typename T, bool LOGITS>
 __global__ void __launch_bounds__(kThreadsW, 3)
 bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
                const T *__restrict__ gout, T *__restrict__ gin, T *__restrict__ goff, T *__restrict__ gmask,
-               const Geo q, const int GQ) {
+               const Geo q, const int GQ, const int tiles_x, const int bands_y) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool kScaled = std::is_same<T, __nv_bfloat16>::value;
     __shared__ __align__(16) uint32_t smax[8];
     pdl_enter();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const TileCoord tc = imat::decode_tile_lpt(blockIdx.x, q.Ho, q.Wo, q.N, GQ);
-    const int wy0 = tc.ty * kTile + (q.half_h - q.ph) - 4;  // input row / column of window cell (0, 0)
-    const int wx0 = tc.tx * kTile + (q.half_w - q.pw) - 4;
-    const size_t img_off = (size_t)tc.n * q.H * q.W * q.C + tc.gq * (kGrp * 16);
-    const T *img = in + img_off;
-    const PtGeo pg{q.H, q.W, q.scale};
-
-    unsigned char *Wm = smem + kWinB;
-    unsigned char *Gos = Wm + kWmB;
-    fill_window16<T>(smem, in, img, q, wy0, wx0, tid);
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    const bool dots_role = (blockIdx.x & 1u) == 0u;
+    TileCoord tc;  // (image, band row, tile column, group quad)
     {
-        uint4 *Z = reinterpret_cast<uint4 *>(Wm);
+        unsigned b = blockIdx.x >> 1;
+        tc.gq = (int)(b % (unsigned)GQ); b /= (unsigned)GQ;
+        tc.tx = (int)(b % (unsigned)tiles_x); b /= (unsigned)tiles_x;
+        tc.ty = (int)(b % (unsigned)bands_y);
+        tc.n = (int)(b / (unsigned)bands_y);
+    }
+    const int by0 = tc.ty * 4 + (q.half_h - q.ph) - 4;      // input row / column of band-window cell (0, 0)
+    const int wx0 = tc.tx * kTile + (q.half_w - q.pw) - 4;
+    const size_t img_off = (size_t)tc.n * q.H * q.W * q.C + tc.gq * 64;
+    const PtGeo pg{q.H, q.W, q.scale};
+    const uint32_t smem_s = imat::smem_u32(smem);
+
+    if (dots_role) {  // stage the 12x16-cell x 64-channel window, unswizzled; zero outside the map
+        const int ch = tid & 7, col = (tid >> 3) & 15, r0 = tid >> 7;
+        const int ix = wx0 + col;
+        const bool col_ok = (unsigned)ix < (unsigned)q.W;
+        const size_t step = (size_t)2 * q.W * q.C;
+        const T *p = in + img_off + ((long long)(by0 + r0) * q.W + ix) * q.C + ch * 8;
+        uint32_t dst = smem_s + (r0 * kWinW + col) * 128 + (ch << 4);
+        int iy = by0 + r0;
+#pragma unroll
+        for (int i = 0; i < kBandRows / 2; ++i) {
+            const bool ok = col_ok && (unsigned)iy < (unsigned)q.H;
+            imat::cp_async16(dst, ok ? p : in, ok ? 16 : 0);
+            p += step; dst += 2 * kWinW * 128; iy += 2;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    } else {          // zero the interpolation matrix
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        for (int i = tid; i < kWmB / 16; i += kThreadsW) Z[i] = z;
+#pragma unroll
+        for (int i = 0; i < (kWmB / 16 + kThreadsW - 1) / kThreadsW; ++i) {
+            const int id = i * kThreadsW + tid;
+            if (id < kWmB / 16) sts128(smem_s + id * 16, z);
+        }
     }
 
-    // SIMT roles: 4 lanes per pixel = 2 groups x 2 point halves; all 64 pixels of the tile at once (warp = tile row)
-    const int px = tid >> 2, sub = tid & 3, gl = sub >> 1, h = sub & 1;
-    const int band = px >> 5, pxb = px & 31;  // 4-row band of the pixel and its index inside the band
-    const int g = tc.gq * kGrp + gl;
-    const uint32_t win_s = imat::smem_u32(smem);
-    const uint32_t own16 = (uint32_t)sub << 4, oth16 = (uint32_t)(sub ^ 1) << 4;
-    const uint32_t row_s = imat::smem_u32(Wm) + (band * kGrp + gl) * kGrpB + pxb * kRowB;
-    const uint32_t gos_s = imat::smem_u32(Gos) + gl * kGoGrpB + px * kGoRowB + 16 * h;
-    const T *img_g = img + gl * 16;
-    T *gin_g = gin + img_off + gl * 16;
-    // an offset coordinate with |off * scale| >= 3 px can leave the window (tested on the packed storage bits)
-    const uint32_t thr = imat::storage_bits<T>(3.f / fabsf(q.scale));
-
-    const int oy = tc.ty * kTile + (px >> 3), ox = tc.tx * kTile + (px & 7);
+    // lanes: 8 per pixel = 4 groups x 2 point halves; the band's 32 pixels
+    const int px = tid >> 3, sub = tid & 7, gl = sub >> 1, h = sub & 1;
+    const int g = tc.gq * kWarps + gl;
+    const int oy = tc.ty * 4 + (px >> 3), ox = tc.tx * kTile + (px & 7);
     const bool valid = oy < q.Ho && ox < q.Wo;
     const int cy = min(oy, q.Ho - 1), cx = min(ox, q.Wo - 1);  // clamped: addresses of an idle lane stay legal
     const size_t pix = ((size_t)tc.n * q.Ho + cy) * q.Wo + cx;
@@ -273,15 +310,32 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     uint4 g_own = make_uint4(0u, 0u, 0u, 0u), g_oth = g_own;
     if (valid) {
         g_own = __ldg(gp + h);
-        g_oth = __ldg(gp + (h ^ 1));
+        if (dots_role) g_oth = __ldg(gp + (h ^ 1));
     }
-    uint32_t far = 0u;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        const uint32_t a = roff[k] & 0x7fff7fffu;
-        far |= (a >= (thr << 16) || (a & 0xffffu) >= thr) ? 1u : 0u;
+#ifdef DCNV3_WIN_PREFETCH  // measured SLOWER (P3 195.0 vs 191.0 us at any distance, profiles/r02_bwd_kernel_history.md): off by default
+    // The CTAs of a unit are short (~2 k cycles) and begin with a round trip to DRAM for offsets / masks / grad_output.
+    // A dots CTA therefore asks L2 for the lines of the unit that starts ~kPrefetchUnits later (both of its CTAs profit):
+    // per pixel the 144-byte offset chunk (two lines), the 72-byte mask chunk (two) and the 128-byte grad_output slab.
+    if (dots_role && tid < 160) {
+        unsigned b = (blockIdx.x >> 1) + kPrefetchUnits;
+        TileCoord pc;
+        pc.gq = (int)(b % (unsigned)GQ); b /= (unsigned)GQ;
+        pc.tx = (int)(b % (unsigned)tiles_x); b /= (unsigned)tiles_x;
+        pc.ty = (int)(b % (unsigned)bands_y);
+        pc.n = (int)(b / (unsigned)bands_y);
+        const int pp = tid & 31, which = tid >> 5;
+        const int poy = pc.ty * 4 + (pp >> 3), pox = pc.tx * kTile + (pp & 7);
+        if (pc.n < q.N && poy < q.Ho && pox < q.Wo) {
+            const size_t ppix = ((size_t)pc.n * q.Ho + poy) * q.Wo + pox;
+            const char *a;
+            if (which < 2) a = reinterpret_cast<const char *>(off + (ppix * q.G + pc.gq * kWarps) * 18) + which * 143;
+            else if (which < 4) a = reinterpret_cast<const char *>(mask + (ppix * q.G + pc.gq * kWarps) * 9) + (which - 2) * 71;
+            else a = reinterpret_cast<const char *>(gout + ppix * q.C + pc.gq * 64);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        }
     }
-    if constexpr (kScaled) {  // largest |grad_output| of the tile (bf16 magnitudes compare like integers)
+#endif
+    if constexpr (kScaled) {  // scatter role: largest |grad_output| of the band (bf16 magnitudes compare like integers)
         const uint32_t w[4] = {g_own.x, g_own.y, g_own.z, g_own.w};
         uint32_t mx = 0u;
 #pragma unroll
@@ -292,36 +346,17 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         mx = __reduce_max_sync(0xffffffffu, mx);
         if (lane == 0) smax[warp] = mx;
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    // barrier A: the window is staged, Wm is zero, the per-warp maxima are visible
-    const bool far_tile = __syncthreads_count(far != 0u) * 4 > kThreadsW;
-    if (far_tile) {  // CTA-uniform: the vector family's lane body, straight to global memory
-        VecCoord c;
-        c.pix = (unsigned)pix; c.v = tc.gq * (2 * kGrp) + sub; c.g = g; c.n = tc.n; c.ho = cy; c.wo = cx;
-        bwd_far_lane<T, LOGITS>(c, h, valid, in, off, mask, gout, gin, goff, gmask, q);
-        return;
-    }
-    // B operand of the mma (an idle lane stores zeros).  The interpolation matrix is fp16 for both storage dtypes
-    // (11-bit weights; bf16 weights, 8 bits, miss the atol 2e-3 bar on ~1e-5 of the elements), so bf16 grad_output enters
-    // the product as fp16 after a power-of-two scaling per tile: go' = go * 2^(127 - e_ref), e_ref = biased exponent of
-    // the tile's largest |go|.  Exact for every value within 2^-14 of that maximum, smaller ones lose low bits
-    // (absolute error below 2^-24 of the tile's largest gradient).  The corner dots below use the bf16 values themselves.
-    int e_ref = 127;
-    if constexpr (kScaled) {
-        const uint4 s0 = *reinterpret_cast<const uint4 *>(smax), s1 = *reinterpret_cast<const uint4 *>(smax + 4);
-        const uint32_t mx = max(max(max(s0.x, s0.y), max(s0.z, s0.w)), max(max(s1.x, s1.y), max(s1.z, s1.w)));
-        e_ref = min(max((int)(mx >> 7), 1), 253);
-        const float sc = __uint_as_float((uint32_t)(254 - e_ref) << 23);
-        const uint32_t w[4] = {g_own.x, g_own.y, g_own.z, g_own.w};
-        uint32_t r[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float2 f = imat::unpack2f<T>(w[c]);
-            r[c] = imat::pack2<__half>(f.x * sc, f.y * sc);
+    if (dots_role) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // barrier A: the window is staged / Wm is zero and the per-warp maxima are visible.  A far band is skipped by the
+    // dots CTA and handled as a whole by the scatter CTA (same count in both: same lanes, same offsets).
+    const bool far_band = __syncthreads_count(lane_far<T>(roff, q.scale)) > kFarLanes;
+    if (far_band) {
+        if (!dots_role) {  // the vector family's lane body computes all three gradients of the band
+            VecCoord c;
+            c.pix = (unsigned)pix; c.v = tc.gq * 8 + sub; c.g = g; c.n = tc.n; c.ho = cy; c.wo = cx;
+            bwd_far_lane<T, LOGITS>(c, h, valid, in, off, mask, gout, gin, goff, gmask, q);
         }
-        sts128(gos_s, make_uint4(r[0], r[1], r[2], r[3]));
-    } else {
-        sts128(gos_s, g_own);
+        return;
     }
 
     float p0h_, p0w_;
@@ -336,57 +371,140 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
 #pragma unroll
         for (int k = 0; k < 5; ++k) mk[k] = rm[k];
     }
-    const int by0 = wy0 + 4 * band;  // input row of band row 0
-    uint32_t band_s = win_s + (uint32_t)(4 * band) * (kWinW * kCellB);
-    asm volatile("" : "+r"(band_s));  // the window gathers below depend on this: they stay behind barrier A
-    uint32_t res_off[5];
-    float res_m[5];
-    uint32_t *qo = reinterpret_cast<uint32_t *>(goff) + unit * 9;
-    unsigned short *qm = reinterpret_cast<unsigned short *>(gmask) + unit * 9;
-    uint32_t slowmask = 0u;
 
-    // One straight-line block (no branch inside: ptxas is free to overlap a point's gathers with the previous
-    // point's arithmetic).  A point that is not window-resident reads cell 0 and its results are dropped.
+    if (dots_role) {
+        // =================================================================== grad_offset / grad_mask
+        const uint32_t own16 = (uint32_t)sub << 4, oth16 = (uint32_t)(sub ^ 1) << 4;
+        const T *img_g = in + img_off + gl * 16;
+        uint32_t win_s = smem_s;
+        asm volatile("" : "+r"(win_s));  // the window gathers below depend on this: they stay behind barrier A
+        uint32_t res_off[5];
+        float res_m[5];
+        uint32_t slowmask = 0u;
+        // one straight-line block: a point that is not window-resident reads cell 0 and its results are dropped
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const float2 o = imat::unpack2f<T>(roff[k]);
+            const LeanPoint t = imat::locate_lean(pg, p0h_, p0w_, (float)slot_i(k, h), (float)slot_j(k, h), o.x, o.y);
+            const unsigned u = (unsigned)(t.w_low - wx0), vb = (unsigned)(t.h_low - by0);
+            const bool inband = u <= (unsigned)(kWinW - 2) && vb <= (unsigned)(kBandRows - 2);
+            const bool fast = t.inside && inband && valid;
+            slowmask |= (t.inside && !inband && valid ? 1u : 0u) << k;  // same for both lanes of the pair
+            const uint32_t a = win_s + (fast ? vb * kWinW + u : 0u) * 128u;
+            float d0, d1, d2, d3;
+            if (k < 4) {
+                d0 = corner_dot16<T>(a + own16, a + oth16, g_own, g_oth);
+                d1 = corner_dot16<T>(a + own16 + 128, a + oth16 + 128, g_own, g_oth);
+                d2 = corner_dot16<T>(a + own16 + kWinW * 128, a + oth16 + kWinW * 128, g_own, g_oth);
+                d3 = corner_dot16<T>(a + own16 + kWinW * 128 + 128, a + oth16 + kWinW * 128 + 128, g_own, g_oth);
+            } else {  // point 8: the two lanes take 8 channels each and meet
+                d0 = corner_dot8<T>(a + own16, g_own);
+                d1 = corner_dot8<T>(a + own16 + 128, g_own);
+                d2 = corner_dot8<T>(a + own16 + kWinW * 128, g_own);
+                d3 = corner_dot8<T>(a + own16 + kWinW * 128 + 128, g_own);
+                d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+                d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
+                d2 += __shfl_xor_sync(0xffffffffu, d2, 1);
+                d3 += __shfl_xor_sync(0xffffffffu, d3, 1);
+            }
+            const float lh = t.lh, lw = t.lw;
+            const float hh = sub_rn(1.f, lh), hw = sub_rn(1.f, lw);
+            const float s_m = (hh * hw) * d0 + (hh * lw) * d1 + (lh * hw) * d2 + (lh * lw) * d3;
+            const float s_w = hh * (d1 - d0) + lh * (d3 - d2);
+            const float s_h = hw * (d2 - d0) + lw * (d3 - d1);
+            const float sm = q.scale * mk[k];
+            res_off[k] = fast ? imat::pack2<T>(sm * s_w, sm * s_h) : 0u;
+            res_m[k] = fast ? s_m : 0.f;
+        }
+        if (slowmask) {  // rare: points inside the map but outside the band's window (|offset * scale| >= 3 px)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                if (!((slowmask >> k) & 1u)) continue;
+                const float4 d = dots_point_slow<T>(pg, p0h_, p0w_, slot_i(k, h), slot_j(k, h), roff[k], g_own, g_oth,
+                                                    img_g + 8 * h, h ? -8 : 8, q.C);
+                const float2 o = imat::unpack2f<T>(roff[k]);
+                const LeanPoint t = imat::locate_lean(pg, p0h_, p0w_, (float)slot_i(k, h), (float)slot_j(k, h), o.x, o.y);
+                const float lh = t.lh, lw = t.lw;
+                const float hh = sub_rn(1.f, lh), hw = sub_rn(1.f, lw);
+                const float s_m = (hh * hw) * d.x + (hh * lw) * d.y + (lh * hw) * d.z + (lh * lw) * d.w;
+                const float s_w = hh * (d.y - d.x) + lh * (d.w - d.z);
+                const float s_h = hw * (d.z - d.x) + lw * (d.w - d.y);
+                const float sm = q.scale * mk[k];
+                res_off[k] = imat::pack2<T>(sm * s_w, sm * s_h);
+                res_m[k] = s_m;
+            }
+        }
+        // grad_offset / grad_mask (cuh:144-146); fused softmax: dl_p = m_p (gm_p - sum_q m_q gm_q)
+        if (LOGITS) {
+            float dot = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dot = fmaf(mk[k], res_m[k], dot);
+            if (h == 0) dot = fmaf(mk[4], res_m[4], dot);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) res_m[k] = mk[k] * (res_m[k] - dot);
+        }
+        if (valid) {
+            uint32_t *qo = reinterpret_cast<uint32_t *>(goff) + unit * 9;
+            unsigned short *qm = reinterpret_cast<unsigned short *>(gmask) + unit * 9;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                qo[4 * h + k] = res_off[k];
+                qm[4 * h + k] = (unsigned short)(imat::pack2<T>(res_m[k], 0.f) & 0xffffu);
+            }
+            if (h == 0) {
+                qo[8] = res_off[4];
+                qm[8] = (unsigned short)(imat::pack2<T>(res_m[4], 0.f) & 0xffffu);
+            }
+        }
+        return;
+    }
+
+    // ======================================================================= grad_input
+    const uint32_t wm_s = smem_s, gos_base = smem_s + kWmB;
+    const uint32_t row_s = wm_s + gl * kGrpB + px * kRowB;
+    T *gin_g = gin + img_off + gl * 16;
+    // B operand of the mma (an idle lane stores zeros).  The interpolation matrix is fp16 for both storage dtypes
+    // (11-bit weights; bf16 weights, 8 bits, miss the atol 2e-3 bar on ~1e-5 of the elements), so bf16 grad_output enters
+    // the product as fp16 after a power-of-two scaling per band: go' = go * 2^(127 - e_ref), e_ref = biased exponent of
+    // the band's largest |go|.  Exact for every value within 2^-14 of that maximum, smaller ones lose low bits
+    // (absolute error below 2^-24 of the band's largest gradient).
+    int e_ref = 127;
+    {
+        const uint32_t gos_s = gos_base + gl * kGoGrpB + px * kGoRowB + 16 * h;
+        if constexpr (kScaled) {
+            const uint4 s0 = *reinterpret_cast<const uint4 *>(smax), s1 = *reinterpret_cast<const uint4 *>(smax + 4);
+            const uint32_t mx = max(max(max(s0.x, s0.y), max(s0.z, s0.w)), max(max(s1.x, s1.y), max(s1.z, s1.w)));
+            e_ref = min(max((int)(mx >> 7), 1), 253);
+            const float sc = __uint_as_float((uint32_t)(254 - e_ref) << 23);
+            const uint32_t w[4] = {g_own.x, g_own.y, g_own.z, g_own.w};
+            uint32_t r[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float2 f = imat::unpack2f<T>(w[c]);
+                r[c] = imat::pack2<__half>(f.x * sc, f.y * sc);
+            }
+            sts128(gos_s, make_uint4(r[0], r[1], r[2], r[3]));
+        } else {
+            sts128(gos_s, g_own);
+        }
+    }
+    uint32_t slowmask = 0u;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-        // kernel-grid coordinates of point p = (k == 4 ? 8 : 4h + k): i = p / 3 (kernel_w), j = p % 3 (cuh:253-254)
-        const int pi = k == 4 ? 2 : (h ? (4 + k) / 3 : k / 3), pj = k == 4 ? 2 : (h ? (4 + k) % 3 : k % 3);
         const float2 o = imat::unpack2f<T>(roff[k]);
-        const LeanPoint t = imat::locate_lean(pg, p0h_, p0w_, (float)pi, (float)pj, o.x, o.y);
+        const LeanPoint t = imat::locate_lean(pg, p0h_, p0w_, (float)slot_i(k, h), (float)slot_j(k, h), o.x, o.y);
         const unsigned u = (unsigned)(t.w_low - wx0), vb = (unsigned)(t.h_low - by0);
         const bool inband = u <= (unsigned)(kWinW - 2) && vb <= (unsigned)(kBandRows - 2);
         const bool fast = t.inside && inband && valid;
         slowmask |= (t.inside && !inband && valid ? 1u : 0u) << k;  // same for both lanes of the pair
         const uint32_t e = fast ? vb * kWinW + u : 0u;
-        const uint32_t a = band_s + e * kCellB;
-        float d0, d1, d2, d3;
-        if (k < 4) {
-            d0 = corner_dot16<T>(a + own16, a + oth16, g_own, g_oth);
-            d1 = corner_dot16<T>(a + own16 + kCellB, a + oth16 + kCellB, g_own, g_oth);
-            d2 = corner_dot16<T>(a + own16 + kWinW * kCellB, a + oth16 + kWinW * kCellB, g_own, g_oth);
-            d3 = corner_dot16<T>(a + own16 + kWinW * kCellB + kCellB, a + oth16 + kWinW * kCellB + kCellB, g_own, g_oth);
-        } else {  // point 8: the two lanes take 8 channels each and meet
-            d0 = corner_dot8<T>(a + own16, g_own);
-            d1 = corner_dot8<T>(a + own16 + kCellB, g_own);
-            d2 = corner_dot8<T>(a + own16 + kWinW * kCellB, g_own);
-            d3 = corner_dot8<T>(a + own16 + kWinW * kCellB + kCellB, g_own);
-            d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
-            d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
-            d2 += __shfl_xor_sync(0xffffffffu, d2, 1);
-            d3 += __shfl_xor_sync(0xffffffffu, d3, 1);
-        }
-        const float lh = t.lh, lw = t.lw;
-        const float hh = sub_rn(1.f, lh), hw = sub_rn(1.f, lw);
-        const float s_m = (hh * hw) * d0 + (hh * lw) * d1 + (lh * hw) * d2 + (lh * lw) * d3;
-        const float s_w = hh * (d1 - d0) + lh * (d3 - d2);
-        const float s_h = hw * (d2 - d0) + lw * (d3 - d1);
-        const float sm = q.scale * mk[k];
-        res_off[k] = fast ? imat::pack2<T>(sm * s_w, sm * s_h) : 0u;
-        res_m[k] = fast ? s_m : 0.f;
-        // interpolation-matrix pairs (top: band row vb, bottom: vb + 1).  The lane adds the pair whose row has
-        // parity h and hands the other one to its partner, so neither ever writes a row of the other's.
-        const float hm = hh * mk[k], lm = lh * mk[k];
-        const uint32_t top = imat::pack2<__half>(hm * hw, hm * lw), bot = imat::pack2<__half>(lm * hw, lm * lw);
+        // interpolation-matrix pairs (top: band row vb, bottom: vb + 1).  The lane adds the pair whose row has parity h
+        // and hands the other one to its partner, so neither ever writes a row of the other's.  (Point 8 is known to
+        // both lanes: each adds the row of its parity.)
+        const float hh = sub_rn(1.f, t.lh), hw = sub_rn(1.f, t.lw);
+        const float hm = hh * mk[k], lm = t.lh * mk[k];
+        const uint32_t top = imat::pack2<__half>(hm * hw, hm * t.lw), bot = imat::pack2<__half>(lm * hw, lm * t.lw);
         const bool keep_top = ((vb & 1u) == (unsigned)h);
         wm_add(row_s, keep_top ? e : e + kWinW, keep_top ? top : bot, fast);
         if (k < 4) {
@@ -396,118 +514,81 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
             wm_add(row_s, re & 255u, rw, (re & 256u) != 0u);
         }
     }
-
-    // ---- rare: points inside the map but outside the band's window (|offset * scale| >= 3 px)
-    if (slowmask) {
+    if (slowmask) {  // rare: points inside the map but outside the band's window (|offset * scale| >= 3 px)
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
             if (!((slowmask >> k) & 1u)) continue;
-            const int pi = k == 4 ? 2 : (h ? (4 + k) / 3 : k / 3), pj = k == 4 ? 2 : (h ? (4 + k) % 3 : k % 3);
-            const float4 d = bwd_point_slow<T>(pg, p0h_, p0w_, pi, pj, roff[k], mk[k], g_own, g_oth, k < 4 ? 2 : 1,
-                                               img_g + 8 * h, gin_g + 8 * h, h ? -8 : 8, q.C);
-            const float2 o = imat::unpack2f<T>(roff[k]);
-            const LeanPoint t = imat::locate_lean(pg, p0h_, p0w_, (float)pi, (float)pj, o.x, o.y);
-            const float lh = t.lh, lw = t.lw;
-            const float hh = sub_rn(1.f, lh), hw = sub_rn(1.f, lw);
-            const float s_m = (hh * hw) * d.x + (hh * lw) * d.y + (lh * hw) * d.z + (lh * lw) * d.w;
-            const float s_w = hh * (d.y - d.x) + lh * (d.w - d.z);
-            const float s_h = hw * (d.z - d.x) + lw * (d.w - d.y);
-            const float sm = q.scale * mk[k];
-            res_off[k] = imat::pack2<T>(sm * s_w, sm * s_h);
-            res_m[k] = s_m;
+            scatter_point_slow<T>(pg, p0h_, p0w_, slot_i(k, h), slot_j(k, h), roff[k], mk[k], g_own,
+                                  reinterpret_cast<const T *>(gp + (h ^ 1)), k < 4 ? 2 : 1, gin_g + 8 * h, h ? -8 : 8, q.C);
         }
     }
+    __syncthreads();  // barrier B: Wm and Gos of the band are complete
 
-    // ---- grad_offset / grad_mask (cuh:144-146); fused softmax: dl_p = m_p (gm_p - sum_q m_q gm_q)
-    if (LOGITS) {
-        float dot = 0.f;
+    // ---- tensor cores: GW[band row][cell][ch] = Wm^T * go.  Warp = (group, parity of its band rows); m-tile = one band
+    // row (16 cells), K = the band's 32 pixels (two k-steps), N = the group's 16 channels (two n-tiles).
+    const int mg = warp & 3, qpar = warp >> 2;
+    const uint32_t wm_g = wm_s + mg * kGrpB;
+    float gw[kBandRows / 2][2][4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) dot = fmaf(mk[k], res_m[k], dot);
-        if (h == 0) dot = fmaf(mk[4], res_m[4], dot);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-#pragma unroll
-        for (int k = 0; k < 5; ++k) res_m[k] = mk[k] * (res_m[k] - dot);
-    }
-    if (valid) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            qo[4 * h + k] = res_off[k];
-            qm[4 * h + k] = (unsigned short)(imat::pack2<T>(res_m[k], 0.f) & 0xffffu);
-        }
-        if (h == 0) {
-            qo[8] = res_off[4];
-            qm[8] = (unsigned short)(imat::pack2<T>(res_m[4], 0.f) & 0xffffu);
-        }
-    }
-    __syncthreads();  // barrier B: Wm and Gos of the tile are complete
-
-    // ---- tensor cores: GW[window row][cell][ch] = sum over the tile's pixels of Wm^T * go.  Warp = (group, row quarter):
-    // window rows R = rq + 4j.  Row R takes band 0's band row R (R <= 11) and band 1's band row R - 4 (R >= 4); per band
-    // two k-steps of 16 pixels; m-tile = one window row (16 cells), N = the group's 16 channels (two n-tiles).
-    const int mg = warp & 1, rq = warp >> 1;
-    float gw[4][2][4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int i = 0; i < kBandRows / 2; ++i)
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) gw[j][nt][c] = 0.f;
+            for (int c = 0; c < 4; ++c) gw[i][nt][c] = 0.f;
     {
         const int jm = lane >> 3, jr = lane & 7;
-        const uint32_t go_g = imat::smem_u32(Gos) + mg * kGoGrpB;
+        const uint32_t go_g = gos_base + mg * kGoGrpB;
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            if (b == 1 && tc.ty * kTile + 4 >= q.Ho) break;  // the second band lies below the map (CTA-uniform)
-            const uint32_t wm_g = imat::smem_u32(Wm) + (b * kGrp + mg) * kGrpB;
+        for (int s = 0; s < 2; ++s) {
+            // B = go [16 px x 16 ch]: matrix jm = (px 8(jm & 1).., ch 8(jm >> 1)..)
+            uint32_t b00, b01, b10, b11;
+            imat::ldmatrix_x4_trans(b00, b01, b10, b11, go_g + (16 * s + 8 * (jm & 1) + jr) * kGoRowB + (jm >> 1) * 16);
+            // A = Wm^T [16 cells x 16 px]: matrix jm = (cells 8(jm & 1).., px 8(jm >> 1)..)
+            const uint32_t abase = wm_g + (16 * s + 8 * (jm >> 1) + jr) * kRowB + (jm & 1) * 16 + qpar * (kWinW * 2);
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                // B = go [16 px x 16 ch]: matrix jm = (px 8(jm & 1).., ch 8(jm >> 1)..)
-                uint32_t b00, b01, b10, b11;
-                imat::ldmatrix_x4_trans(b00, b01, b10, b11, go_g + (32 * b + 16 * s + 8 * (jm & 1) + jr) * kGoRowB + (jm >> 1) * 16);
-                // A = Wm^T [16 cells x 16 px]: matrix jm = (cells 8(jm & 1).., px 8(jm >> 1)..)
-                const uint32_t abase = wm_g + (16 * s + 8 * (jm >> 1) + jr) * kRowB + (jm & 1) * 16 + (rq - 4 * b) * (kWinW * 2);
-#pragma unroll
-                for (int j = b; j < 3 + b; ++j) {  // window row R = rq + 4j, band row R - 4b in [0, 12)
-                    uint32_t a0, a1, a2, a3;
-                    imat::ldmatrix_x4_trans(a0, a1, a2, a3, abase + j * (4 * kWinW * 2));
-                    imat::mma_16816<__half>(gw[j][0], a0, a1, a2, a3, b00, b01);
-                    imat::mma_16816<__half>(gw[j][1], a0, a1, a2, a3, b10, b11);
-                }
+            for (int i = 0; i < kBandRows / 2; ++i) {  // band row rr = qpar + 2i
+                uint32_t a0, a1, a2, a3;
+                imat::ldmatrix_x4_trans(a0, a1, a2, a3, abase + i * (2 * kWinW * 2));
+                imat::mma_16816<__half>(gw[i][0], a0, a1, a2, a3, b00, b01);
+                imat::mma_16816<__half>(gw[i][1], a0, a1, a2, a3, b10, b11);
             }
         }
     }
 
-    // ---- flush: the warp's 4 window rows x 16 cells x 16 channels leave as packed 16-bit vector reductions.
-    // Fragment (c0, c1) / (c2, c3) of n-tile nt = channels 8nt + 2tq, +1 of cells gID / gID + 8; a 4x4 transpose inside
-    // the quad gives every lane the 8 channels of ONE (cell, n-tile): lane tq <- cell gID + 8 (tq & 1), n-tile tq >> 1.
+    // ---- flush: the warp's 6 band rows x 16 cells x 16 channels leave as packed 16-bit vector reductions.  The mma
+    // fragments (c0, c1) / (c2, c3) of n-tile nt = channels 8nt + 2tq, +1 of cells gID / gID + 8, packed to the storage
+    // dtype, are exactly stmatrix fragments: one stmatrix.x4 lays a band row out as [16 cells][16 channels] in shared
+    // memory — in the Wm rows of this warp's own parity, which nobody else reads (cell c -> pixel row c, band row slot
+    // qpar + 2i: 400-byte stride, conflict-free) — and every lane reads back the 8 channels of ONE (cell, half).
+    __syncwarp();
     {
-        const int gID = lane >> 2, tq = lane & 3;
-        const int cell = gID + 8 * (tq & 1), nt = tq >> 1;
-        const int ix = wx0 + cell;
-        const bool col_ok = (unsigned)ix < (unsigned)q.W;
-        T *dst0 = gin + img_off + mg * 16 + nt * 8;
+        const int jm = lane >> 3, jr = lane & 7;
+        const uint32_t st_addr = wm_g + (jr + 8 * (jm & 1)) * kRowB + qpar * (kWinW * 2) + (jm >> 1) * 16;
         const float unscale = __uint_as_float((uint32_t)e_ref << 23);  // 2^(e_ref - 127), bf16 storage only
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int iy = wy0 + rq + 4 * j;
+        for (int i = 0; i < kBandRows / 2; ++i) {
             if constexpr (kScaled) {
 #pragma unroll
                 for (int n2 = 0; n2 < 2; ++n2)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) gw[j][n2][c] *= unscale;
+                    for (int c = 0; c < 4; ++c) gw[i][n2][c] *= unscale;
             }
-            const uint32_t wd[4] = {imat::pack2<T>(gw[j][0][0], gw[j][0][1]), imat::pack2<T>(gw[j][0][2], gw[j][0][3]),
-                                    imat::pack2<T>(gw[j][1][0], gw[j][1][1]), imat::pack2<T>(gw[j][1][2], gw[j][1][3])};
-            uint32_t v[4];
-            v[0] = sel4(wd, tq);
+            stmatrix_x4(st_addr + i * (2 * kWinW * 2), imat::pack2<T>(gw[i][0][0], gw[i][0][1]), imat::pack2<T>(gw[i][0][2], gw[i][0][3]),
+                        imat::pack2<T>(gw[i][1][0], gw[i][1][1]), imat::pack2<T>(gw[i][1][2], gw[i][1][3]));
+        }
+        __syncwarp();
+        const int cell = lane >> 1, half = lane & 1;
+        const int ix = wx0 + cell;
+        const bool col_ok = (unsigned)ix < (unsigned)q.W;
+        const uint32_t ld_addr = wm_g + cell * kRowB + qpar * (kWinW * 2) + half * 16;
+        T *dst0 = gin + img_off + mg * 16 + half * 8 + (size_t)ix * q.C;
 #pragma unroll
-            for (int r = 1; r < 4; ++r) v[r] = __shfl_xor_sync(0xffffffffu, sel4(wd, tq ^ r), r);
-            // v[r] came from lane tq ^ r = channels 2 (tq ^ r), +1 of this lane's (cell, n-tile)
-            uint4 o;
-            o.x = sel4(v, tq); o.y = sel4(v, tq ^ 1); o.z = sel4(v, tq ^ 2); o.w = sel4(v, tq ^ 3);
+        for (int i = 0; i < kBandRows / 2; ++i) {
+            const int iy = by0 + qpar + 2 * i;
+            const uint4 o = imat::lds128(ld_addr + i * (2 * kWinW * 2));
             const bool nz = ((o.x | o.y | o.z | o.w) & 0x7fff7fffu) != 0u;
             const bool ok = col_ok && (unsigned)iy < (unsigned)q.H && nz;
-            red_add_v4<T>(ok ? dst0 + ((size_t)iy * q.W + ix) * q.C : gin, o, ok);
+            red_add_v4<T>(ok ? dst0 + (size_t)iy * q.W * q.C : gin, o, ok);
         }
     }
 }
