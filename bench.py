@@ -32,6 +32,10 @@ SITES = {  # name: (N, H, W, G, gc)
     "P3": (16, 80, 80, 8, 16),
     "P4": (16, 40, 40, 16, 16),
     "P5": (16, 20, 20, 32, 16),
+    # BASELINE configs[4]: 1280x1280 inference, batch 32 over 8 GPUs = 4 images per GPU (--infer)
+    "I3": (4, 160, 160, 8, 16),
+    "I4": (4, 80, 80, 16, 16),
+    "I5": (4, 40, 40, 32, 16),
 }
 KGEO = dict(kh=3, kw=3, sh=1, sw=1, ph=1, pw=1, dh=1, dw=1, scale=1.0)
 N_BUFFER_SETS = 4  # inputs rotate over 4 sets (~1.7 GB) so every step starts L2-cold
@@ -58,9 +62,11 @@ def algo_bytes(site, e, N=None):
 
 
 def ncu_traffic(op):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the op's main kernel, per launch, from the
-    committed ncu capture (profiles/r01_ncu_traffic.json); None when that op was not captured."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    """dram__bytes_read.sum + dram__bytes_write.sum summed over EVERY kernel the op launches (16-bit backward:
+    zero_fill_kernel + bwd_win_kernel), per call, from the committed ncu capture of this same command
+    (profiles/r02_ncu_traffic.json, written by tools/ncu_traffic.py from profiles/r02_ncu_launches.csv);
+    None when that op was not captured.  A constant of the capture, not something this run measured."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
     try:
         with open(p) as f:
             t = json.load(f).get(op)
@@ -173,7 +179,7 @@ class Workload:
         # zero_select_kernel + bwd_imat_kernel + bwd_vec_kernel (returns at once unless the selector picked
         # it) + cast_ws_kernel; with a family forced by DCNV3_B200_BWD: backward kernel + cast (+ a driver memset).
         forced = os.environ.get("DCNV3_B200_BWD") in ("vec", "imat", "tile")
-        bwd = (2 if forced else 4) if (lowp and accum == "opmath") else 1  # 'tile': bwd_win_kernel (+ a driver memset)
+        bwd = (2 if forced else 4) if (lowp and accum == "opmath") else (2 if lowp and accum == "tile" else 1)  # 'tile': zero_fill_kernel + bwd_win_kernel
         self.launches_per_step = len(sites) * (1 + bwd)
 
     def fwd(self, b, st):
@@ -291,26 +297,50 @@ def time_e2e(wl, steps, warmup, dist):
 # bf16 autocast, CE + 0.5 Dice, SGD-nesterov; DDP (NCCL) gradient all-reduce when world > 1.
 # Every step copies its images/labels from pinned host memory and reads the loss back.
 # ----------------------------------------------------------------------------------------------
-def time_seg(dev, dist, world, steps, warmup, batch, model_name, channels_last=True):
+def pinned_like(t, channels_last):
+    """Pinned host copy of an NCHW tensor; channels_last = stored HWC (what an image decoder produces), so that the
+    upload into a channels_last device tensor is one plain DMA."""
+    if not channels_last:
+        return t.pin_memory()
+    n, c, h, w = t.shape
+    buf = torch.empty(n, h, w, c, dtype=t.dtype).pin_memory().permute(0, 3, 1, 2)
+    buf.copy_(t)
+    return buf
+
+
+def seg_model(dev, model_name, channels_last=True, fused_softmax=False):
     from yolo_dual_b200 import seg
-    torch.manual_seed(0)
-    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(0)  # same initial weights on every rank
     cfg = {"yolov5seg": seg.YOLOV5_SEG, "yolov8seg": seg.YOLOV8_SEG}[model_name]
-    model = seg.SegModel(cfg, dcn="dcnv3").to(dev)
+    model = seg.SegModel(cfg, dcn="dcnv3", fused_softmax=fused_softmax).to(dev)
     if channels_last:  # NHWC activations: the NCHW<->NHWC permutes around every DCNv3 become views
         model = model.to(memory_format=torch.channels_last)
+    return model
+
+
+def time_seg(dev, dist, world, steps, warmup, batch, model_name, channels_last=True, ddp_opts=None, graph=False):
+    from yolo_dual_b200 import seg
+    torch.backends.cudnn.benchmark = True
+    ddp_opts = ddp_opts or {}
+    model = seg_model(dev, model_name, channels_last)
     crit = seg.SegmentationLoss(12, class_weights=seg.CAMVID_CLASS_WEIGHTS).to(dev)
-    ddp = seg.wrap_ddp(model, dev)
+    side = torch.cuda.Stream(device=dev)  # torch's CUDA-graph notes: build DDP on a side stream when it will be captured
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ddp = seg.wrap_ddp(model, dev, **ddp_opts)
+    torch.cuda.current_stream().wait_stream(side)
     opt = seg.smart_optimizer(ddp)
     ddp.train()
     g = torch.Generator().manual_seed(1 + (dist.get_rank() if dist is not None else 0))
-    imgs_h = torch.randn(batch, 3, 640, 640, generator=g).pin_memory()
+    imgs_h = pinned_like(torch.randn(batch, 3, 640, 640, generator=g), channels_last)
     lab_h = torch.randint(0, 12, (batch, 640, 640), generator=g).pin_memory()
     # the data-loader side of the loop: batch k+1 is uploaded on a copy stream while step k computes (two device
     # slots), and the loss of step k is read back into pinned memory and looked at one step later
     copy_st = torch.cuda.Stream(device=dev)
     slots = [(torch.empty(batch, 3, 640, 640, device=dev), torch.empty(batch, 640, 640, dtype=torch.int64, device=dev))
              for _ in range(2)]
+    if channels_last:
+        slots = [(a.contiguous(memory_format=torch.channels_last), b) for a, b in slots]
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
     loss_h = torch.zeros(2, dtype=torch.float32).pin_memory()
@@ -328,15 +358,30 @@ def time_seg(dev, dist, world, steps, warmup, batch, model_name, channels_last=T
         ev.record()
     upload(0)
 
+    graphed, graph_note = None, "off"
+    if graph:
+        try:
+            def batches():
+                while True:
+                    yield slots[0]
+            torch.cuda.current_stream().wait_event(ready[0])
+            graphed = seg.GraphedTrainStep(ddp, crit, opt, batches(), autocast_dtype=torch.bfloat16)
+            graph_note = "whole step (forward, loss, backward + DDP all-reduce, SGD) replayed as one CUDA graph"
+        except Exception as ex:  # capture is an optimisation: report and run eagerly
+            if world > 1:
+                raise
+            graphed, graph_note = None, "capture failed, eager: " + repr(ex)[:200]
+
     def one():
         k = state["k"]
         upload(k + 1)
         cur = torch.cuda.current_stream()
         cur.wait_event(ready[k % 2])
         imgs, lab = slots[k % 2]
-        if channels_last:
-            imgs = imgs.contiguous(memory_format=torch.channels_last)
-        loss, _ = seg.train_step(ddp, crit, opt, imgs, lab, autocast_dtype=torch.bfloat16)
+        if graphed is not None:
+            loss, _ = graphed(imgs, lab)
+        else:
+            loss, _ = seg.train_step(ddp, crit, opt, imgs, lab, autocast_dtype=torch.bfloat16)
         freed[k % 2].record(cur)
         loss_h[k % 2].copy_(loss, non_blocking=True)   # D2H: the step's result
         loss_ev[k % 2].record(cur)
@@ -366,17 +411,161 @@ def time_seg(dev, dist, world, steps, warmup, batch, model_name, channels_last=T
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     n_params = sum(p.numel() for p in model.parameters())
-    return {"model": f"{model_name} with C3_DCNV3 at P3/P4/P5 (DCNv3 C=128/256/512, group_channels 16)",
-            "imgs_per_s": batch * world * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps,
-            "batch_per_gpu": batch, "global_batch": batch * world, "image": "640x640", "autocast": "bf16",
-            "memory_format": "channels_last" if channels_last else "contiguous",
-            "optimizer": "SGD nesterov 3 groups", "params": n_params, "loss_last": last,
-            "h2d_bytes_per_step": imgs_h.numel() * 4 + lab_h.numel() * 8, "d2h_bytes_per_step": 4,
-            "input_pipeline": "pinned host batch uploaded every step on a copy stream, one step ahead; loss read back "
-                              "into pinned memory every step and inspected one step later",
-            "fused": "deferred last Upsample, fused CE+Dice loss, fused BN+SiLU, NHWC resize kernels (this repo's "
-                     "segloss_b200 / bnact_b200 / resize_b200)",
-            "data_parallel": f"DDP x{world} (NCCL all-reduce of {n_params * 4 / 1e6:.1f} MB fp32 grads)" if world > 1 else "single GPU"}
+    comp = ddp_opts.get("grad_compress") or "fp32"
+    res = {"model": f"{model_name} with C3_DCNV3 at P3/P4/P5 (DCNv3 C=128/256/512, group_channels 16)",
+           "imgs_per_s": batch * world * steps / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps,
+           "batch_per_gpu": batch, "global_batch": batch * world, "image": "640x640", "autocast": "bf16",
+           "memory_format": "channels_last" if channels_last else "contiguous",
+           "optimizer": "SGD nesterov 3 groups", "params": n_params, "loss_last": last,
+           "h2d_bytes_per_step": imgs_h.numel() * 4 + lab_h.numel() * 8, "d2h_bytes_per_step": 4,
+           "input_pipeline": "pinned host batch uploaded every step on a copy stream, one step ahead; loss read back "
+                             "into pinned memory every step and inspected one step later",
+           "fused": "deferred last Upsample, fused CE+Dice loss, fused BN+SiLU, NHWC resize kernels (this repo's "
+                    "segloss_b200 / bnact_b200 / resize_b200)",
+           "cuda_graph": graph_note,
+           "data_parallel": (f"DDP x{world} (NCCL all-reduce of {n_params * (2 if comp == 'bf16' else 4) / 1e6:.1f} MB {comp} grads, "
+                             f"bucket_cap_mb {ddp_opts.get('bucket_cap_mb') or 25}, first bucket {ddp_opts.get('first_bucket_mb') or 1} MB)")
+           if world > 1 else "single GPU"}
+    del graphed, ddp, opt, model, slots
+    torch.cuda.empty_cache()
+    return res
+
+
+def dp_grad_check(dev, dist, world, model_name, batch, ddp_opts=None):
+    """SURVEY §8(e)'s correctness test on the real thing: the gradients DDP leaves on every rank after ONE backward over
+    the rank's shard (the CUDA DCNv3 op, bf16 autocast, fused loss, NCCL all-reduce) against rank 0's own
+    recomputation over the concatenated global batch — shard by shard, gradients accumulated and divided by the
+    world size, which is what data parallelism promises (the class-weighted CE normalises per shard, so it is the
+    shard losses that are averaged, reference and here alike).  BatchNorm in eval mode: batch statistics are
+    per-shard by design (no SyncBN, seg_diceloss_yolov5.py:991).  Returns max over parameters of
+    max|g_ddp - g_ref| / max|g_ref|."""
+    from yolo_dual_b200 import seg
+    model = seg_model(dev, model_name)
+    # non-zero DCNv3 heads: a fresh layer has zero offset / mask heads and would sample the regular grid only
+    gen = torch.Generator(device="cpu").manual_seed(7)
+    with torch.no_grad():
+        for _, m in model.dcn_sites():
+            m.offset.weight.copy_(torch.randn(m.offset.weight.shape, generator=gen) * 0.05)
+            m.mask.weight.copy_(torch.randn(m.mask.weight.shape, generator=gen) * 0.05)
+    crit = seg.SegmentationLoss(12, class_weights=seg.CAMVID_CLASS_WEIGHTS).to(dev)
+    model.eval()
+    ddp = seg.wrap_ddp(model, dev, **(ddp_opts or {}))
+    rank = dist.get_rank()
+    g = torch.Generator().manual_seed(100 + rank)
+    imgs = torch.randn(batch, 3, 640, 640, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+    lab = torch.randint(0, 12, (batch, 640, 640), generator=g).to(dev)
+    loss, _ = seg.forward_loss(ddp, crit, imgs, lab, torch.bfloat16)
+    loss.backward()
+    torch.cuda.synchronize()
+    got = {n: p.grad.detach().float().clone() for n, p in model.named_parameters() if p.grad is not None}
+    all_imgs = [torch.empty_like(imgs) for _ in range(world)]
+    all_lab = [torch.empty_like(lab) for _ in range(world)]
+    dist.all_gather(all_imgs, imgs.contiguous())
+    dist.all_gather(all_lab, lab)
+    out = None
+    if rank == 0:
+        model.zero_grad(set_to_none=True)
+        for xi, yi in zip(all_imgs, all_lab):
+            l, _ = seg.forward_loss(model, crit, xi.contiguous(memory_format=torch.channels_last), yi, torch.bfloat16)
+            (l / world).backward()
+        worst, name = 0.0, ""
+        for n, p in model.named_parameters():
+            if p.grad is None or n not in got:
+                continue
+            ref = p.grad.detach().float()
+            rel = float((got[n] - ref).abs().max() / ref.abs().max().clamp_min(1e-20))
+            if rel > worst:
+                worst, name = rel, n
+        out = {"dp_grad_max_rel": worst, "worst_param": name, "params_compared": len(got),
+               "what": f"DDP x{world} gradients ({model_name}, {batch} images per rank, bf16 autocast, CUDA DCNv3 op, BN eval) vs rank 0's "
+                       f"shard-by-shard recomputation on the gathered global batch"}
+    dist.barrier()
+    del ddp, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def trainer_smoke(dev, dist, world):
+    """`Trainer` under NCCL: nominal-batch accumulation with DDP.no_sync on the non-boundary
+    micro-steps, EMA, checkpoint + resume, with the real DCNv3 op.  Returns a short status dict (rank 0)."""
+    import tempfile
+    from yolo_dual_b200 import seg
+    from yolo_dual_b200.trainer import Trainer
+    model = seg_model(dev, "yolov5seg")
+    crit = seg.SegmentationLoss(12, class_weights=seg.CAMVID_CLASS_WEIGHTS).to(dev)
+    t = Trainer(model, crit, batch_size=16 * world, epochs=3, autocast_dtype=torch.bfloat16, device=dev)
+    g = torch.Generator().manual_seed(5 + dist.get_rank())
+    x = torch.randn(4, 3, 640, 640, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 12, (4, 640, 640), generator=g).to(dev)
+    stepped = []
+    for i in range(2 * t.accumulate):
+        loss, _, st = t.micro_step(x, y)
+        stepped.append(bool(st))
+    t.end_epoch(fitness=0.5)
+    ok_sync = True
+    for p in model.parameters():  # after an optimizer step every rank must hold the same weights
+        ref = p.detach().clone()
+        dist.broadcast(ref, 0)
+        ok_sync &= bool(torch.equal(ref, p.detach()))
+    out = None
+    if dist.get_rank() == 0:
+        with tempfile.TemporaryDirectory() as d:
+            t.save(os.path.join(d, "last.pt"), os.path.join(d, "best.pt"), is_best=True)
+            ck = torch.load(os.path.join(d, "last.pt"), weights_only=False)
+        out = {"accumulate": t.accumulate, "optimizer_steps": sum(stepped), "micro_steps": len(stepped),
+               "ema_updates": t.ema.updates, "weights_identical_across_ranks": ok_sync, "ckpt_epoch": ck["epoch"],
+               "loss_finite": bool(torch.isfinite(loss)), "world": world}
+    dist.barrier()
+    del t, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def time_infer(dev, dist, world, steps, warmup, batch):
+    """BASELINE configs[4]: C3-DCN seg inference at 1280x1280, fp16, fused mask-softmax, `batch` images per GPU (batch
+    32 sharded over 8 GPUs = 4).  Every step uploads its images from pinned host memory and reads the class map
+    back; images/s over all ranks."""
+    from yolo_dual_b200 import seg
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(0)
+    model = seg.SegModel(seg.YOLOV5_SEG, dcn="dcnv3", fused_softmax=True, img_size=(1280, 1280)).to(dev)
+    model = model.half().eval().to(memory_format=torch.channels_last)
+    g = torch.Generator().manual_seed(3 + (dist.get_rank() if dist is not None else 0))
+    imgs_h = pinned_like(torch.randn(batch, 3, 1280, 1280, generator=g).half(), True)
+    out_h = torch.empty(batch, 1280, 1280, dtype=torch.uint8).pin_memory()
+    x = torch.empty(batch, 3, 1280, 1280, device=dev, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+
+    def one():
+        x.copy_(imgs_h, non_blocking=True)
+        with torch.no_grad():
+            prob = model(x)
+            out_h.copy_(prob.argmax(1).to(torch.uint8), non_blocking=True)
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        dist.barrier()
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    del model
+    torch.cuda.empty_cache()
+    return {"workload": "configs[4]: yolov5seg with C3_DCNV3, 1280x1280, fp16, fused mask-softmax (mask logits go straight to the "
+                        "kernels), eval", "imgs_per_s": batch * world * steps / (ms * 1e-3), "ms_per_step": ms / steps,
+            "batch_per_gpu": batch, "global_batch": batch * world, "steps": steps,
+            "h2d_bytes_per_step": imgs_h.numel() * 2, "d2h_bytes_per_step": out_h.numel(),
+            "classes_seen": int(out_h.max()) + 1}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -440,14 +629,15 @@ def cpu_tensors(sites):
     return {s: make_inputs(*SITES[s], dist="unit", seed=i) for i, s in enumerate(sites)}
 
 
-def cpu_run(sites, e_workload, steps, warmup, budget_s):
+CPU_SAMPLE_IMAGES = 2  # fixed: the CPU arm always runs the same 2 of the 16 images, so GPU/CPU ratios compare run to run
+
+
+def cpu_run(sites, e_workload, steps, warmup):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     tens = cpu_tensors(sites)
-    n_img = SITES[sites[0]][0]
-    t0 = time.perf_counter(); cpu_step(sites, 1, tens); t1 = time.perf_counter() - t0  # also a warm-up
-    while n_img > 1 and t1 * n_img * (steps + warmup) > budget_s:
-        n_img //= 2
+    n_img = min(CPU_SAMPLE_IMAGES, SITES[sites[0]][0])
+    cpu_step(sites, 1, tens)  # page-in / thread-pool warm-up
     for _ in range(warmup):
         cpu_step(sites, n_img, tens)
     ts = []
@@ -456,7 +646,7 @@ def cpu_run(sites, e_workload, steps, warmup, budget_s):
     total = sum(ts)
     by = sum(sum(algo_bytes(s, e_workload, N=n_img)) for s in sites)
     gbps = by * steps / total / 1e9
-    sample = (f"{steps} steps of fwd+bwd over {'+'.join(sites)} on {n_img} of {SITES[sites[0]][0]} images, fp32 "
+    sample = (f"{steps} steps of fwd+bwd over {'+'.join(sites)} on {n_img} of {SITES[sites[0]][0]} images (fixed sample), fp32 "
               f"torch restatement of dcnv3_core_pytorch, {torch.get_num_threads()} threads; GB/s counts the "
               f"workload's storage-dtype algorithmic bytes so the GPU/CPU ratio is a time ratio")
     return gbps, total / steps * 1e3, cores, sample, n_img
@@ -493,6 +683,15 @@ def main():
                     help="fixed global batch split over the GPUs (strong scaling, BASELINE configs[3]: 64)")
     ap.add_argument("--seg-model", default="yolov5seg", choices=["yolov5seg", "yolov8seg"])
     ap.add_argument("--seg-nchw", action="store_true", help="keep NCHW activations in the seg model")
+    ap.add_argument("--no-seg-strong", action="store_true", help="skip the configs[3] line (yolov8seg, global batch 64)")
+    ap.add_argument("--seg-graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the training step as one CUDA graph (auto: on)")
+    ap.add_argument("--ddp-compress", default="bf16", choices=["bf16", "none"], help="gradient all-reduce dtype")
+    ap.add_argument("--ddp-bucket-mb", type=float, default=0.0, help="DDP bucket_cap_mb (0: torch's 25)")
+    ap.add_argument("--ddp-first-bucket-mb", type=float, default=0.0, help="DDP first bucket (0: torch's 1)")
+    ap.add_argument("--no-dp-check", action="store_true")
+    ap.add_argument("--no-infer", action="store_true", help="skip the configs[4] inference line")
+    ap.add_argument("--infer-steps", type=int, default=10)
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3
@@ -515,7 +714,10 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        gbps, ms, cores, sample, n_img = cpu_run(sites, e, a.steps, a.warmup, budget_s=150.0)
+        # bounded: ~45 ms per image and site set on 16 cores -> the arm caps its own step count so that any
+        # --steps / --warmup the driver passes ends within a few minutes (the line reports the steps it ran)
+        a.steps, a.warmup = min(a.steps, 20), min(a.warmup, 3)
+        gbps, ms, cores, sample, n_img = cpu_run(sites, e, a.steps, a.warmup)
         print(file=out_stream, flush=True, *[json.dumps({
             "impl": "reference", "metric": METRIC, "value": gbps, "unit": "GB/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -551,19 +753,66 @@ def main():
                "api": "yolo_dual_b200.host.HostPipeline -> DCNv3Function.apply + autograd on pinned host tensors; "
                       "H2D of input/offset/mask/grad_out and D2H of output + 3 grads every step (one pinned arena per direction), copies and kernels "
                       "on three streams, three steps in flight"}
-    seg_res = None
+    seg_res, seg_detail, infer = None, None, None
     if not a.no_seg:
         del wl
         torch.cuda.empty_cache()
+        ddp_opts = {"grad_compress": None if a.ddp_compress == "none" else a.ddp_compress,
+                    "bucket_cap_mb": a.ddp_bucket_mb or None, "first_bucket_mb": a.ddp_first_bucket_mb or None}
+        graph = a.seg_graph != "off"
+        seg_res, seg_detail = {}, {}
+
+        def short(r, scaling):
+            return {"model": r["model"].split(" ")[0], "imgs_per_s": r["imgs_per_s"], "ms_per_step": r["ms_per_step"],
+                    "batch_per_gpu": r["batch_per_gpu"], "global_batch": r["global_batch"], "scaling": scaling,
+                    "cuda_graph": not r["cuda_graph"].startswith(("off", "capture failed"))}
         try:
+            if world > 1 and not a.no_dp_check:
+                chk = dp_grad_check(dev, dist, world, "yolov5seg", 4, ddp_opts)
+                tr = trainer_smoke(dev, dist, world)
+                if rank == 0:
+                    seg_detail["dp_check"], seg_detail["trainer_nccl"] = chk, tr
+                    seg_res["dp_grad_max_rel"] = chk["dp_grad_max_rel"]
+                    seg_res["trainer_nccl"] = "ok" if tr["weights_identical_across_ranks"] and tr["loss_finite"] else "FAILED"
             seg_batch = a.seg_global_batch // world if a.seg_global_batch else a.seg_batch
-            seg_res = time_seg(dev, dist, world, a.seg_steps, 3, seg_batch, a.seg_model, not a.seg_nchw)
-            seg_res["scaling"] = "strong (global batch fixed)" if a.seg_global_batch else "weak (batch per GPU fixed)"
+            r = time_seg(dev, dist, world, a.seg_steps, 3, seg_batch, a.seg_model, not a.seg_nchw, ddp_opts, graph)
+            sc = "strong (global batch fixed)" if a.seg_global_batch else "weak (batch per GPU fixed)"
+            seg_detail["weak" if not a.seg_global_batch else "strong"] = r
+            seg_res["weak" if not a.seg_global_batch else "strong"] = short(r, sc)
+            if not a.no_seg_strong and not a.seg_global_batch and 64 % world == 0:
+                # BASELINE configs[3]: YOLOv8-seg, global batch 64 split over the GPUs (strong scaling)
+                r = time_seg(dev, dist, world, a.seg_steps, 3, 64 // world, "yolov8seg", not a.seg_nchw, ddp_opts, graph)
+                seg_detail["strong"] = r
+                seg_res["strong"] = short(r, "strong (global batch 64 fixed)")
         except Exception as ex:
             if world > 1:
                 raise  # a rank must not leave a collective half-done
             seg_res = {"error": repr(ex)[:300]}
         wl = None
+    if not a.no_infer:
+        try:
+            infer = time_infer(dev, dist, world, a.infer_steps, 3, 4)
+            iw = Workload(dev, torch.float16, ["I3", "I4", "I5"], "tile", True)
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            per = {}
+            for i, nm in enumerate(iw.sites):
+                evs = []
+                for k in range(3 + 20):
+                    b = iw.sets[k % N_BUFFER_SETS][i]
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); iw.fwd(b, st); e1.record()
+                    evs.append((e0, e1))
+                torch.cuda.synchronize()
+                us = statistics.mean(x.elapsed_time(y) for x, y in evs[3:]) * 1e3
+                by = algo_bytes(nm, 2)[0]
+                per[nm] = {"us": us, "GBps": by / us / 1e3, "shape": dict(zip(("N", "H", "W", "G", "gc"), SITES[nm]))}
+            infer["dcnv3_fwd_sites_fp16_fused_softmax"] = per
+            del iw
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            if world > 1:
+                raise
+            infer = {"error": repr(ex)[:300]}
     ref_cuda = None
     if rank == 0 and not a.no_ref_cuda:
         try:
@@ -587,20 +836,32 @@ def main():
         t["frac_of_hbm"] = t["GBps"] / peak
         table[nm] = t
     dom = max(table, key=lambda k: table[k]["us_mean"])
-    roofline = {"bound": "hbm", "kernel": dom + ((" (memset + bwd_vec_kernel + cast_ws_kernel)" if os.environ.get("DCNV3_B200_BWD") == "vec" else
-                                        " (zero_select_kernel + bwd_imat_kernel [+ bwd_vec_kernel, skipped by the selector] + cast_ws_kernel)") if dom.startswith("bwd") and e == 2 and a.grad_accum == "opmath" else ""),
+    kernels = ""
+    if dom.startswith("bwd") and e == 2:
+        if a.grad_accum == "tile":
+            kernels = " (zero_fill_kernel + bwd_win_kernel)"
+        elif a.grad_accum == "opmath":
+            kernels = (" (memset + bwd_vec_kernel + cast_ws_kernel)" if os.environ.get("DCNV3_B200_BWD") == "vec" else
+                       " (zero_select_kernel + bwd_imat_kernel [+ bwd_vec_kernel, skipped by the selector] + cast_ws_kernel)")
+    roofline = {"bound": "hbm", "kernel": dom + kernels,
                 "achieved": table[dom]["GBps"], "peak": peak, "unit": "GB/s", "frac": table[dom]["GBps"] / peak,
                 "peak_source": peak_src, "traffic": ncu_traffic(dom),
+                "traffic_source": "profiles/r02_ncu_traffic.json: ncu dram__bytes_read.sum + dram__bytes_write.sum summed over "
+                                  "every kernel of the op, per call (a committed capture of this command, not measured by this run)",
                 "step_frac": value / world / peak}
     out = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": a.steps,
            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": a.dtype if a.dtype != "fp32" else "f32", "data": "synthetic",
-           "config": config, "pct_hbm_peak": 100.0 * value / world / peak, "roofline": roofline,
-           "ops": table, "seg_train": seg_res, "reference_cuda": ref_cuda, "e2e": e2e, "gpu_launches": launches, "clocks": clk}
+           "config": config, "ops": table, "reference_cuda": ref_cuda, "seg_detail": seg_detail,
+           "pct_hbm_peak": 100.0 * value / world / peak, "roofline": roofline, "gpu_launches": launches, "clocks": clk}
     if not a.no_cpu_baseline:
-        gbps, cms, cores, sample, _ = cpu_run(sites, e, 3, 1, budget_s=30.0)
+        gbps, cms, cores, sample, _ = cpu_run(sites, e, 3, 1)
         out["cpu_baseline"] = {"value": gbps, "unit": "GB/s", "cores": cores, "kind": "port",
                                "sample": sample, "ms_per_step_sample": cms}
+    # last keys (they survive a tail of the line): end-to-end, configs[4] inference, the data-parallel training step
+    out["e2e"] = e2e
+    out["infer"] = infer
+    out["seg_train"] = seg_res
     print(json.dumps(out), file=out_stream, flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -55,6 +55,20 @@ def test_fused_loss_is_softmax_output_invariant_and_ignores_bad_labels():
     assert abs(float(dice) - want) < 1e-5
 
 
+def test_fused_loss_out_of_range_labels_poison_the_loss():
+    """Labels outside [0, C) make the reference's cross_entropy / scatter_ raise; the fused path (no host sync)
+    returns NaN instead of silently dropping those pixels."""
+    pred, target, cw = _case(2, 12, 32, 32, 1, 3, True)
+    fus = SegmentationLoss(12, class_weights=cw, fused=True).to(DEV)
+    assert torch.isfinite(fus(pred, target)[0])
+    bad = target.clone()
+    bad[0, 3, 5] = 255
+    assert torch.isnan(fus(pred, bad)[0])
+    bad = target.clone()
+    bad[1, 0, 0] = -1
+    assert torch.isnan(fus(pred, bad)[0])
+
+
 def test_fused_loss_argument_errors():
     fus = SegmentationLoss(12, fused=True)
     with pytest.raises(RuntimeError):

@@ -98,16 +98,16 @@ def test_checkpoint_layout_and_resume(tmp_path):
     t.save(last, best, is_best=True)
     ck = torch.load(last, weights_only=False)
     assert set(ck) == {"model", "optimizer", "epoch", "best_fitness"}          # reference layout
-    assert isinstance(ck["model"], SegModel) and ck["epoch"] == 2 and ck["best_fitness"] == 0.4
+    assert isinstance(ck["model"], SegModel) and ck["epoch"] == 1 and ck["best_fitness"] == 0.4  # index of the epoch just finished
     assert set(torch.load(best, weights_only=False)) == {"model"}
     t2 = Trainer(tiny(), crit, batch_size=64, epochs=10)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         t2.resume(ck)
-    assert t2.epoch == 3 and t2.best_fitness == 0.4
+    assert t2.epoch == 2 and t2.best_fitness == 0.4   # two epochs trained -> continue with epoch index 2
     for (k, a), (_, b) in zip(ck["model"].state_dict().items(), t2.raw_model.state_dict().items()):
         assert torch.equal(a.float(), b.float()), k
-    assert abs(t2.optimizer.param_groups[0]["lr"] - HYP["lr0"] * lr_lambda(10)(3)) < 1e-9
+    assert abs(t2.optimizer.param_groups[0]["lr"] - HYP["lr0"] * lr_lambda(10)(2)) < 1e-9
     assert t2.optimizer.state_dict()["state"].keys() == ck["optimizer"]["state"].keys()
 
 
@@ -127,3 +127,23 @@ def test_sync_bn_switch_converts_every_batchnorm():
     t = Trainer(tiny(dcn="dcnv3"), SegmentationLoss(12), batch_size=16, epochs=1, ema=False, sync_bn=True)
     kinds = {type(m).__name__ for m in t.raw_model.modules() if "BatchNorm" in type(m).__name__}
     assert kinds == {"SyncBatchNorm"}  # including the BN inside every DCNv3.dw_conv
+
+
+def test_resume_warns_when_shapes_do_not_fit():
+    """A checkpoint built with another DCNv3 group count must not lose its heads silently."""
+    crit = SegmentationLoss(12)
+    src = SegModel(YOLOV5_SEG, dcn="dcnv3", dcn_group=None, img_size=(32, 32))    # the reference's group = g = 1
+    dst = Trainer(SegModel(YOLOV5_SEG, dcn="dcnv3", img_size=(32, 32)), crit, batch_size=64, epochs=2, ema=False)
+    with pytest.warns(RuntimeWarning, match="NOT loaded"):
+        dst.resume({"model": src, "optimizer": None, "epoch": 0})
+    assert dst.dropped_keys and all(".offset." in k or ".mask." in k for k in dst.dropped_keys)
+
+
+def test_default_block_has_the_reference_parameter_shapes():
+    """common and yolo.py:9 passes group=g (default 1): offset head [18, C], mask head [9, C]."""
+    from yolo_dual_b200.blocks import C3_DCNV3
+    blk = C3_DCNV3(64, 64)
+    d = blk.m[0].cv2.dcnv3
+    assert d.group == 1 and tuple(d.offset.weight.shape) == (18, 32) and tuple(d.mask.weight.shape) == (9, 32)
+    d16 = C3_DCNV3(64, 64, dcn_group="gc16").m[0].cv2.dcnv3
+    assert d16.group == 2 and d16.group_channels == 16

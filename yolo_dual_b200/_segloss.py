@@ -68,6 +68,12 @@ class FusedSegLoss(torch.autograd.Function):
         dice = 1.0 - ((2.0 * inter + FusedSegLoss.EPS) / denom).mean()
         ce = stats[-2] / stats[-1]
         total = ce + 0.5 * dice
+        # Labels outside [0, C) (a 255 "void" label, negatives) match no class in the kernels and would silently drop
+        # out of every sum, where the reference's F.cross_entropy / scatter_ raise.  Raising needs a device->host sync
+        # per step; instead the per-class label counts must add up to the number of labels or the loss is NaN (loud
+        # in any training loop, no synchronisation).
+        n_labels = float(n) * (h * scale) * (w * scale)
+        total = torch.where(osum.sum() == n_labels, total, torch.full_like(total, float("nan")))
         ctx.save_for_backward(pred, target, class_weights, inter, denom, stats[-1])
         ctx.scale = scale
         ctx.mark_non_differentiable(ce, dice)

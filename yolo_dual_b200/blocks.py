@@ -4,9 +4,11 @@ with the same class names, constructor arguments and forward semantics.
 
 Additions, each labelled:
   * ``dcn_group``: the notes forward YOLO's conv-group argument ``g`` (default 1) as the DCNv3
-    group count, i.e. one group of 128/256/512 channels.  BASELINE's shapes use
-    group_channels = 16, so ``dcn_group=None`` picks ``channels // 16`` and ``g`` is still honoured
-    when given explicitly (SURVEY §3.4 "Group count").
+    group count, i.e. one group of 128/256/512 channels, and that is the default here too
+    (``dcn_group=None``): a default-built block has the reference's parameter shapes (offset head
+    ``[18, C]``, mask head ``[9, C]``) and loads reference-trained weights.  BASELINE's shapes use
+    group_channels = 16: ``dcn_group="gc16"`` picks ``channels // 16`` groups (what the seg / detection
+    builders of this package pass by default), an integer sets the count (SURVEY §3.4 "Group count").
   * ``C2f_DCNV3``: a *derived* block — no DCNv3 variant of the YOLOv8 ``C2f_DCN``
     (unet-lite/yolo8-seg/seg_diceloss_yolov8.py:431-471) exists in the reference; this one keeps
     C2f's split/concat and swaps each inner block for ``DCNV3_YoLo``.
@@ -20,12 +22,18 @@ from .ops_dcnv3.modules.conv import Conv
 from .ops_dcnv3.modules.dcnv3 import DCNv3
 
 
+GC16 = "gc16"  # dcn_group value: group_channels = 16, the BASELINE shapes
+
+
 def _pick_group(channels: int, g, dcn_group):
-    if dcn_group is not None:
-        return dcn_group
-    if g not in (None, 1):
-        return g
-    return max(channels // 16, 1) if channels % 16 == 0 else 1
+    """DCNv3 group count: the reference's `group=g` unless `dcn_group` says otherwise (module docstring)."""
+    if dcn_group is None:
+        return 1 if g is None else g
+    if dcn_group == GC16:
+        if g not in (None, 1):
+            return g
+        return max(channels // 16, 1) if channels % 16 == 0 else 1
+    return int(dcn_group)
 
 
 class DCNV3_YoLo(nn.Module):

@@ -422,7 +422,7 @@ bool plan_tile(const Geo &q, bool logits, const void *in, const void *gout, cons
     const TileKnobs kn = tile_knobs();
     if (kn.force != 2) return false;
     if (sizeof(T) > 4 || q.gc != kTileGC) return false;
-    if (logits && !(q.kh == 3 && q.kw == 3) && q.P > kMaxSoftmaxP) return false;
+    if (logits && q.P > kMaxSoftmaxP) return false;
     if (!aligned_to(in, 8 * (int)sizeof(T)) || !aligned_to(gout, 8 * (int)sizeof(T)) || !aligned16(acc)) return false;
     if (reinterpret_cast<uintptr_t>(off) & (2 * sizeof(T) - 1)) return false;
     if ((unsigned long long)q.H * q.W * q.C * 4ull >= (1ull << 31)) return false;
@@ -540,7 +540,7 @@ int backward_t(const void *in_, const void *off_, const void *mask_, const void 
         if (grad_accum == DCNV3_B200_ACC_TILE) {
             const int fam = knobs().bwd;
             if ((fam == 0 || fam == 5) && win_eligible<T>(q, in_, off_, mask_, gout_, gin_, goff_, gmask_)) {
-                if ((e = cudaMemsetAsync(gin, 0, n_in * sizeof(T), st)) != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(grad_input)");
+                launch(win::zero_fill_kernel, 148 * 4, 256, 0, st, reinterpret_cast<uint4 *>(gin), n_in * sizeof(T) / 16);
                 if (n_pix == 0) return 0;
                 return launch_bwd_win<T>(in, off, mask, gout, gin, goff, gmask, q, logits, st);
             }
@@ -657,6 +657,10 @@ int dcnv3_b200_forward(const void *input, const void *offset, const void *mask, 
     if (rc) return rc;
     if (!dtype_size(dtype)) return fail(DCNV3_B200_EINVAL, "unknown dtype %d", dtype);
     if (mask_is_logits != 0 && mask_is_logits != 1) return fail(DCNV3_B200_EINVAL, "mask_is_logits must be 0 or 1");
+    // same bound as the backward (backward_launch): a fused-softmax forward must not succeed where autograd's
+    // backward would then fail
+    if (mask_is_logits && q.P > kMaxSoftmaxP)
+        return fail(DCNV3_B200_EINVAL, "fused softmax supports at most %d sampling points (got %d)", kMaxSoftmaxP, q.P);
     if (q.N == 0) return 0;
     if (!input || !offset || !mask || !output) return fail(DCNV3_B200_ENULL, "null tensor pointer");
     if ((rc = check_device())) return rc;

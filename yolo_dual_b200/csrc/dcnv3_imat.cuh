@@ -741,10 +741,10 @@ __global__ void __launch_bounds__(32 * kWarps, 2)
 bwd_imat_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
                 const T *__restrict__ gout, float *__restrict__ gacc, T *__restrict__ goff,
                 T *__restrict__ gmask, const Geo q, const int tiles_x, const int tiles_y, const int GQ,
-                const int *__restrict__ sel) {
+                const int *sel) {
     extern __shared__ __align__(128) unsigned char smem[];
     pdl_enter();
-    if (sel != nullptr && *sel != kSelImat) return;  // select_kernel chose the vector family
+    if (sel != nullptr && __ldcg(sel) != kSelImat) return;  // select_kernel chose the vector family
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TileCoord tc = decode_tile_lpt(blockIdx.x, q.Ho, q.Wo, q.N, GQ);
     const int g = tc.gq * kWarps + warp;

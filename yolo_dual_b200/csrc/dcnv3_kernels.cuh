@@ -563,14 +563,14 @@ __global__ void __launch_bounds__(kThreads)
 bwd_vec_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
                const T *__restrict__ gout, A *__restrict__ gin, T *__restrict__ goff,
                T *__restrict__ gmask, const Geo q, const int vec_per_pix,
-               const int lanes_per_group, const unsigned total, const int *__restrict__ sel = nullptr,
+               const int lanes_per_group, const unsigned total, const int *sel = nullptr,
                const unsigned per_cta = 1, const unsigned n_blocks = 0) {
     // Wait first, like every kernel of the chain.  (Reading `sel` ahead of the wait and letting unneeded CTAs
     // leave at once is legal — zero_select_kernel has completed by then — but it lets the NEXT kernel's
     // thousands of CTAs become resident and sit in their own wait while bwd_imat_kernel is still in its
     // tail, which slowed the back-to-back step by 20-170 us.  Waiting CTAs are not free.)
     pdl_enter();
-    if (sel != nullptr && *sel != 1) return;
+    if (sel != nullptr && __ldcg(sel) != 1) return;  // written by the previous kernel of the PDL chain: coherent load, never .nc
     if (per_cta == 1) {
         bwd_vec_body<T, A, BPL, KP, LOGITS>(blockIdx.x, in, off, mask, gout, gin, goff, gmask, q, vec_per_pix, lanes_per_group, total);
         return;
@@ -582,17 +582,20 @@ bwd_vec_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
 // fp32 workspace -> 16-bit grad_input (ACC_OPMATH), 8 elements per thread
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-cast_ws_kernel(const float *__restrict__ ws, T *__restrict__ dst, const size_t n_vec8,
+cast_ws_kernel(const float *ws, T *__restrict__ dst, const size_t n_vec8,
                const size_t n_total) {
     pdl_enter();
+    // `ws` was written by the previous kernels of the PDL chain while this one was already resident: it is neither
+    // const __restrict__ nor read through the non-coherent path (ld.global.nc is only defined for data that is
+    // read-only for the kernel's whole lifetime) — __ldcg = ld.global.cg, served by L2 where the reductions landed.
     const size_t i = blockIdx.x * (size_t)kThreads + threadIdx.x;
     if (i < n_vec8) {
-        const float4 a = *reinterpret_cast<const float4 *>(ws + i * 8);
-        const float4 b = *reinterpret_cast<const float4 *>(ws + i * 8 + 4);
+        const float4 a = __ldcg(reinterpret_cast<const float4 *>(ws + i * 8));
+        const float4 b = __ldcg(reinterpret_cast<const float4 *>(ws + i * 8 + 4));
         const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         *reinterpret_cast<uint4 *>(dst + i * 8) = pack(v, (const T *)nullptr);
     } else if (i == n_vec8) {  // scalar tail (generic path only)
-        for (size_t k = n_vec8 * 8; k < n_total; ++k) dst[k] = from_math<T>(ws[k]);
+        for (size_t k = n_vec8 * 8; k < n_total; ++k) dst[k] = from_math<T>(__ldcg(ws + k));
     }
 }
 

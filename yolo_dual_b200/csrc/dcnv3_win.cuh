@@ -232,6 +232,17 @@ __device__ __forceinline__ void stmatrix_x4(uint32_t addr, uint32_t r0, uint32_t
     asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
 
+// Zero fill of grad_input in front of bwd_win_kernel (replaces cudaMemsetAsync, which is not part of a programmatic
+// launch chain: the backward kernel could not become resident before the memset had drained).  It waits for the
+// previous kernel of the stream BEFORE it releases its dependents, so once bwd_win_kernel's CTAs run, everything
+// older than this kernel is complete and visible; bwd_win_kernel itself only has to wait (griddepcontrol.wait) right
+// before its first access to grad_input.
+__global__ void __launch_bounds__(256) zero_fill_kernel(uint4 *__restrict__ p, const size_t n16) {
+    pdl_enter();
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n16; i += (size_t)gridDim.x * 256) p[i] = z;
+}
+
 template <typename T, bool LOGITS>
 __global__ void __launch_bounds__(kThreadsW, 3)
 bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
@@ -240,7 +251,11 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool kScaled = std::is_same<T, __nv_bfloat16>::value;
     __shared__ __align__(16) uint32_t smax[8];
-    pdl_enter();
+    // Programmatic launch: the kernel in front of this one is zero_fill_kernel, which has already waited for ITS
+    // predecessor (so input / offset / mask / grad_output are final and grad_offset / grad_mask may be written);
+    // only grad_input is still being zeroed — pdl_wait() sits in front of every access to it (flush, far band,
+    // out-of-window points).
+    pdl_release();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool dots_role = (blockIdx.x & 1u) == 0u;
     TileCoord tc;  // (image, band row, tile column, group quad)
@@ -354,6 +369,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         if (!dots_role) {  // the vector family's lane body computes all three gradients of the band
             VecCoord c;
             c.pix = (unsigned)pix; c.v = tc.gq * 8 + sub; c.g = g; c.n = tc.n; c.ho = cy; c.wo = cx;
+            pdl_wait();
             bwd_far_lane<T, LOGITS>(c, h, valid, in, off, mask, gout, gin, goff, gmask, q);
         }
         return;
@@ -515,6 +531,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         }
     }
     if (slowmask) {  // rare: points inside the map but outside the band's window (|offset * scale| >= 3 px)
+        pdl_wait();
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
             if (!((slowmask >> k) & 1u)) continue;
@@ -577,6 +594,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                         imat::pack2<T>(gw[i][1][0], gw[i][1][1]), imat::pack2<T>(gw[i][1][2], gw[i][1][3]));
         }
         __syncwarp();
+        pdl_wait();  // grad_input is zero from here on (zero_fill_kernel complete and visible)
         const int cell = lane >> 1, half = lane & 1;
         const int ix = wx0 + cell;
         const bool col_ok = (unsigned)ix < (unsigned)q.W;

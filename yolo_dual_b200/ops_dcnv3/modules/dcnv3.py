@@ -28,6 +28,7 @@ from ..functions import DCNv3Function, DCNv3SoftmaxFunction
 from .conv import Conv, autopad  # noqa: F401  (re-exported: the reference module exposes both names)
 
 IM2COL_STEP = 256  # what the reference module always passes (dcnv3.py:133); a no-op here
+MAX_FUSED_SOFTMAX_POINTS = 49  # kMaxSoftmaxP in csrc/dcnv3_kernels.cuh (forward and backward check the same bound)
 
 
 def _is_power_of_2(n):
@@ -51,6 +52,9 @@ class DCNv3(nn.Module):
         super().__init__()
         if channels % group:
             raise ValueError(f'channels must be divisible by group, but got {channels} and {group}')
+        if fused_softmax and kernel_size * kernel_size > MAX_FUSED_SOFTMAX_POINTS:
+            raise ValueError(f'fused_softmax supports at most {MAX_FUSED_SOFTMAX_POINTS} sampling points per group '
+                             f'(kernel_size {kernel_size} has {kernel_size * kernel_size})')
         if not _is_power_of_2(channels // group):
             warnings.warn("You'd better set channels in DCNv3 to make the dimension of each attention head a "
                           "power of 2 which is more efficient in our CUDA implementation.")

@@ -201,7 +201,7 @@ class SegModel(nn.Module):
     """YOLOv5Seg / YOLOv8Seg of the reference (seg_diceloss_yolov5.py:511-659) over a layer table."""
 
     def __init__(self, cfg: Dict = YOLOV5_SEG, num_classes: Optional[int] = None, dcn: str = "dcnv3",
-                 dcn_group: Optional[int] = None, fused_softmax: bool = False, outer_residual: bool = False,
+                 dcn_group="gc16", fused_softmax: bool = False, outer_residual: bool = False,
                  img_size: Sequence[int] = (640, 640), defer_upsample: bool = True):
         """defer_upsample: run the pointwise tail of the head (1x1 Conv + BN + SiLU, channel Softmax) BEFORE the last
         nearest Upsample instead of after it.  Every one of those ops commutes with pixel replication — the batch
@@ -416,14 +416,32 @@ def shard_batch(n_global: int, rank: int, world: int):
     return slice(rank * per, (rank + 1) * per)
 
 
-def wrap_ddp(model: nn.Module, device=None):
-    """smart_DDP (utils/torch_utils.py:55-63): DDP with static_graph when a process group is up."""
+def wrap_ddp(model: nn.Module, device=None, bucket_cap_mb: Optional[float] = None, grad_compress: Optional[str] = None,
+             first_bucket_mb: Optional[float] = None):
+    """smart_DDP (utils/torch_utils.py:55-63): DDP with static_graph when a process group is up.
+
+    Additions (all off by default = the reference's plain DDP): `bucket_cap_mb` sizes the gradient buckets (DDP's 25 MB
+    default puts this model's 21 M parameters into three ring all-reduces, the last of which cannot overlap with the
+    backward), `first_bucket_mb` the first one (the gradients of the LAST layers: it fires while most of the
+    backward is still to run), `grad_compress='bf16'` all-reduces the buckets in bfloat16 (torch's
+    bf16_compress_hook: half the bytes; the sum of `world` bf16 values per element rounds once more than fp32)."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return model
     from torch.nn.parallel import DistributedDataParallel as DDP
     ids = [device.index] if device is not None and device.type == "cuda" else None
-    return DDP(model, device_ids=ids, static_graph=True, gradient_as_bucket_view=True)  # grads live in the buckets
+    kw = {}
+    if bucket_cap_mb:
+        kw["bucket_cap_mb"] = bucket_cap_mb
+    if first_bucket_mb:
+        dist._DEFAULT_FIRST_BUCKET_BYTES = int(first_bucket_mb * 1024 * 1024)  # read by DDP's constructor
+    ddp = DDP(model, device_ids=ids, static_graph=True, gradient_as_bucket_view=True, **kw)  # grads live in the buckets
+    if grad_compress == "bf16":
+        from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+        ddp.register_comm_hook(None, default_hooks.bf16_compress_hook)
+    elif grad_compress not in (None, "none"):
+        raise ValueError("grad_compress must be None or 'bf16'")
+    return ddp
 
 
 def forward_loss(model, criterion, imgs, labels, autocast_dtype=None):
@@ -444,3 +462,47 @@ def train_step(model, criterion, optimizer, imgs, labels, autocast_dtype=None):
     loss.backward()
     optimizer.step()
     return loss.detach(), parts
+
+
+class GraphedTrainStep:
+    """`train_step` as ONE CUDA graph: forward, CE + Dice, backward (DDP's bucketed NCCL all-reduces included) and the
+    SGD update are captured once and replayed per step.  The eager step of these models is 850-1250 kernel launches;
+    at 8 images per GPU (BASELINE configs[3] on 8 GPUs) the host cannot issue them as fast as the GPU retires them.
+    Every kernel of this package is capturable (explicit stream, no host synchronisation, caller-visible workspaces).
+
+    Rules kept from torch's CUDA-graph notes: `warmup` eager steps on a side stream first (cuDNN autotuning, DDP's
+    first static-graph iteration, lazy workspaces; >= 11 under DDP), gradients set to None before the capture so that
+    they live in the graph's private pool, a fixed learning rate while the graph is in use (re-capture after a
+    scheduler step).  The warm-up steps are real optimizer steps on the batches `batches` yields."""
+
+    def __init__(self, model, criterion, optimizer, batches, autocast_dtype=None, warmup: Optional[int] = None):
+        ddp = isinstance(model, nn.parallel.DistributedDataParallel)
+        warmup = (11 if ddp else 3) if warmup is None else warmup
+        it = iter(batches)
+        imgs, labels = next(it)
+        self.imgs, self.labels = torch.empty_like(imgs), torch.empty_like(labels)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for k in range(warmup):
+                if k:
+                    imgs, labels = next(it)
+                self.imgs.copy_(imgs)
+                self.labels.copy_(labels)
+                train_step(model, criterion, optimizer, self.imgs, self.labels, autocast_dtype)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        optimizer.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            loss, parts = forward_loss(model, criterion, self.imgs, self.labels, autocast_dtype)
+            loss.backward()
+            optimizer.step()
+        self.loss, self.parts = loss.detach(), parts
+
+    def __call__(self, imgs, labels):
+        self.imgs.copy_(imgs, non_blocking=True)
+        self.labels.copy_(labels, non_blocking=True)
+        self.graph.replay()
+        return self.loss, self.parts

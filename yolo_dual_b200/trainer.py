@@ -19,6 +19,7 @@ gradient all-reduce happens once per optimizer step (the reference never runs it
 from __future__ import annotations
 
 import math
+import warnings
 from contextlib import nullcontext
 from copy import deepcopy
 from typing import Optional
@@ -118,8 +119,11 @@ class Trainer:
 
     # ---- checkpoints: the reference pickles the whole EMA module (seg_diceloss_yolov5.py:1204-1212)
     def checkpoint(self) -> dict:
+        """Call after `end_epoch()` (the reference saves after its scheduler step, :1204-1212): 'epoch' is the index
+        of the epoch just FINISHED, so `resume` continues at that index + 1 and the schedule is stepped once per
+        epoch actually trained."""
         m = self.ema.ema if self.ema else de_parallel(self.model)
-        return {"model": deepcopy(m), "optimizer": self.optimizer.state_dict(), "epoch": self.epoch,
+        return {"model": deepcopy(m), "optimizer": self.optimizer.state_dict(), "epoch": self.epoch - 1,
                 "best_fitness": self.best_fitness}
 
     def save(self, last_path, best_path=None, is_best: bool = False) -> None:
@@ -133,6 +137,12 @@ class Trainer:
         src = ckpt["model"].float().state_dict()
         dst = de_parallel(self.model).state_dict()
         keep = {k: v for k, v in src.items() if k in dst and v.shape == dst[k].shape}
+        bad = [k for k, v in src.items() if k in dst and v.shape != dst[k].shape]
+        if bad:  # the reference's intersect drops these silently (:944-952); a dropped DCNv3 head stays zero-initialised
+            warnings.warn(f"Trainer.resume: {len(bad)} checkpoint tensors do not fit this model's shapes and were NOT "
+                          f"loaded (first: {bad[0]} {tuple(src[bad[0]].shape)} vs {tuple(dst[bad[0]].shape)}); build the "
+                          f"blocks with the checkpoint's DCNv3 group count (dcn_group=...)", RuntimeWarning, stacklevel=2)
+        self.dropped_keys = bad
         de_parallel(self.model).load_state_dict(keep, strict=False)
         if ckpt.get("optimizer") is not None:
             self.optimizer.load_state_dict(ckpt["optimizer"])

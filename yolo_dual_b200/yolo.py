@@ -172,7 +172,7 @@ _REPEAT_INSIDE = {"C3", "C3_DCNV3", "C2f_DCNV3"}     # blocks that take the repe
 _ALIASES = {"C3_DCN": "C3_DCNV3", "C2f_DCN": "C2f_DCNV3", "Upsample": "nn.Upsample"}
 
 
-def build_layers(cfg: Dict, ch: Sequence[int] = (3,), dcn: str = "dcnv3", dcn_group: Optional[int] = None,
+def build_layers(cfg: Dict, ch: Sequence[int] = (3,), dcn: str = "dcnv3", dcn_group="gc16",
                  fused_softmax: bool = False):
     """Layer table -> (nn.Sequential, sorted save list, output channels per layer, stride per layer).
 
@@ -258,7 +258,7 @@ class DetectionModel(nn.Module):
     """models/yolo.py:165-262 over `build_layers` (no CPU stride probe; see module docstring)."""
 
     def __init__(self, cfg: Dict = YOLOV5N_DCNV3, ch: int = 3, nc: Optional[int] = None, dcn: str = "dcnv3",
-                 dcn_group: Optional[int] = None, fused_softmax: bool = False):
+                 dcn_group="gc16", fused_softmax: bool = False):
         super().__init__()
         self.yaml = deepcopy(cfg)
         if nc and nc != self.yaml["nc"]:
