@@ -91,7 +91,8 @@ def test_win_vs_pixel_oracle(case, dtype, sigma, pixel_oracle):
     got = _run(DCNv3Function, x, off, m, go, args, dtype)
     eps = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
     for g_, w_, name in zip(got, want, ("output", "grad_input", "grad_offset", "grad_mask")):
-        if name == "grad_input" and sigma > 1.0:  # out-of-window points round per contribution (ACC_STORAGE's bound)
+        if name == "grad_input" and sigma * scale > 1.0:  # out-of-window points (|offset * scale| >= 3 px: 4.5 % of the
+            # coordinates at sigma * scale = 1.5) round per contribution in an order that varies run to run (ACC_STORAGE's bound)
             _close(g_, w_, name, rtol=max(1e-2, 6 * eps), atol=max(2e-3, 6 * eps))
         elif name == "grad_input":
             _close(g_, w_, name, **_gi_tol(dtype))

@@ -313,8 +313,9 @@ bool win_eligible(const Geo &q, const void *in, const void *off, const void *mas
                   const void *goff, const void *gmask) {
     if (sizeof(T) != 2 || !win_geometry(q)) return false;
     if (!aligned16(in) || !aligned16(gout) || !aligned16(gin)) return false;
-    if ((reinterpret_cast<uintptr_t>(off) & 3u) || (reinterpret_cast<uintptr_t>(goff) & 3u) ||
-        (reinterpret_cast<uintptr_t>(mask) & 1u) || (reinterpret_cast<uintptr_t>(gmask) & 1u)) return false;
+    // offsets / masks move as 16- / 8-byte chunks (4 groups of a pixel: 144 / 72 contiguous bytes)
+    if (!aligned16(off) || !aligned16(goff) || (reinterpret_cast<uintptr_t>(mask) & 7u) ||
+        (reinterpret_cast<uintptr_t>(gmask) & 7u)) return false;
     const unsigned long long blocks = (unsigned long long)q.N * ((q.Ho + 3) / 4) * ((q.Wo + 7) / 8) * (q.G / imat::kWarps);
     if (blocks == 0 || blocks >= (1ull << 30)) return false;
     // the far-band fallback indexes (pixel, 8-channel vector) lanes with 32 bits
@@ -545,8 +546,8 @@ int backward_t(const void *in_, const void *off_, const void *mask_, const void 
                 return launch_bwd_win<T>(in, off, mask, gout, gin, goff, gmask, q, logits, st);
             }
             if (win_geometry(q) && (!ws || ws_bytes == 0))
-                return fail(DCNV3_B200_EALIGN, "ACC_TILE needs 16-byte aligned input / grad_output / grad_input (4-byte offset / "
-                                               "grad_offset); pass an ACC_OPMATH workspace to fall back");
+                return fail(DCNV3_B200_EALIGN, "ACC_TILE needs 16-byte aligned input / grad_output / grad_input / offset / "
+                                               "grad_offset (8-byte mask / grad_mask); pass an ACC_OPMATH workspace to fall back");
             grad_accum = DCNV3_B200_ACC_OPMATH;
         }
     }

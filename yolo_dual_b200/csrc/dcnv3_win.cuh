@@ -53,7 +53,18 @@ constexpr int kGoGrpB = 32 * kGoRowB;
 constexpr int kGoB = kWarps * kGoGrpB;                   // 6 144 B
 constexpr int kScatB = kWmB + kGoB;                      // 57 408 B: three CTAs per SM
 constexpr int kDwinB = kBandRows * kWinW * 128;          // dots role: the band's 12x16-cell x 64-channel window, 24 576 B
-constexpr int kSmemB = kScatB > kDwinB ? kScatB : kDwinB;
+// Staging area for the band's offsets / masks (in) and grad_offset / grad_mask (out): the four groups of a pixel are one
+// contiguous 144-byte (offsets) resp. 72-byte (masks) run in global memory, so they move as whole 16- / 8-byte
+// chunks (cp.async in, vector stores out) instead of one 4- / 2-byte access per lane and point (ncu, round 2: those
+// scalar accesses were 9.5 M of the launch's 38 M L1 wavefronts and moved 5x their bytes in L2 sectors).  Pixel pitch
+// 160 B: lane (pixel i, group g, half h) reads word 40 i + 9 g + 4 h + k — all 32 banks distinct.
+constexpr int kStOffPx = 160;
+constexpr int kStMaskPx = 80;
+constexpr int kStOffB = 32 * kStOffPx;                   // 5 120 B
+constexpr int kStMaskB = 32 * kStMaskPx;                 // 2 560 B
+constexpr int kStageB = kStOffB + kStMaskB;
+constexpr int kStageOff = kScatB > kDwinB ? kScatB : kDwinB;  // behind either role's buffers
+constexpr int kSmemB = kStageOff + kStageB;              // 65 088 B: still three CTAs per SM
 #ifndef DCNV3_WIN_PREFETCH_UNITS
 #define DCNV3_WIN_PREFETCH_UNITS 320
 #endif
@@ -74,6 +85,22 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 }
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v, bool pred) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.shared.u32 [%0], %1;\n\t}" ::"r"(addr), "r"(v), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src, int bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -232,11 +259,9 @@ __device__ __forceinline__ void stmatrix_x4(uint32_t addr, uint32_t r0, uint32_t
     asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
 }
 
-// Zero fill of grad_input in front of bwd_win_kernel (replaces cudaMemsetAsync, which is not part of a programmatic
-// launch chain: the backward kernel could not become resident before the memset had drained).  It waits for the
-// previous kernel of the stream BEFORE it releases its dependents, so once bwd_win_kernel's CTAs run, everything
-// older than this kernel is complete and visible; bwd_win_kernel itself only has to wait (griddepcontrol.wait) right
-// before its first access to grad_input.
+// Zero fill of grad_input in front of bwd_win_kernel: a kernel of this library instead of cudaMemsetAsync, so that it is
+// part of the programmatic launch chain (the backward kernel's CTAs are resident when it drains) and its DRAM
+// traffic shows up in the ncu launch list next to the backward kernel's (profiles/r02_ncu_traffic.json).
 __global__ void __launch_bounds__(256) zero_fill_kernel(uint4 *__restrict__ p, const size_t n16) {
     pdl_enter();
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -251,11 +276,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool kScaled = std::is_same<T, __nv_bfloat16>::value;
     __shared__ __align__(16) uint32_t smax[8];
-    // Programmatic launch: the kernel in front of this one is zero_fill_kernel, which has already waited for ITS
-    // predecessor (so input / offset / mask / grad_output are final and grad_offset / grad_mask may be written);
-    // only grad_input is still being zeroed — pdl_wait() sits in front of every access to it (flush, far band,
-    // out-of-window points).
-    pdl_release();
+    pdl_enter();  // (waiting only in front of the first grad_input access instead measured nothing: 190.4 vs 191.0 us at P3)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool dots_role = (blockIdx.x & 1u) == 0u;
     TileCoord tc;  // (image, band row, tile column, group quad)
@@ -272,6 +293,24 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     const PtGeo pg{q.H, q.W, q.scale};
     const uint32_t smem_s = imat::smem_u32(smem);
 
+    // the band's offsets and masks -> staging area, whole chunks (a pixel outside the map: zero fill).  A warp's lanes
+    // are 4 pixels x 4 groups x 2 halves, so every warp stages (and later writes back) exactly the 4 x 9 chunks of its
+    // own four pixels: no CTA barrier on either side, __syncwarp() is enough.
+    const uint32_t stage_s = smem_s + kStageOff;
+    const size_t gq_unit = (size_t)tc.gq * kWarps;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int t = it * 32 + lane;           // chunk 0..35 of the warp
+        if (t < 36) {
+            const int ppx = warp * 4 + t / 9, chk = t % 9;
+            const int poy = tc.ty * 4 + (ppx >> 3), pox = tc.tx * kTile + (ppx & 7);
+            const bool ok = poy < q.Ho && pox < q.Wo;
+            const size_t u0 = (((size_t)tc.n * q.Ho + min(poy, q.Ho - 1)) * q.Wo + min(pox, q.Wo - 1)) * q.G + gq_unit;
+            imat::cp_async16(stage_s + ppx * kStOffPx + chk * 16, reinterpret_cast<const char *>(off) + u0 * 36 + chk * 16, ok ? 16 : 0);
+            cp_async8(stage_s + kStOffB + ppx * kStMaskPx + chk * 8, reinterpret_cast<const char *>(mask) + u0 * 18 + chk * 8, ok ? 8 : 0);
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // group 0: this warp's offsets / masks
     if (dots_role) {  // stage the 12x16-cell x 64-channel window, unswizzled; zero outside the map
         const int ch = tid & 7, col = (tid >> 3) & 15, r0 = tid >> 7;
         const int ix = wx0 + col;
@@ -286,7 +325,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
             imat::cp_async16(dst, ok ? p : in, ok ? 16 : 0);
             p += step; dst += 2 * kWinW * 128; iy += 2;
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");  // group 1: the window (needed behind barrier A)
     } else {          // zero the interpolation matrix
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
@@ -304,28 +343,30 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     const int cy = min(oy, q.Ho - 1), cx = min(ox, q.Wo - 1);  // clamped: addresses of an idle lane stay legal
     const size_t pix = ((size_t)tc.n * q.Ho + cy) * q.Wo + cx;
     const size_t unit = pix * q.G + g;
-    const uint32_t *po = reinterpret_cast<const uint32_t *>(off) + unit * 9;
-    const unsigned short *pm = reinterpret_cast<const unsigned short *>(mask) + unit * 9;
     const uint4 *gp = reinterpret_cast<const uint4 *>(gout + pix * q.C + g * 16);
+    uint4 g_own = make_uint4(0u, 0u, 0u, 0u), g_oth = g_own;
+    if (valid) {  // in flight while the staging copies land
+        g_own = __ldg(gp + h);
+        if (dots_role) g_oth = __ldg(gp + (h ^ 1));
+    }
+    if (dots_role) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();  // this warp's offsets / masks are staged (the window may still be in flight)
 
-    // ---- loads: offsets of points 4h..4h+3 and 8, their masks (all nine for the softmax), grad_output
+    // ---- this lane's offsets of points 4h..4h+3 and 8, their masks (all nine for the softmax), grad_output
+    const uint32_t so_l = stage_s + px * kStOffPx + gl * 36, sm_l = stage_s + kStOffB + px * kStMaskPx + gl * 18;
     uint32_t roff[5];
     float rm[LOGITS ? 9 : 5];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) roff[k] = valid ? __ldg(po + 4 * h + k) : 0u;
-    roff[4] = valid ? __ldg(po + 8) : 0u;
+    for (int k = 0; k < 4; ++k) roff[k] = lds32(so_l + (4 * h + k) * 4);
+    roff[4] = lds32(so_l + 32);
     if (LOGITS) {
 #pragma unroll
-        for (int p = 0; p < 9; ++p) rm[p] = valid ? imat::half_to_float<T>(__ldg(pm + p)) : 0.f;
+        for (int p = 0; p < 9; ++p) rm[p] = valid ? imat::half_to_float<T>((unsigned short)lds16(sm_l + p * 2)) : 0.f;
     } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) rm[k] = valid ? imat::half_to_float<T>(__ldg(pm + 4 * h + k)) : 0.f;
-        rm[4] = valid ? imat::half_to_float<T>(__ldg(pm + 8)) : 0.f;
-    }
-    uint4 g_own = make_uint4(0u, 0u, 0u, 0u), g_oth = g_own;
-    if (valid) {
-        g_own = __ldg(gp + h);
-        if (dots_role) g_oth = __ldg(gp + (h ^ 1));
+        for (int k = 0; k < 4; ++k) rm[k] = imat::half_to_float<T>((unsigned short)lds16(sm_l + (4 * h + k) * 2));
+        rm[4] = imat::half_to_float<T>((unsigned short)lds16(sm_l + 16));
     }
 #ifdef DCNV3_WIN_PREFETCH  // measured SLOWER (P3 195.0 vs 191.0 us at any distance, profiles/r02_bwd_kernel_history.md): off by default
     // The CTAs of a unit are short (~2 k cycles) and begin with a round trip to DRAM for offsets / masks / grad_output.
@@ -369,7 +410,6 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         if (!dots_role) {  // the vector family's lane body computes all three gradients of the band
             VecCoord c;
             c.pix = (unsigned)pix; c.v = tc.gq * 8 + sub; c.g = g; c.n = tc.n; c.ho = cy; c.wo = cx;
-            pdl_wait();
             bwd_far_lane<T, LOGITS>(c, h, valid, in, off, mask, gout, gin, goff, gmask, q);
         }
         return;
@@ -460,17 +500,30 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
 #pragma unroll
             for (int k = 0; k < 5; ++k) res_m[k] = mk[k] * (res_m[k] - dot);
         }
-        if (valid) {
-            uint32_t *qo = reinterpret_cast<uint32_t *>(goff) + unit * 9;
-            unsigned short *qm = reinterpret_cast<unsigned short *>(gmask) + unit * 9;
+        // results -> the warp's own part of the staging area -> whole chunks to global memory
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                qo[4 * h + k] = res_off[k];
-                qm[4 * h + k] = (unsigned short)(imat::pack2<T>(res_m[k], 0.f) & 0xffffu);
-            }
-            if (h == 0) {
-                qo[8] = res_off[4];
-                qm[8] = (unsigned short)(imat::pack2<T>(res_m[4], 0.f) & 0xffffu);
+        for (int k = 0; k < 4; ++k) {
+            sts32(so_l + (4 * h + k) * 4, res_off[k], true);
+            sts16(sm_l + (4 * h + k) * 2, imat::pack2<T>(res_m[k], 0.f) & 0xffffu);
+        }
+        if (h == 0) {
+            sts32(so_l + 32, res_off[4], true);
+            sts16(sm_l + 16, imat::pack2<T>(res_m[4], 0.f) & 0xffffu);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int t = it * 32 + lane;
+            if (t < 36) {
+                const int ppx = warp * 4 + t / 9, chk = t % 9;
+                const int poy = tc.ty * 4 + (ppx >> 3), pox = tc.tx * kTile + (ppx & 7);
+                if (poy < q.Ho && pox < q.Wo) {
+                    const size_t u0 = (((size_t)tc.n * q.Ho + poy) * q.Wo + pox) * q.G + gq_unit;
+                    *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(goff) + u0 * 36 + chk * 16) =
+                        imat::lds128(stage_s + ppx * kStOffPx + chk * 16);
+                    *reinterpret_cast<uint2 *>(reinterpret_cast<char *>(gmask) + u0 * 18 + chk * 8) =
+                        lds64(stage_s + kStOffB + ppx * kStMaskPx + chk * 8);
+                }
             }
         }
         return;
@@ -531,7 +584,6 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         }
     }
     if (slowmask) {  // rare: points inside the map but outside the band's window (|offset * scale| >= 3 px)
-        pdl_wait();
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
             if (!((slowmask >> k) & 1u)) continue;
@@ -594,7 +646,6 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                         imat::pack2<T>(gw[i][1][0], gw[i][1][1]), imat::pack2<T>(gw[i][1][2], gw[i][1][3]));
         }
         __syncwarp();
-        pdl_wait();  // grad_input is zero from here on (zero_fill_kernel complete and visible)
         const int cell = lane >> 1, half = lane & 1;
         const int ix = wx0 + cell;
         const bool col_ok = (unsigned)ix < (unsigned)q.W;

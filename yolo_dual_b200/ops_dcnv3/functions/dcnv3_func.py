@@ -150,7 +150,7 @@ def _backward(ctx, logits, grad_output):
         grad_offset = torch.empty_like(offset)
         grad_mask = torch.empty_like(mask)
         accum = _grad_accum
-        if accum == _lib.ACC_TILE and ((input.data_ptr() | grad_output.data_ptr()) & 15 or offset.data_ptr() & 3):
+        if accum == _lib.ACC_TILE and ((input.data_ptr() | grad_output.data_ptr() | offset.data_ptr()) & 15 or mask.data_ptr() & 7):
             accum = _lib.ACC_OPMATH  # views at odd byte offsets: the tile kernel needs 16-byte channel vectors
         ws_bytes = lib.dcnv3_b200_backward_workspace_bytes(dt, ctypes.byref(geo), accum)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=input.device) if ws_bytes else None
