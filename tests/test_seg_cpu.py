@@ -153,6 +153,45 @@ def test_data_parallel_step_world2_gloo(tmp_path):
     torch.testing.assert_close((r0["loss"] + r1["loss"]) / 2, (sum(losses) / 2).detach(), rtol=1e-5, atol=1e-6)
 
 
+def _trainer_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from yolo_dual_b200.trainer import Trainer
+        torch.manual_seed(0)
+        torch.set_num_threads(1)
+        model = SegModel(YOLOV5_SEG, dcn="none", img_size=(32, 32))
+        crit = SegmentationLoss(12, class_weights=CAMVID_CLASS_WEIGHTS)
+        t = Trainer(model, crit, batch_size=32, epochs=2, ema=True)   # nominal 64 -> accumulate = 2
+        assert t.accumulate == 2 and hasattr(t.model, "no_sync")
+        gen = torch.Generator().manual_seed(10 + rank)
+        stepped = []
+        for _ in range(4):  # micro-steps 1 and 3 run inside no_sync(): no all-reduce, gradients accumulate locally
+            x = torch.randn(2, 3, 32, 32, generator=gen)
+            y = torch.randint(0, 12, (2, 32, 32), generator=gen)
+            stepped.append(t.micro_step(x, y)[2])
+        torch.save({"stepped": stepped, "w": {k: v.clone() for k, v in model.state_dict().items()}, "ema": t.ema.updates},
+                   os.path.join(tmp, f"t{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_trainer_accumulates_under_ddp_world2_gloo(tmp_path):
+    """Trainer + DDP + gradient accumulation (the first backward runs inside no_sync(): DDP(static_graph=True) asserts
+    there — found on the GPU box under NCCL, pinned here over gloo): optimizer steps every second micro-step, weights
+    identical on both ranks afterwards although the ranks saw different data."""
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_trainer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "t0.pt"), torch.load(tmp_path / "t1.pt")
+    assert r0["stepped"] == [False, True, False, True] == r1["stepped"] and r0["ema"] == 2
+    for k, v in r0["w"].items():
+        if v.dtype.is_floating_point and "running_" not in k:  # BatchNorm statistics are per rank (no SyncBN)
+            assert torch.equal(v, r1["w"][k]), k
+
+
 @pytest.mark.parametrize("cfg", [YOLOV5_SEG, YOLOV8_SEG], ids=["v5", "v8"])
 def test_deferred_upsample_is_the_reference_order(cfg):
     """The pointwise tail (1x1 Conv + BN(train) + SiLU, channel Softmax) commutes with the last nearest Upsample:

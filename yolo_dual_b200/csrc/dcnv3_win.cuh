@@ -64,7 +64,10 @@ constexpr int kStOffB = 32 * kStOffPx;                   // 5 120 B
 constexpr int kStMaskB = 32 * kStMaskPx;                 // 2 560 B
 constexpr int kStageB = kStOffB + kStMaskB;
 constexpr int kStageOff = kScatB > kDwinB ? kScatB : kDwinB;  // behind either role's buffers
-constexpr int kSmemB = kStageOff + kStageB;              // 65 088 B: still three CTAs per SM
+#ifndef DCNV3_WIN_EXTRA_SMEM
+#define DCNV3_WIN_EXTRA_SMEM 0  // occupancy experiments: pad the CTA's shared memory (profiles/r02_bwd_kernel_history.md)
+#endif
+constexpr int kSmemB = kStageOff + kStageB + DCNV3_WIN_EXTRA_SMEM;  // 65 088 B: still three CTAs per SM
 #ifndef DCNV3_WIN_PREFETCH_UNITS
 #define DCNV3_WIN_PREFETCH_UNITS 320
 #endif

@@ -417,7 +417,7 @@ def shard_batch(n_global: int, rank: int, world: int):
 
 
 def wrap_ddp(model: nn.Module, device=None, bucket_cap_mb: Optional[float] = None, grad_compress: Optional[str] = None,
-             first_bucket_mb: Optional[float] = None):
+             first_bucket_mb: Optional[float] = None, static_graph: bool = True):
     """smart_DDP (utils/torch_utils.py:55-63): DDP with static_graph when a process group is up.
 
     Additions (all off by default = the reference's plain DDP): `bucket_cap_mb` sizes the gradient buckets (DDP's 25 MB
@@ -435,7 +435,11 @@ def wrap_ddp(model: nn.Module, device=None, bucket_cap_mb: Optional[float] = Non
         kw["bucket_cap_mb"] = bucket_cap_mb
     if first_bucket_mb:
         dist._DEFAULT_FIRST_BUCKET_BYTES = int(first_bucket_mb * 1024 * 1024)  # read by DDP's constructor
-    ddp = DDP(model, device_ids=ids, static_graph=True, gradient_as_bucket_view=True, **kw)  # grads live in the buckets
+    # static_graph (smart_DDP's choice) cannot be combined with a first iteration inside no_sync() (reducer.cpp asserts
+    # expect_autograd_hooks_): callers that accumulate gradients pass static_graph=False (Trainer does)
+    # (the layer tables compute layers whose outputs nobody reads: without static_graph DDP has to look for unused parameters)
+    ddp = DDP(model, device_ids=ids, static_graph=static_graph, find_unused_parameters=not static_graph,
+              gradient_as_bucket_view=True, **kw)  # grads live in the buckets
     if grad_compress == "bf16":
         from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
         ddp.register_comm_hook(None, default_hooks.bf16_compress_hook)

@@ -78,10 +78,12 @@ class Trainer:
             if device is not None:
                 model = model.to(device)
         self.raw_model = model
-        self.model = wrap_ddp(model, device)
+        self.accumulate = max(round(NOMINAL_BATCH / batch_size), 1)
+        # found by running this class under NCCL (bench.py trainer_smoke): DDP(static_graph=True) asserts when its first
+        # backward runs inside no_sync(), which is exactly what gradient accumulation does
+        self.model = wrap_ddp(model, device, static_graph=self.accumulate == 1)
         self.criterion = criterion
         self.epochs = epochs
-        self.accumulate = max(round(NOMINAL_BATCH / batch_size), 1)
         wd = self.hyp["weight_decay"] * batch_size * self.accumulate / NOMINAL_BATCH
         self.optimizer = smart_optimizer(self.model, self.hyp["lr0"], self.hyp["momentum"], wd)
         self.scheduler = torch.optim.lr_scheduler.LambdaLR(self.optimizer, lr_lambda(epochs, self.hyp["lrf"], cos_lr))
