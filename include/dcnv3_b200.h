@@ -92,7 +92,9 @@ enum {
     DCNV3_B200_EALIGN = -3,    /* buffer not aligned for the vector path (16 B) */
     DCNV3_B200_EWORKSPACE = -4,/* workspace missing or too small */
     DCNV3_B200_ERANGE = -5,    /* a tensor has >= 2^31 * 16 B addressable units */
-    DCNV3_B200_EDEVICE = -6    /* no sm_100 device / wrong device */
+    DCNV3_B200_EDEVICE = -6,   /* no sm_100 device / wrong device */
+    DCNV3_B200_ENOTSUP = -7    /* the *_packed entry points only: shape / dtype / alignment outside what the staged-window
+                                  kernels take; nothing was launched, call the unpacked entry points instead */
 };
 
 /* geometry shared by every call (reference argument order kept:
@@ -139,6 +141,19 @@ int dcnv3_b200_backward(const void *input, const void *offset, const void *mask,
                         void *grad_mask, void *workspace, size_t workspace_bytes,
                         int dtype, const dcnv3_b200_geometry *geo, int mask_is_logits,
                         int grad_accum, void *cuda_stream);
+
+/* Packed sampling heads (no reference counterpart; LIB/modules/dcnv3.py:121-123 computes offset and mask with two
+ * Linear layers).  `heads` is ONE tensor [N, Ho, Wo, 3*G*P] in the storage dtype: per pixel the G*P*2 offsets in the
+ * reference's order followed by the G*P masks (or mask logits) — the output of a single Linear(C, 3*G*P) whose weight is
+ * the two heads' weights stacked.  The kernels read it with a pixel pitch, so the split costs no copy, and the backward
+ * writes `grad_heads` in the same layout, so the Linear's backward sees one tensor.  16-bit storage, group_channels = 16,
+ * 3x3 s1 d1, group % 8 == 0 (16-byte pixel pitch), 16-byte aligned buffers; grad_input accumulates as ACC_TILE (no
+ * workspace).  Anything else: ENOTSUP, nothing launched — split the tensor and call the functions above. */
+int dcnv3_b200_forward_packed(const void *input, const void *heads, void *output, int dtype,
+                              const dcnv3_b200_geometry *geo, int mask_is_logits, void *cuda_stream);
+int dcnv3_b200_backward_packed(const void *input, const void *heads, const void *grad_output,
+                               void *grad_input, void *grad_heads, int dtype,
+                               const dcnv3_b200_geometry *geo, int mask_is_logits, void *cuda_stream);
 
 /* The integer contract, exposed for parity tests: for every (n, ho, wo, g, p)
  *   hw_low [N,Ho,Wo,G,P,2] int32 = (h_low, w_low)   (dcnv3_im2col_cuda.cuh:39-40)

@@ -12,6 +12,7 @@ from .build import LIB
 
 F32, F16, BF16, F64 = 0, 1, 2, 3
 ACC_OPMATH, ACC_STORAGE, ACC_TILE = 0, 1, 2
+ENOTSUP = -7
 
 SYMBOLS = (
     "dcnv3_b200_version",
@@ -22,6 +23,8 @@ SYMBOLS = (
     "dcnv3_b200_backward_workspace_bytes",
     "dcnv3_b200_backward",
     "dcnv3_b200_debug_indices",
+    "dcnv3_b200_forward_packed",
+    "dcnv3_b200_backward_packed",
 )
 
 
@@ -58,6 +61,8 @@ def load() -> ctypes.CDLL:
     lib.dcnv3_b200_backward_workspace_bytes.restype = ctypes.c_size_t
     lib.dcnv3_b200_backward.argtypes = [vp] * 8 + [ctypes.c_size_t, ip, gp, ip, ip, vp]
     lib.dcnv3_b200_debug_indices.argtypes = [vp, vp, vp, ip, gp, vp]
+    lib.dcnv3_b200_forward_packed.argtypes = [vp, vp, vp, ip, gp, ip, vp]
+    lib.dcnv3_b200_backward_packed.argtypes = [vp, vp, vp, vp, vp, ip, gp, ip, vp]
     _lib = lib
     return lib
 

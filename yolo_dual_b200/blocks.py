@@ -40,27 +40,28 @@ class DCNV3_YoLo(nn.Module):
     """1x1 Conv -> NHWC -> DCNv3 -> NCHW (common and yolo.py:2-13)."""
 
     def __init__(self, inc, ouc, k=1, s=1, p=None, g=1, d=1, act=True, dcn_group=None,
-                 fused_softmax=False):
+                 fused_softmax=False, packed_heads=False):
         super().__init__()
         self.conv = Conv(inc, ouc, k=1)
         self.dcnv3 = DCNv3(ouc, kernel_size=k, stride=s, group=_pick_group(ouc, g, dcn_group),
-                           dilation=d, fused_softmax=fused_softmax)
+                           dilation=d, fused_softmax=fused_softmax, packed_heads=packed_heads)
 
     def forward(self, x):
-        x = self.conv(x)
-        x = x.permute(0, 2, 3, 1)
-        x = self.dcnv3(x.contiguous())
-        return x.permute(0, 3, 1, 2)
+        x = self.conv(x).permute(0, 2, 3, 1)   # NHWC view
+        if not x.is_contiguous():              # a channels-last model never gets here: the view is already dense NHWC
+            x = x.contiguous()                 # (NCHW-contiguous model: the reference's permute + copy)
+        return self.dcnv3(x).permute(0, 3, 1, 2)   # NCHW view of the NHWC result = a channels-last tensor, no copy
 
 
 class Bottleneck_DCNV3(nn.Module):
     """cv1 1x1 -> DCNV3_YoLo 3x3, residual when shapes allow (common and yolo.py:15-25)."""
 
-    def __init__(self, c1, c2, shortcut=True, g=1, e=0.5, dcn_group=None, fused_softmax=False):
+    def __init__(self, c1, c2, shortcut=True, g=1, e=0.5, dcn_group=None, fused_softmax=False, packed_heads=False):
         super().__init__()
         c_ = int(c2 * e)
         self.cv1 = Conv(c1, c_, 1, 1)
-        self.cv2 = DCNV3_YoLo(c_, c2, 3, 1, g=g, dcn_group=dcn_group, fused_softmax=fused_softmax)
+        self.cv2 = DCNV3_YoLo(c_, c2, 3, 1, g=g, dcn_group=dcn_group, fused_softmax=fused_softmax,
+                              packed_heads=packed_heads)
         self.add = shortcut and c1 == c2
 
     def forward(self, x):
@@ -70,14 +71,14 @@ class Bottleneck_DCNV3(nn.Module):
 class C3_DCNV3(nn.Module):
     """CSP bottleneck with 3 convolutions, DCNv3 inner blocks (common and yolo.py:27-38)."""
 
-    def __init__(self, c1, c2, n=1, shortcut=True, g=1, e=0.5, dcn_group=None, fused_softmax=False):
+    def __init__(self, c1, c2, n=1, shortcut=True, g=1, e=0.5, dcn_group=None, fused_softmax=False, packed_heads=False):
         super().__init__()
         c_ = int(c2 * e)
         self.cv1 = Conv(c1, c_, 1, 1)
         self.cv2 = Conv(c1, c_, 1, 1)
         self.cv3 = Conv(2 * c_, c2, 1)
         self.m = nn.Sequential(*(Bottleneck_DCNV3(c_, c_, shortcut, g, e=1.0, dcn_group=dcn_group,
-                                                  fused_softmax=fused_softmax) for _ in range(n)))
+                                                  fused_softmax=fused_softmax, packed_heads=packed_heads) for _ in range(n)))
 
     def forward(self, x):
         return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), 1))
@@ -86,13 +87,13 @@ class C3_DCNV3(nn.Module):
 class C2f_DCNV3(nn.Module):
     """Derived block (see module docstring): YOLOv8 C2f with DCNv3 inner blocks."""
 
-    def __init__(self, c1, c2, n=1, shortcut=False, g=1, e=0.5, dcn_group=None, fused_softmax=False):
+    def __init__(self, c1, c2, n=1, shortcut=False, g=1, e=0.5, dcn_group=None, fused_softmax=False, packed_heads=False):
         super().__init__()
         self.c = int(c2 * e)
         self.cv1 = Conv(c1, 2 * self.c, 1, 1)
         self.cv2 = Conv((2 + n) * self.c, c2, 1)
         self.m = nn.ModuleList(Bottleneck_DCNV3(self.c, self.c, shortcut, g, e=1.0, dcn_group=dcn_group,
-                                                fused_softmax=fused_softmax) for _ in range(n))
+                                                fused_softmax=fused_softmax, packed_heads=packed_heads) for _ in range(n))
 
     def forward(self, x):
         y = list(self.cv1(x).chunk(2, 1))

@@ -78,6 +78,8 @@ int make_geo(const dcnv3_b200_geometry *g, Geo &q) {
         return fail(DCNV3_B200_EINVAL, "kernel window larger than the padded input (Ho=%d Wo=%d)",
                     q.Ho, q.Wo);
     q.P = q.kh * q.kw;
+    q.opitch = q.G * q.P * 2;  // separate, dense offset / mask tensors (dcnv3_b200_*_packed overrides these)
+    q.mpitch = q.G * q.P;
     q.half_h = (q.dh * (q.kh - 1)) >> 1;
     q.half_w = (q.dw * (q.kw - 1)) >> 1;
     // per-image element counts are addressed with 32-bit ints inside the kernels
@@ -316,6 +318,7 @@ bool win_eligible(const Geo &q, const void *in, const void *off, const void *mas
     // offsets / masks move as 16- / 8-byte chunks (4 groups of a pixel: 144 / 72 contiguous bytes)
     if (!aligned16(off) || !aligned16(goff) || (reinterpret_cast<uintptr_t>(mask) & 7u) ||
         (reinterpret_cast<uintptr_t>(gmask) & 7u)) return false;
+    if ((q.opitch * 2) % 16 || (q.mpitch * 2) % 8) return false;  // packed heads: every pixel's run starts on a chunk boundary
     const unsigned long long blocks = (unsigned long long)q.N * ((q.Ho + 3) / 4) * ((q.Wo + 7) / 8) * (q.G / imat::kWarps);
     if (blocks == 0 || blocks >= (1ull << 30)) return false;
     // the far-band fallback indexes (pixel, 8-channel vector) lanes with 32 bits
@@ -342,20 +345,20 @@ int launch_bwd_win(const T *in, const T *off, const T *mask, const T *gout, T *g
 // ------------------------------------------------------------------ forward
 template <typename T>
 int forward_t(const void *in_, const void *off_, const void *mask_, void *out_, const Geo &q,
-              bool logits, cudaStream_t st) {
+              bool logits, cudaStream_t st, bool packed = false) {
     const T *in = (const T *)in_, *off = (const T *)off_, *mask = (const T *)mask_;
     T *out = (T *)out_;
     const size_t n_pix = (size_t)q.N * q.Ho * q.Wo;
     if (n_pix == 0) return 0;
     if constexpr (sizeof(T) == 2) {
         const int fam = knobs().fwd;
-        if (fam == 3 && imat_eligible<T>(q, {in_, out_}, off_))
+        if (fam == 3 && !packed && imat_eligible<T>(q, {in_, out_}, off_))
             return launch_fwd_imat<T>(in, off, mask, out, q, logits, st);
         // Default for the C3-DCN shapes (16-bit, group_channels = 16, 3x3 s1 d1, G % 4 = 0): the forward from a
         // staged window (imat::fwd_tile_kernel), unless the map wastes more than 40 % of its 8x8 tiles.
         // DCNV3_B200_FWD=vec forces the vector kernel, =win this one.
         const long long tiles64 = 64ll * ((q.Ho + 7) / 8) * ((q.Wo + 7) / 8);
-        if ((fam == 5 || (fam == 0 && 10ll * q.Ho * q.Wo >= 6ll * tiles64)) && imat_eligible<T>(q, {in_, out_}, off_) &&
+        if ((packed || fam == 5 || (fam == 0 && 10ll * q.Ho * q.Wo >= 6ll * tiles64)) && imat_eligible<T>(q, {in_, out_}, off_) &&
             !(reinterpret_cast<uintptr_t>(mask_) & 1u) && q.N <= 65535 && (q.Ho + 7) / 8 <= 65535) {
             const int tiles_y = (q.Ho + 7) / 8, tiles_x = (q.Wo + 7) / 8, GQ = q.G / imat::kWarps;
             const dim3 grid((unsigned)(tiles_x * GQ), (unsigned)tiles_y, (unsigned)q.N);
@@ -369,6 +372,7 @@ int forward_t(const void *in_, const void *off_, const void *mask_, void *out_, 
             }
             return 0;
         }
+        if (packed) return fail(DCNV3_B200_ENOTSUP, "packed heads: this shape / alignment does not take the staged-window forward");
         // opt-in (DCNV3_B200_FWD=pts): the point-split kernel — 25 % fewer instructions, measured SLOWER
         // (P3 98.7 vs 82.3 us): a lane's 32-byte LDG.256 costs L1 two passes where the channel-split
         // pair of 16-byte lanes shares one; the forward is bound by L1 wavefronts, not by issue slots
@@ -382,6 +386,7 @@ int forward_t(const void *in_, const void *off_, const void *mask_, void *out_, 
             return 0;
         }
     }
+    if (packed) return fail(DCNV3_B200_ENOTSUP, "packed heads need 16-bit storage");
     const Plan pl = plan_vec<T>(q, n_pix, logits, {in_, out_}, off_, sizeof(T));
     if constexpr (sizeof(T) <= 4) {
         if (pl.vec) {
@@ -525,7 +530,7 @@ int backward_launch(const T *in, const T *off, const T *mask, const T *gout, A *
 template <typename T>
 int backward_t(const void *in_, const void *off_, const void *mask_, const void *gout_,
                void *gin_, void *goff_, void *gmask_, void *ws, size_t ws_bytes, const Geo &q,
-               bool logits, int grad_accum, cudaStream_t st) {
+               bool logits, int grad_accum, cudaStream_t st, bool packed = false) {
     using M = typename OpMath<T>::type;
     const T *in = (const T *)in_, *off = (const T *)off_, *mask = (const T *)mask_;
     const T *gout = (const T *)gout_;
@@ -540,17 +545,19 @@ int backward_t(const void *in_, const void *off_, const void *mask_, const void 
         // tiles, no workspace.  Shapes it does not take fall through to ACC_OPMATH (which needs the workspace).
         if (grad_accum == DCNV3_B200_ACC_TILE) {
             const int fam = knobs().bwd;
-            if ((fam == 0 || fam == 5) && win_eligible<T>(q, in_, off_, mask_, gout_, gin_, goff_, gmask_)) {
+            if ((packed || fam == 0 || fam == 5) && win_eligible<T>(q, in_, off_, mask_, gout_, gin_, goff_, gmask_)) {
                 launch(win::zero_fill_kernel, 148 * 4, 256, 0, st, reinterpret_cast<uint4 *>(gin), n_in * sizeof(T) / 16);
                 if (n_pix == 0) return 0;
                 return launch_bwd_win<T>(in, off, mask, gout, gin, goff, gmask, q, logits, st);
             }
+            if (packed) return fail(DCNV3_B200_ENOTSUP, "packed heads: this shape / alignment does not take the window backward");
             if (win_geometry(q) && (!ws || ws_bytes == 0))
                 return fail(DCNV3_B200_EALIGN, "ACC_TILE needs 16-byte aligned input / grad_output / grad_input / offset / "
                                                "grad_offset (8-byte mask / grad_mask); pass an ACC_OPMATH workspace to fall back");
             grad_accum = DCNV3_B200_ACC_OPMATH;
         }
     }
+    if (packed) return fail(DCNV3_B200_ENOTSUP, "packed heads need 16-bit storage and grad_accum = ACC_TILE");
     if (lowp && grad_accum == DCNV3_B200_ACC_OPMATH) {
         // reference semantics (dcnv3_cuda.cu:126-133,168-170): fp32 accumulation, one rounding
         const size_t acc_bytes = (n_in * sizeof(float) + 255) & ~(size_t)255;
@@ -675,6 +682,52 @@ int dcnv3_b200_forward(const void *input, const void *offset, const void *mask, 
     }
     if (rc) return rc;
     return finish(st, "dcnv3_b200_forward launch");
+}
+
+// offsets and mask (logits) of a pixel side by side in ONE tensor [N, Ho, Wo, 3*G*P] — the output of a single Linear
+int dcnv3_b200_forward_packed(const void *input, const void *heads, void *output, int dtype,
+                              const dcnv3_b200_geometry *geo, int mask_is_logits, void *cuda_stream) {
+    g_err[0] = 0;
+    Geo q;
+    int rc = make_geo(geo, q);
+    if (rc) return rc;
+    if (dtype != DCNV3_B200_F16 && dtype != DCNV3_B200_BF16) return fail(DCNV3_B200_ENOTSUP, "packed heads need 16-bit storage");
+    if (mask_is_logits != 0 && mask_is_logits != 1) return fail(DCNV3_B200_EINVAL, "mask_is_logits must be 0 or 1");
+    if (q.N == 0) return 0;
+    if (!input || !heads || !output) return fail(DCNV3_B200_ENULL, "null tensor pointer");
+    if ((rc = check_device())) return rc;
+    q.opitch = q.mpitch = 3 * q.G * q.P;
+    const void *mask = static_cast<const char *>(heads) + (size_t)2 * q.G * q.P * 2;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    rc = dtype == DCNV3_B200_F16 ? forward_t<__half>(input, heads, mask, output, q, mask_is_logits != 0, st, true)
+                                 : forward_t<__nv_bfloat16>(input, heads, mask, output, q, mask_is_logits != 0, st, true);
+    if (rc) return rc;
+    return finish(st, "dcnv3_b200_forward_packed launch");
+}
+
+int dcnv3_b200_backward_packed(const void *input, const void *heads, const void *grad_output, void *grad_input,
+                               void *grad_heads, int dtype, const dcnv3_b200_geometry *geo, int mask_is_logits,
+                               void *cuda_stream) {
+    g_err[0] = 0;
+    Geo q;
+    int rc = make_geo(geo, q);
+    if (rc) return rc;
+    if (dtype != DCNV3_B200_F16 && dtype != DCNV3_B200_BF16) return fail(DCNV3_B200_ENOTSUP, "packed heads need 16-bit storage");
+    if (mask_is_logits != 0 && mask_is_logits != 1) return fail(DCNV3_B200_EINVAL, "mask_is_logits must be 0 or 1");
+    if (q.N == 0) return 0;
+    if (!input || !heads || !grad_output || !grad_input || !grad_heads) return fail(DCNV3_B200_ENULL, "null tensor pointer");
+    if ((rc = check_device())) return rc;
+    q.opitch = q.mpitch = 3 * q.G * q.P;
+    const size_t mo = (size_t)2 * q.G * q.P * 2;
+    const void *mask = static_cast<const char *>(heads) + mo;
+    void *gmask = static_cast<char *>(grad_heads) + mo;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const bool lg = mask_is_logits != 0;
+    rc = dtype == DCNV3_B200_F16
+             ? backward_t<__half>(input, heads, mask, grad_output, grad_input, grad_heads, gmask, nullptr, 0, q, lg, DCNV3_B200_ACC_TILE, st, true)
+             : backward_t<__nv_bfloat16>(input, heads, mask, grad_output, grad_input, grad_heads, gmask, nullptr, 0, q, lg, DCNV3_B200_ACC_TILE, st, true);
+    if (rc) return rc;
+    return finish(st, "dcnv3_b200_backward_packed launch");
 }
 
 size_t dcnv3_b200_backward_workspace_bytes(int dtype, const dcnv3_b200_geometry *geo, int grad_accum) {

@@ -23,6 +23,10 @@ struct Geo {
     int Ho, Wo, P;
     int half_h, half_w;  // (dilation*(kernel-1)) >> 1, cuh:232,235
     float scale;         // offset_scale
+    // elements between one output pixel's offsets (masks) and the next pixel's: G*P*2 (G*P) for the reference's separate
+    // tensors, 3*G*P for the packed heads tensor [N,Ho,Wo, offsets | masks] (dcnv3_b200_*_packed).  Honoured by the
+    // kernels those entry points can reach: fwd_tile_kernel, bwd_win_kernel and the vector lane bodies inside them.
+    int opitch, mpitch;
 };
 
 // storage type -> op-math type (at::opmath_type, cuh:30): float for 16/32-bit, double for f64

@@ -1264,9 +1264,9 @@ fwd_tile_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
         oy[it] = tc.ty * kTile + (px >> 3);
         ox[it] = tc.tx * kTile + (px & 7);
         valid[it] = oy[it] < q.Ho && ox[it] < q.Wo;
-        const size_t unit = (((size_t)tc.n * q.Ho + oy[it]) * q.Wo + ox[it]) * q.G + g;
-        const uint32_t *po = reinterpret_cast<const uint32_t *>(off) + unit * 9;
-        const unsigned short *pm = reinterpret_cast<const unsigned short *>(mask) + unit * 9;
+        const size_t pixi = ((size_t)tc.n * q.Ho + oy[it]) * q.Wo + ox[it];
+        const uint32_t *po = reinterpret_cast<const uint32_t *>(off) + pixi * (q.opitch >> 1) + g * 9;
+        const unsigned short *pm = reinterpret_cast<const unsigned short *>(mask) + pixi * q.mpitch + g * 9;
 #pragma unroll
         for (int k = 0; k < 4; ++k) roff[it][k] = valid[it] ? __ldg(po + 4 * h + k) : 0u;
         roff[it][4] = valid[it] ? __ldg(po + 8) : 0u;

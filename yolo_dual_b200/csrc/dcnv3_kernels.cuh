@@ -153,9 +153,8 @@ __device__ __forceinline__ void fwd_vec_body(const VecCoord &c, const T *__restr
     const char *im = reinterpret_cast<const char *>(in + (size_t)c.n * q.H * q.W * q.C + c.v * CH);
     const int sC = q.C * (int)sizeof(T);  // byte strides of one pixel / one row
     const int sW = q.W * sC;
-    const size_t pg = (size_t)c.pix * q.G + c.g;
-    const T *po = off + pg * q.P * 2;
-    const T *pm = mask + pg * q.P;
+    const T *po = off + (size_t)c.pix * q.opitch + c.g * q.P * 2;
+    const T *pm = mask + (size_t)c.pix * q.mpitch + c.g * q.P;
 
     float mx = 0.f, inv = 1.f;
     if (LOGITS) softmax_stats<T, KP>(pm, q.P, mx, inv);
@@ -437,11 +436,11 @@ bwd_vec_lane(const VecCoord &c, const int lane_in_group, const bool active, cons
     const int sC = q.C * (int)sizeof(T), sW = q.W * sC;
     constexpr int ARATIO = (int)sizeof(A) / (int)sizeof(T) > 0 ? (int)sizeof(A) / (int)sizeof(T) : 1;
     static_assert(sizeof(A) >= sizeof(T), "");
-    const size_t pg = (size_t)c.pix * q.G + c.g;
-    const T *po = off + pg * q.P * 2;
-    const T *pm = mask + pg * q.P;
-    T *d_o = goff + pg * q.P * 2;
-    T *d_m = gmask + pg * q.P;
+    const size_t o_el = (size_t)c.pix * q.opitch + c.g * q.P * 2, m_el = (size_t)c.pix * q.mpitch + c.g * q.P;
+    const T *po = off + o_el;
+    const T *pm = mask + m_el;
+    T *d_o = goff + o_el;
+    T *d_m = gmask + m_el;
     const bool writer = active && lane_in_group == 0;
 
     // grad_output: this lane's channels (for the dots) ...

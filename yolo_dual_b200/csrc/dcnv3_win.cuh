@@ -308,9 +308,11 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
             const int ppx = warp * 4 + t / 9, chk = t % 9;
             const int poy = tc.ty * 4 + (ppx >> 3), pox = tc.tx * kTile + (ppx & 7);
             const bool ok = poy < q.Ho && pox < q.Wo;
-            const size_t u0 = (((size_t)tc.n * q.Ho + min(poy, q.Ho - 1)) * q.Wo + min(pox, q.Wo - 1)) * q.G + gq_unit;
-            imat::cp_async16(stage_s + ppx * kStOffPx + chk * 16, reinterpret_cast<const char *>(off) + u0 * 36 + chk * 16, ok ? 16 : 0);
-            cp_async8(stage_s + kStOffB + ppx * kStMaskPx + chk * 8, reinterpret_cast<const char *>(mask) + u0 * 18 + chk * 8, ok ? 8 : 0);
+            const size_t pp = ((size_t)tc.n * q.Ho + min(poy, q.Ho - 1)) * q.Wo + min(pox, q.Wo - 1);
+            imat::cp_async16(stage_s + ppx * kStOffPx + chk * 16,
+                             reinterpret_cast<const char *>(off) + (pp * q.opitch + gq_unit * 18) * 2 + chk * 16, ok ? 16 : 0);
+            cp_async8(stage_s + kStOffB + ppx * kStMaskPx + chk * 8,
+                      reinterpret_cast<const char *>(mask) + (pp * q.mpitch + gq_unit * 9) * 2 + chk * 8, ok ? 8 : 0);
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");  // group 0: this warp's offsets / masks
@@ -521,10 +523,10 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                 const int ppx = warp * 4 + t / 9, chk = t % 9;
                 const int poy = tc.ty * 4 + (ppx >> 3), pox = tc.tx * kTile + (ppx & 7);
                 if (poy < q.Ho && pox < q.Wo) {
-                    const size_t u0 = (((size_t)tc.n * q.Ho + poy) * q.Wo + pox) * q.G + gq_unit;
-                    *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(goff) + u0 * 36 + chk * 16) =
+                    const size_t pp = ((size_t)tc.n * q.Ho + poy) * q.Wo + pox;
+                    *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(goff) + (pp * q.opitch + gq_unit * 18) * 2 + chk * 16) =
                         imat::lds128(stage_s + ppx * kStOffPx + chk * 16);
-                    *reinterpret_cast<uint2 *>(reinterpret_cast<char *>(gmask) + u0 * 18 + chk * 8) =
+                    *reinterpret_cast<uint2 *>(reinterpret_cast<char *>(gmask) + (pp * q.mpitch + gq_unit * 9) * 2 + chk * 8) =
                         lds64(stage_s + kStOffB + ppx * kStMaskPx + chk * 8);
                 }
             }

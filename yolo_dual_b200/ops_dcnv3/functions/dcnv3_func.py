@@ -218,6 +218,97 @@ class DCNv3SoftmaxFunction(Function):
         return _backward(ctx, True, grad_output)
 
 
+class DCNv3PackedFunction(Function):
+    """``DCNv3PackedFunction.apply(input, heads, kernel_h, ..., offset_scale, im2col_step, mask_is_logits)``
+
+    `heads` [N, Ho, Wo, 3*G*P]: per pixel the G*P*2 offsets followed by the G*P masks (or mask logits) — the output of
+    ONE Linear(C, 3*G*P) holding the reference's two heads (LIB/modules/dcnv3.py:121-123) stacked.  The kernels read it
+    with a pixel pitch (no split copies) and the backward writes ONE `grad_heads` tensor in the same layout (no cat), so
+    the Linear's backward is a single pair of GEMMs.  Same arithmetic as DCNv3Function / DCNv3SoftmaxFunction with
+    grad_accum 'tile'.  Shapes the staged-window kernels do not take (not 16-bit, group_channels != 16, not 3x3 s1 d1,
+    group % 8, unaligned views) go through those two functions on split copies instead — same results."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, input, heads, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w,
+                group, group_channels, offset_scale, im2col_step, mask_is_logits):
+        geo = _geometry(input, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, group,
+                        group_channels, offset_scale)
+        P = int(kernel_h) * int(kernel_w)
+        n_off = group * P * 2
+        if heads.dim() != 4 or heads.shape[-1] != 3 * group * P:
+            raise RuntimeError(f"heads must be [N, Ho, Wo, {3 * group * P}], got {tuple(heads.shape)}")
+        Ho, Wo = _check_inputs(input, _FakeShape(heads, n_off), _FakeShape(heads, group * P), geo, im2col_step)
+        if tuple(heads.shape[:3]) != (input.shape[0], Ho, Wo):
+            raise RuntimeError(f"heads shape {tuple(heads.shape)} does not match the output size ({Ho}, {Wo})")
+        if not heads.is_contiguous():
+            raise RuntimeError("heads tensor has to be contiguous")
+        ctx.args = (kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, group,
+                    group_channels, offset_scale, im2col_step)
+        ctx.logits, ctx.n_off = bool(mask_is_logits), n_off
+        lib = _lib.load()
+        with torch.cuda.device_of(input):
+            output = torch.empty((input.shape[0], Ho, Wo, input.shape[3]), dtype=input.dtype, device=input.device)
+            rc = lib.dcnv3_b200_forward_packed(input.data_ptr(), heads.data_ptr(), output.data_ptr(),
+                                               _DTYPES[input.dtype], ctypes.byref(geo), int(ctx.logits),
+                                               _stream(input.device))
+        ctx.packed = rc == 0
+        if rc == _lib.ENOTSUP:  # split copies through the unpacked entry point (same kernels' generic siblings)
+            off, msk = heads[..., :n_off].contiguous(), heads[..., n_off:].contiguous()
+            with torch.cuda.device_of(input):
+                rc = lib.dcnv3_b200_forward(input.data_ptr(), off.data_ptr(), msk.data_ptr(), output.data_ptr(),
+                                            _DTYPES[input.dtype], ctypes.byref(geo), int(ctx.logits),
+                                            _stream(input.device))
+        _lib.check(rc, "dcnv3_b200_forward_packed")
+        ctx.save_for_backward(input, heads)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_output):
+        input, heads = ctx.saved_tensors
+        grad_output = grad_output.contiguous()
+        if grad_output.dtype != input.dtype:
+            grad_output = grad_output.to(input.dtype)
+        a = ctx.args
+        geo = _geometry(input, *a[:11])
+        lib = _lib.load()
+        rc = _lib.ENOTSUP
+        if ctx.packed and not ((input.data_ptr() | grad_output.data_ptr() | heads.data_ptr()) & 15):
+            with torch.cuda.device_of(input):
+                grad_input, grad_heads = torch.empty_like(input), torch.empty_like(heads)
+                rc = lib.dcnv3_b200_backward_packed(input.data_ptr(), heads.data_ptr(), grad_output.data_ptr(),
+                                                    grad_input.data_ptr(), grad_heads.data_ptr(),
+                                                    _DTYPES[input.dtype], ctypes.byref(geo), int(ctx.logits),
+                                                    _stream(input.device))
+        if rc == _lib.ENOTSUP:
+            class _C:  # the unpacked backward on split copies, gradients concatenated
+                pass
+            c = _C()
+            (c.kernel_h, c.kernel_w, c.stride_h, c.stride_w, c.pad_h, c.pad_w, c.dilation_h, c.dilation_w, c.group,
+             c.group_channels, c.offset_scale, c.im2col_step) = a
+            c.saved_tensors = (input, heads[..., :ctx.n_off].contiguous(), heads[..., ctx.n_off:].contiguous())
+            gi, go_, gm = _backward(c, ctx.logits, grad_output)[:3]
+            return (gi, torch.cat((go_, gm), -1)) + (None,) * 13
+        _lib.check(rc, "dcnv3_b200_backward_packed")
+        return (grad_input, grad_heads) + (None,) * 13
+
+
+class _FakeShape:
+    """Stands in for the offset / mask slice of a packed heads tensor in `_check_inputs` (shape algebra only)."""
+
+    def __init__(self, heads, width):
+        self._h, self.shape = heads, tuple(heads.shape[:3]) + (width,)
+        self.is_cuda, self.dtype, self.device = heads.is_cuda, heads.dtype, heads.device
+
+    def is_contiguous(self):
+        return True
+
+    def dim(self):
+        return 4
+
+
 def dcnv3_debug_indices(offset, H, W, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w,
                         dilation_h, dilation_w, group, offset_scale):
     """The integer contract of the kernels: (hw_low int32 [N,Ho,Wo,G,P,2], bounds uint8

@@ -15,6 +15,9 @@ Behaviour kept from the reference on purpose:
 
 Added here: `fused_softmax=True` hands the mask *logits* to the kernels, which apply the softmax over the
 K*K points of each group themselves, forward and backward (the reference calls F.softmax, dcnv3.py:122-123).
+`packed_heads=True` (needs `fused_softmax`) computes the offset and mask heads with ONE GEMM — the two Linear layers keep
+their parameters and names, their weights are stacked per call — and hands the [N, H, W, 3*G*K*K] result to the kernels
+as it is: no split copies in the forward, one `grad_heads` tensor (no cat) in the backward.
 """
 from __future__ import annotations
 
@@ -24,7 +27,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from ..functions import DCNv3Function, DCNv3SoftmaxFunction
+from ..functions import DCNv3Function, DCNv3PackedFunction, DCNv3SoftmaxFunction
 from .conv import Conv, autopad  # noqa: F401  (re-exported: the reference module exposes both names)
 
 IM2COL_STEP = 256  # what the reference module always passes (dcnv3.py:133); a no-op here
@@ -39,7 +42,7 @@ def _is_power_of_2(n):
 
 class DCNv3(nn.Module):
     def __init__(self, channels=64, kernel_size=3, stride=1, pad=1, dilation=1, group=4, offset_scale=1.0,
-                 act_layer='GELU', norm_layer='LN', fused_softmax=False):
+                 act_layer='GELU', norm_layer='LN', fused_softmax=False, packed_heads=False):
         """
         channels       C of the NHWC input (= group * group_channels)
         kernel_size    K: K*K sampling points per group
@@ -48,6 +51,7 @@ class DCNv3(nn.Module):
         group          G; group_channels = C // G — a multiple of 8 keeps the vector kernels
         offset_scale   scale applied to the learned offsets
         fused_softmax  softmax over the K*K points inside the CUDA kernels
+        packed_heads   offset + mask heads as one GEMM whose output the kernels read in place (needs fused_softmax)
         """
         super().__init__()
         if channels % group:
@@ -63,6 +67,10 @@ class DCNv3(nn.Module):
         self.dilation = 1
         self.offset_scale = offset_scale
         self.fused_softmax = bool(fused_softmax)
+        self.packed_heads = bool(packed_heads)
+        if self.packed_heads and not self.fused_softmax:
+            raise ValueError('packed_heads=True needs fused_softmax=True (an unfused softmax would have to rewrite the '
+                             'mask part of the packed tensor)')
 
         points = group * kernel_size * kernel_size
         self.dw_conv = Conv(channels, channels, kernel_size, g=channels)
@@ -94,9 +102,17 @@ class DCNv3(nn.Module):
         value = self.input_proj(input)
         # depthwise 3x3 works on NCHW views; with a channels-last model both permutes are free
         feat = self.dw_conv(input.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+        k, s, p, d = self.kernel_size, self.stride, self.pad, self.dilation
+        if self.packed_heads:  # one GEMM for both heads; the kernels split its output by address
+            heads = F.linear(feat, torch.cat((self.offset.weight, self.mask.weight), 0),
+                             torch.cat((self.offset.bias, self.mask.bias), 0))
+            if heads.dtype != value.dtype:
+                heads = heads.to(value.dtype)
+            sampled = DCNv3PackedFunction.apply(value.contiguous(), heads.contiguous(), k, k, s, s, p, p, d, d, self.group,
+                                                self.group_channels, self.offset_scale, IM2COL_STEP, True)
+            return self.output_proj(sampled)
         offset, mask = self._sampling_heads(feat, value.dtype)
         core = DCNv3SoftmaxFunction if self.fused_softmax else DCNv3Function
-        k, s, p, d = self.kernel_size, self.stride, self.pad, self.dilation
         sampled = core.apply(value.contiguous(), offset, mask, k, k, s, s, p, p, d, d,
                              self.group, self.group_channels, self.offset_scale, IM2COL_STEP)
         return self.output_proj(sampled)

@@ -201,7 +201,7 @@ class SegModel(nn.Module):
     """YOLOv5Seg / YOLOv8Seg of the reference (seg_diceloss_yolov5.py:511-659) over a layer table."""
 
     def __init__(self, cfg: Dict = YOLOV5_SEG, num_classes: Optional[int] = None, dcn: str = "dcnv3",
-                 dcn_group="gc16", fused_softmax: bool = False, outer_residual: bool = False,
+                 dcn_group="gc16", fused_softmax: bool = False, outer_residual: bool = False, packed_heads: bool = False,
                  img_size: Sequence[int] = (640, 640), defer_upsample: bool = True):
         """defer_upsample: run the pointwise tail of the head (1x1 Conv + BN + SiLU, channel Softmax) BEFORE the last
         nearest Upsample instead of after it.  Every one of those ops commutes with pixel replication — the batch
@@ -216,7 +216,7 @@ class SegModel(nn.Module):
         self.num_classes = cfg["nc"] if num_classes is None else num_classes
         self.img_size = list(img_size)
         self.dcn, self.dcn_group = dcn, dcn_group
-        self.fused_softmax, self.outer_residual = fused_softmax, outer_residual
+        self.fused_softmax, self.outer_residual, self.packed_heads = fused_softmax, outer_residual, packed_heads
         self.layers = nn.ModuleList()
         self.froms: List = []
         chs: List[int] = []
@@ -277,7 +277,7 @@ class SegModel(nn.Module):
             if self.dcn == "none":
                 return (C3 if is_c3 else C2f)(c1, c2, n), c2
             blk = (C3_DCNV3 if is_c3 else C2f_DCNV3)(c1, c2, n=max(n, 1), dcn_group=self.dcn_group,
-                                                     fused_softmax=self.fused_softmax)
+                                                     fused_softmax=self.fused_softmax, packed_heads=self.packed_heads)
             return _WithOuterResidual(blk, self.outer_residual and c1 == c2), c2
         if name == "SPPF":
             return SPPF(c1, *args), args[0]
