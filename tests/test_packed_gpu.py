@@ -58,13 +58,17 @@ def test_packed_equals_unpacked(case, dtype, sigma, logits):
     yb = DCNv3PackedFunction.apply(xb, heads, *args, logits)
     yb.backward(go)
     torch.cuda.synchronize()
-    assert torch.equal(ya, yb)
+    if 10 * H * W >= 6 * 64 * ((H + 7) // 8) * ((W + 7) // 8):
+        assert torch.equal(ya, yb)      # both sides ran the staged-window forward: same arithmetic, other addresses
+    else:  # the unpacked call takes the vector kernel on maps that fill < 60 % of their 8x8 tiles (fp32 corner weights)
+        torch.testing.assert_close(yb.float(), ya.float(), rtol=1e-2, atol=1e-2)
     n_off = G * 18
     eps = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
     scale = lambda t: max(1.0, float(t.float().abs().max()))
     # grad_offset / grad_mask: one writer per element, same arithmetic
     torch.testing.assert_close(heads.grad[..., :n_off].float(), a[1].grad.float(), rtol=0, atol=0)
     torch.testing.assert_close(heads.grad[..., n_off:].float(), a[2].grad.float(), rtol=0, atol=0)
+    assert heads.grad.is_contiguous() and heads.grad.shape == heads.shape
     s = scale(a[0].grad)
     torch.testing.assert_close(xb.grad.float() / s, a[0].grad.float() / s, rtol=0, atol=8 * eps)
 

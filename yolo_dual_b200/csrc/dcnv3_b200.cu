@@ -325,12 +325,13 @@ bool win_eligible(const Geo &q, const void *in, const void *off, const void *mas
     return (unsigned long long)q.N * q.Ho * q.Wo * (q.C / 8) < (1ull << 31);
 }
 
-// one launch: CTA 2u = grad_offset / grad_mask of unit u, CTA 2u + 1 = its grad_input (dcnv3_win.cuh)
+// one launch, one CTA per unit (image, 4-row band, 8-column tile, group quad): grad_offset / grad_mask, then grad_input
+// over the same shared memory (dcnv3_win.cuh)
 template <typename T>
 int launch_bwd_win(const T *in, const T *off, const T *mask, const T *gout, T *gin, T *goff, T *gmask,
                    const Geo &q, bool logits, cudaStream_t st) {
     const int tiles_x = (q.Wo + 7) / 8, bands_y = (q.Ho + 3) / 4, GQ = q.G / imat::kWarps;
-    const unsigned grid = 2u * (unsigned)((size_t)q.N * bands_y * tiles_x * GQ);
+    const unsigned grid = (unsigned)((size_t)q.N * bands_y * tiles_x * GQ);
     int rc;
     if (logits) {
         if ((rc = set_smem(win::bwd_win_kernel<T, true>, win::kSmemB, "cudaFuncSetAttribute(bwd_win_kernel)"))) return rc;

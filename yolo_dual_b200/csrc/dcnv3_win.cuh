@@ -74,6 +74,7 @@ constexpr int kSmemB = kStageOff + kStageB + DCNV3_WIN_EXTRA_SMEM;  // 65 088 B:
 constexpr unsigned kPrefetchUnits = DCNV3_WIN_PREFETCH_UNITS;  // L2 prefetch distance in units (~2/3 of a wave of 444 CTAs apart... see bwd_win_kernel)
 constexpr int kFarLanes = kThreadsW / 4;                 // a band is "far" when more lanes than this see a >= 3 px offset
 static_assert(kWmB % 16 == 0 && kGrpB % 16 == 0 && kRowB % 16 == 0, "ldmatrix rows are 16-byte aligned");
+static_assert(kDwinB % (16 * kThreadsW) == 0 && kDwinB <= kWmB, "the window aliases the start of the interpolation matrix");
 
 using imat::Mix;
 
@@ -253,10 +254,16 @@ __device__ __forceinline__ int slot_i(int k, int h) { return k == 4 ? 2 : (h ? (
 __device__ __forceinline__ int slot_j(int k, int h) { return k == 4 ? 2 : (h ? (4 + k) % 3 : k % 3); }
 
 // ===========================================================================================================
-// One launch, two kinds of CTA.  Unit u = (image, 4-row band, 8-column tile, group quad); CTA 2u computes the
-// unit's grad_offset / grad_mask ("dots" role: needs the 12x16-cell window, 24 KB), CTA 2u + 1 its grad_input
-// ("scatter" role: interpolation matrix + grad_output, 57 KB).  The two roles stress different pipes (FMA / issue
-// versus shared-memory wavefronts) and neighbours in blockIdx order land on the same SM three at a time.
+// One CTA per unit u = (image, 4-row band, 8-column tile, group quad), two phases in sequence:
+//   1. "dots"    grad_offset / grad_mask from the staged 12x16-cell window (24 KB at the start of shared memory);
+//   2. "scatter" grad_input: the interpolation matrix (51 KB) is built OVER the window once every warp has left phase 1,
+//                expanded by the tensor cores and flushed.
+// Round 2 first ran the two phases as two CTAs of one launch (CTA 2u / 2u + 1: 190.5 us at P3).  The occupancy
+// experiment (profiles/r02_bwd_kernel_history.md: T = 117 us + 226 us / CTAs per SM) showed two thirds of that CTA
+// lifetime to be latency — first loads, barriers, dependent chains — that only co-resident work hides.  With the phases
+// in ONE CTA the shared-memory footprint is the same 65 KB (the buffers alias), three CTAs per SM still fit, but each
+// now carries a whole unit: twice the work in flight per SM, one prologue (unit decode, offset / mask / grad_output
+// loads, far-band vote) instead of two.
 // ===========================================================================================================
 __device__ __forceinline__ void stmatrix_x4(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
     asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
@@ -281,10 +288,9 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     __shared__ __align__(16) uint32_t smax[8];
     pdl_enter();  // (waiting only in front of the first grad_input access instead measured nothing: 190.4 vs 191.0 us at P3)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool dots_role = (blockIdx.x & 1u) == 0u;
     TileCoord tc;  // (image, band row, tile column, group quad)
     {
-        unsigned b = blockIdx.x >> 1;
+        unsigned b = blockIdx.x;
         tc.gq = (int)(b % (unsigned)GQ); b /= (unsigned)GQ;
         tc.tx = (int)(b % (unsigned)tiles_x); b /= (unsigned)tiles_x;
         tc.ty = (int)(b % (unsigned)bands_y);
@@ -316,7 +322,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");  // group 0: this warp's offsets / masks
-    if (dots_role) {  // stage the 12x16-cell x 64-channel window, unswizzled; zero outside the map
+    {  // stage the 12x16-cell x 64-channel window, unswizzled; zero outside the map
         const int ch = tid & 7, col = (tid >> 3) & 15, r0 = tid >> 7;
         const int ix = wx0 + col;
         const bool col_ok = (unsigned)ix < (unsigned)q.W;
@@ -331,12 +337,13 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
             p += step; dst += 2 * kWinW * 128; iy += 2;
         }
         asm volatile("cp.async.commit_group;" ::: "memory");  // group 1: the window (needed behind barrier A)
-    } else {          // zero the interpolation matrix
+    }
+    {   // zero the part of the interpolation matrix that lies behind the window (the rest: after phase 1)
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-        for (int i = 0; i < (kWmB / 16 + kThreadsW - 1) / kThreadsW; ++i) {
+        for (int i = 0; i < ((kWmB - kDwinB) / 16 + kThreadsW - 1) / kThreadsW; ++i) {
             const int id = i * kThreadsW + tid;
-            if (id < kWmB / 16) sts128(smem_s + id * 16, z);
+            if (id < (kWmB - kDwinB) / 16) sts128(smem_s + kDwinB + id * 16, z);
         }
     }
 
@@ -352,10 +359,9 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     uint4 g_own = make_uint4(0u, 0u, 0u, 0u), g_oth = g_own;
     if (valid) {  // in flight while the staging copies land
         g_own = __ldg(gp + h);
-        if (dots_role) g_oth = __ldg(gp + (h ^ 1));
+        g_oth = __ldg(gp + (h ^ 1));
     }
-    if (dots_role) asm volatile("cp.async.wait_group 1;" ::: "memory");
-    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncwarp();  // this warp's offsets / masks are staged (the window may still be in flight)
 
     // ---- this lane's offsets of points 4h..4h+3 and 8, their masks (all nine for the softmax), grad_output
@@ -373,29 +379,6 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         for (int k = 0; k < 4; ++k) rm[k] = imat::half_to_float<T>((unsigned short)lds16(sm_l + (4 * h + k) * 2));
         rm[4] = imat::half_to_float<T>((unsigned short)lds16(sm_l + 16));
     }
-#ifdef DCNV3_WIN_PREFETCH  // measured SLOWER (P3 195.0 vs 191.0 us at any distance, profiles/r02_bwd_kernel_history.md): off by default
-    // The CTAs of a unit are short (~2 k cycles) and begin with a round trip to DRAM for offsets / masks / grad_output.
-    // A dots CTA therefore asks L2 for the lines of the unit that starts ~kPrefetchUnits later (both of its CTAs profit):
-    // per pixel the 144-byte offset chunk (two lines), the 72-byte mask chunk (two) and the 128-byte grad_output slab.
-    if (dots_role && tid < 160) {
-        unsigned b = (blockIdx.x >> 1) + kPrefetchUnits;
-        TileCoord pc;
-        pc.gq = (int)(b % (unsigned)GQ); b /= (unsigned)GQ;
-        pc.tx = (int)(b % (unsigned)tiles_x); b /= (unsigned)tiles_x;
-        pc.ty = (int)(b % (unsigned)bands_y);
-        pc.n = (int)(b / (unsigned)bands_y);
-        const int pp = tid & 31, which = tid >> 5;
-        const int poy = pc.ty * 4 + (pp >> 3), pox = pc.tx * kTile + (pp & 7);
-        if (pc.n < q.N && poy < q.Ho && pox < q.Wo) {
-            const size_t ppix = ((size_t)pc.n * q.Ho + poy) * q.Wo + pox;
-            const char *a;
-            if (which < 2) a = reinterpret_cast<const char *>(off + (ppix * q.G + pc.gq * kWarps) * 18) + which * 143;
-            else if (which < 4) a = reinterpret_cast<const char *>(mask + (ppix * q.G + pc.gq * kWarps) * 9) + (which - 2) * 71;
-            else a = reinterpret_cast<const char *>(gout + ppix * q.C + pc.gq * 64);
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-        }
-    }
-#endif
     if constexpr (kScaled) {  // scatter role: largest |grad_output| of the band (bf16 magnitudes compare like integers)
         const uint32_t w[4] = {g_own.x, g_own.y, g_own.z, g_own.w};
         uint32_t mx = 0u;
@@ -407,16 +390,14 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         mx = __reduce_max_sync(0xffffffffu, mx);
         if (lane == 0) smax[warp] = mx;
     }
-    if (dots_role) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     // barrier A: the window is staged / Wm is zero and the per-warp maxima are visible.  A far band is skipped by the
     // dots CTA and handled as a whole by the scatter CTA (same count in both: same lanes, same offsets).
     const bool far_band = __syncthreads_count(lane_far<T>(roff, q.scale)) > kFarLanes;
     if (far_band) {
-        if (!dots_role) {  // the vector family's lane body computes all three gradients of the band
-            VecCoord c;
-            c.pix = (unsigned)pix; c.v = tc.gq * 8 + sub; c.g = g; c.n = tc.n; c.ho = cy; c.wo = cx;
-            bwd_far_lane<T, LOGITS>(c, h, valid, in, off, mask, gout, gin, goff, gmask, q);
-        }
+        VecCoord c;  // the vector family's lane body computes all three gradients of the band
+        c.pix = (unsigned)pix; c.v = tc.gq * 8 + sub; c.g = g; c.n = tc.n; c.ho = cy; c.wo = cx;
+        bwd_far_lane<T, LOGITS>(c, h, valid, in, off, mask, gout, gin, goff, gmask, q);
         return;
     }
 
@@ -433,8 +414,8 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         for (int k = 0; k < 5; ++k) mk[k] = rm[k];
     }
 
-    if (dots_role) {
-        // =================================================================== grad_offset / grad_mask
+    {
+        // =================================================================== phase 1: grad_offset / grad_mask
         const uint32_t own16 = (uint32_t)sub << 4, oth16 = (uint32_t)(sub ^ 1) << 4;
         const T *img_g = in + img_off + gl * 16;
         uint32_t win_s = smem_s;
@@ -531,10 +512,15 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                 }
             }
         }
-        return;
     }
 
-    // ======================================================================= grad_input
+    // ======================================================================= phase 2: grad_input
+    __syncthreads();  // barrier C: every warp has left the window
+    {   // zero the part of the interpolation matrix that aliases it
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int i = 0; i < kDwinB / 16 / kThreadsW; ++i) sts128(smem_s + (i * kThreadsW + tid) * 16, z);
+    }
     const uint32_t wm_s = smem_s, gos_base = smem_s + kWmB;
     const uint32_t row_s = wm_s + gl * kGrpB + px * kRowB;
     T *gin_g = gin + img_off + gl * 16;
@@ -563,6 +549,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
             sts128(gos_s, g_own);
         }
     }
+    __syncthreads();  // barrier D: the interpolation matrix is zero
     uint32_t slowmask = 0u;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
