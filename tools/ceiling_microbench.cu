@@ -1,0 +1,266 @@
+// On-chip ceiling of the DCNv3 kernels at site P3 (N = 16, 80x80, C = 128, G = 8, gc = 16, bf16): the MINIMUM stream of
+// shared-memory and FMA work the staged-window formulation needs, with everything data-dependent removed
+// ("window fill + conflict-free LDS.128 gathers + the minimum FMA stream, no location math").
+//
+//   fwd_ceiling   per CTA (8x8 pixels x 4 groups, 256 threads, as imat::fwd_tile_kernel): cp.async fill of the 20x20-cell x
+//                 64-channel window (zero fill outside the map), then per lane and pixel 36 LDS.128 corner gathers at
+//                 FIXED in-window cells (a function of the lane, no offsets, no floor, no bounds logic), 288 mixed-precision
+//                 FMAs with constant weights, one shuffle exchange, one 16-byte store.  No offset / mask traffic.
+//   bwd_ceiling   per CTA (4x8 pixels x 4 groups, as win::bwd_win_kernel): window fill (12x16 cells), per lane 36 gathers +
+//                 288 FMAs (the corner dots), 18 packed 16-bit read-modify-writes into the lane's private interpolation-matrix
+//                 row at fixed positions, barrier, the 12 x (2 k-steps) tensor-core products, stmatrix + one packed 16-bit
+//                 vector reduction per (cell, half).  No offsets / masks / grad_offset / grad_mask traffic, no location math.
+//
+// Both read real memory (rotating over 4 input sets) so the window fill pays its L2 / HBM cost.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ceiling.bin tools/ceiling_microbench.cu && tools/ceiling.bin
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+constexpr int N = 16, H = 80, W = 80, G = 8, C = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void axpy2(float &a0, float &a1, uint32_t x, uint32_t w) {
+    asm("{\n\t.reg .b16 xl, xh, wl, wh;\n\tmov.b32 {xl, xh}, %2;\n\tmov.b32 {wl, wh}, %3;\n\t"
+        "fma.rn.f32.bf16 %0, xl, wl, %0;\n\tfma.rn.f32.bf16 %1, xh, wl, %1;\n\t}" : "+f"(a0), "+f"(a1) : "r"(x), "r"(w));
+}
+__device__ __forceinline__ void dot2(float &s0, float &s1, uint32_t x, uint32_t g) {
+    asm("{\n\t.reg .b16 xl, xh, gl, gh;\n\tmov.b32 {xl, xh}, %2;\n\tmov.b32 {gl, gh}, %3;\n\t"
+        "fma.rn.f32.bf16 %0, xl, gl, %0;\n\tfma.rn.f32.bf16 %1, xh, gh, %1;\n\t}" : "+f"(s0), "+f"(s1) : "r"(x), "r"(g));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+constexpr int kFwin = 20, kFhalo = 6;
+__global__ void __launch_bounds__(256, 3) fwd_ceiling(const __nv_bfloat16 *__restrict__ in, __nv_bfloat16 *__restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int tx = blockIdx.x >> 1, gq = blockIdx.x & 1, ty = blockIdx.y, n = blockIdx.z;
+    const int wy0 = ty * 8 - kFhalo, wx0 = tx * 8 - kFhalo;
+    const __nv_bfloat16 *img = in + (size_t)n * H * W * C + gq * 64;
+    const uint32_t ws = smem_u32(smem);
+    {   // window fill: 400 cells x 8 chunks
+        const int ch = tid & 7;
+        for (int cell = tid >> 3; cell < kFwin * kFwin; cell += 32) {
+            const int r = cell / kFwin, c = cell - r * kFwin, iy = wy0 + r, ix = wx0 + c;
+            const bool ok = (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
+            cp_async16(ws + cell * 128 + (ch << 4), ok ? img + ((size_t)iy * W + ix) * C + ch * 8 : in, ok ? 16 : 0);
+        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int sub = tid & 7, h = sub & 1;
+    const uint32_t own16 = (uint32_t)sub << 4, oth16 = (uint32_t)(sub ^ 1) << 4;
+    const uint32_t wq = 0x3e80u;  // bf16(0.25): constant corner weight x mask
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int px = it * 32 + (tid >> 3), py = px >> 3, pxx = px & 7;
+        float acc[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {  // points 4h..4h+3 whole, point 8 by halves
+            const int p = k < 4 ? 4 * h + k : 8;
+            const uint32_t a = ws + ((py + kFhalo - 1 + p / 3) * kFwin + (pxx + kFhalo - 1 + p % 3)) * 128;
+#pragma unroll
+            for (int cn = 0; cn < 4; ++cn) {
+                const uint32_t ac = a + (cn & 1) * 128 + (cn >> 1) * kFwin * 128;
+                const uint4 x0 = lds128(ac + own16);
+                axpy2(acc[0], acc[1], x0.x, wq); axpy2(acc[2], acc[3], x0.y, wq);
+                axpy2(acc[4], acc[5], x0.z, wq); axpy2(acc[6], acc[7], x0.w, wq);
+                if (k < 4) {
+                    const uint4 x1 = lds128(ac + oth16);
+                    axpy2(acc[8], acc[9], x1.x, wq); axpy2(acc[10], acc[11], x1.y, wq);
+                    axpy2(acc[12], acc[13], x1.z, wq); axpy2(acc[14], acc[15], x1.w, wq);
+                }
+            }
+        }
+        // the pair exchanges the halves it computed for the partner's channels
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = acc[k] + __shfl_xor_sync(0xffffffffu, acc[8 + k], 1);
+        const int oy = ty * 8 + py, ox = tx * 8 + pxx;
+        const uint4 v = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+        *reinterpret_cast<uint4 *>(out + (((size_t)n * H + oy) * W + ox) * C + gq * 64 + sub * 8) = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+constexpr int kWinW = 16, kBandRows = 12, kRowB = kBandRows * kWinW * 2 + 16, kGrpB = 32 * kRowB + 16, kWmB = 4 * kGrpB;
+constexpr int kGoRowB = 48, kGoGrpB = 32 * kGoRowB, kGoB = 4 * kGoGrpB, kDwinB = kBandRows * kWinW * 128;
+__device__ __forceinline__ void ldsm_x4_t(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, uint32_t a) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__global__ void __launch_bounds__(256, 3) bwd_ceiling(const __nv_bfloat16 *__restrict__ in, const __nv_bfloat16 *__restrict__ gout,
+                                                      __nv_bfloat16 *__restrict__ gin, float *__restrict__ sink) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned b = blockIdx.x;
+    const int gq = b & 1; b >>= 1;
+    const int tx = b % 10; b /= 10;
+    const int ty = b % 20, n = b / 20;
+    const int by0 = ty * 4 - 4, wx0 = tx * 8 - 4;
+    const size_t img_off = (size_t)n * H * W * C + gq * 64;
+    const uint32_t ws = smem_u32(smem);
+    {   // window fill: 192 cells x 8 chunks
+        const int ch = tid & 7, col = (tid >> 3) & 15, r0 = tid >> 7;
+        const int ix = wx0 + col;
+#pragma unroll
+        for (int i = 0; i < kBandRows / 2; ++i) {
+            const int r = r0 + 2 * i, iy = by0 + r;
+            const bool ok = (unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W;
+            cp_async16(ws + (r * kWinW + col) * 128 + (ch << 4), ok ? in + img_off + ((size_t)iy * W + ix) * C + ch * 8 : in, ok ? 16 : 0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    const int px = tid >> 3, sub = tid & 7, gl = sub >> 1, h = sub & 1;
+    const int oy = ty * 4 + (px >> 3), ox = tx * 8 + (px & 7);
+    const uint4 *gp = reinterpret_cast<const uint4 *>(gout + (((size_t)n * H + oy) * W + ox) * C + (gq * 4 + gl) * 16);
+    const uint4 g_own = __ldg(gp + h), g_oth = __ldg(gp + (h ^ 1));
+    {   // zero the part of the interpolation matrix behind the window
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int id = tid; id < (kWmB - kDwinB) / 16; id += 256)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ws + kDwinB + id * 16), "r"(z.x), "r"(z.y), "r"(z.z), "r"(z.w) : "memory");
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // ---- corner dots: 36 gathers + 288 FMAs per lane at fixed cells
+    const uint32_t own16 = (uint32_t)sub << 4, oth16 = (uint32_t)(sub ^ 1) << 4;
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int p = k < 4 ? 4 * h + k : 8;
+        const uint32_t a = ws + (((px >> 3) + 3 + p / 3) * kWinW + ((px & 7) + 3 + p % 3)) * 128;
+#pragma unroll
+        for (int cn = 0; cn < 4; ++cn) {
+            const uint32_t ac = a + (cn & 1) * 128 + (cn >> 1) * kWinW * 128;
+            const uint4 x0 = lds128(ac + own16);
+            float s0 = 0.f, s1 = 0.f;
+            dot2(s0, s1, x0.x, g_own.x); dot2(s0, s1, x0.y, g_own.y); dot2(s0, s1, x0.z, g_own.z); dot2(s0, s1, x0.w, g_own.w);
+            if (k < 4) {
+                const uint4 x1 = lds128(ac + oth16);
+                dot2(s0, s1, x1.x, g_oth.x); dot2(s0, s1, x1.y, g_oth.y); dot2(s0, s1, x1.z, g_oth.z); dot2(s0, s1, x1.w, g_oth.w);
+            }
+            tot += s0 + s1;
+        }
+    }
+    if (tot == 12345.678f) sink[0] = tot;  // keeps the dots alive, never taken
+    __syncthreads();  // every warp has left the window
+    {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int id = tid; id < kDwinB / 16; id += 256)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ws + id * 16), "r"(z.x), "r"(z.y), "r"(z.z), "r"(z.w) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(ws + kWmB + gl * kGoGrpB + px * kGoRowB + 16 * h), "r"(g_own.x), "r"(g_own.y), "r"(g_own.z), "r"(g_own.w) : "memory");
+    }
+    __syncthreads();
+    // ---- 18 packed read-modify-writes into the lane's private rows (parity h) at fixed, conflict-prone-as-in-life positions
+    const uint32_t row_s = ws + gl * kGrpB + px * kRowB;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int vb = (px >> 3) + 3 + k / 3 + ((((px >> 3) + 3 + k / 3) & 1) != h);  // a row of parity h
+        const int u = (px & 7) + 3 + k % 3;
+        const uint32_t wa = row_s + (((vb * kWinW + u) >> 1) << 2);
+        uint32_t w0, w1;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(wa));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w1) : "r"(wa + 4));
+        asm volatile("{\n\t.reg .b32 t;\n\tadd.f16x2 t, %1, %2;\n\tst.shared.u32 [%0], t;\n\t}" ::"r"(wa), "r"(w0), "r"(0x34003400u) : "memory");
+        asm volatile("{\n\t.reg .b32 t;\n\tadd.f16x2 t, %1, %2;\n\tst.shared.u32 [%0], t;\n\t}" ::"r"(wa + 4), "r"(w1), "r"(0x34003400u) : "memory");
+    }
+    __syncthreads();
+    // ---- tensor cores + flush, as win::bwd_win_kernel
+    const int mg = warp & 3, qpar = warp >> 2;
+    const uint32_t wm_g = ws + mg * kGrpB;
+    float gw[6][2][4];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) gw[i][nt][c] = 0.f;
+    const int jm = lane >> 3, jr = lane & 7;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        uint32_t b00, b01, b10, b11;
+        ldsm_x4_t(b00, b01, b10, b11, ws + kWmB + mg * kGoGrpB + (16 * s + 8 * (jm & 1) + jr) * kGoRowB + (jm >> 1) * 16);
+        const uint32_t abase = wm_g + (16 * s + 8 * (jm >> 1) + jr) * kRowB + (jm & 1) * 16 + qpar * 32;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            uint32_t a0, a1, a2, a3;
+            ldsm_x4_t(a0, a1, a2, a3, abase + i * 64);
+            mma16816(gw[i][0], a0, a1, a2, a3, b00, b01);
+            mma16816(gw[i][1], a0, a1, a2, a3, b10, b11);
+        }
+    }
+    __syncwarp();
+    const uint32_t st_addr = wm_g + (jr + 8 * (jm & 1)) * kRowB + qpar * 32 + (jm >> 1) * 16;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+        asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(st_addr + i * 64),
+                     "r"(pack_bf16(gw[i][0][0], gw[i][0][1])), "r"(pack_bf16(gw[i][0][2], gw[i][0][3])),
+                     "r"(pack_bf16(gw[i][1][0], gw[i][1][1])), "r"(pack_bf16(gw[i][1][2], gw[i][1][3])) : "memory");
+    __syncwarp();
+    const int cell = lane >> 1, half = lane & 1, ix = wx0 + cell;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int iy = by0 + qpar + 2 * i;
+        const uint4 o = lds128(wm_g + cell * kRowB + qpar * 32 + half * 16 + i * 64);
+        const bool ok = (unsigned)ix < (unsigned)W && (unsigned)iy < (unsigned)H;
+        if (ok) {
+            __nv_bfloat16 *dst = gin + img_off + mg * 16 + half * 8 + ((size_t)iy * W + ix) * C;
+            asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+        }
+    }
+}
+
+int main() {
+    const size_t n_el = (size_t)N * H * W * C;
+    constexpr int SETS = 4;
+    __nv_bfloat16 *in[SETS], *go[SETS], *out[SETS];
+    float *sink;
+    cudaMalloc(&sink, 256);
+    for (int s = 0; s < SETS; ++s) {
+        cudaMalloc(&in[s], n_el * 2); cudaMalloc(&go[s], n_el * 2); cudaMalloc(&out[s], n_el * 2);
+        cudaMemset(in[s], 0x3c, n_el * 2); cudaMemset(go[s], 0x3c, n_el * 2); cudaMemset(out[s], 0, n_el * 2);
+    }
+    // L2 flush buffer between launches is not needed: the 4 sets are 315 MB >> 126 MB L2
+    const int fsmem = kFwin * kFwin * 128, bsmem = kWmB + kGoB;
+    cudaFuncSetAttribute(fwd_ceiling, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem);
+    cudaFuncSetAttribute(bwd_ceiling, cudaFuncAttributeMaxDynamicSharedMemorySize, bsmem);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int which = 0; which < 2; ++which) {
+        float sum = 0.f; int cnt = 0;
+        for (int rep = 0; rep < 24; ++rep) {
+            const int s = rep % SETS;
+            cudaEventRecord(e0);
+            if (which == 0) fwd_ceiling<<<dim3(20, 10, 16), 256, fsmem>>>(in[s], out[s]);
+            else bwd_ceiling<<<16 * 20 * 10 * 2, 256, bsmem>>>(in[s], go[s], out[s], sink);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            if (rep >= 4) { sum += ms; ++cnt; }
+        }
+        const double us = sum / cnt * 1e3;
+        const double bytes = which == 0 ? 96665600.0 : 167116800.0;  // algorithmic bytes of the real op at P3 (BASELINE.md par. 3)
+        printf("%s ceiling at P3: %.1f us  (= %.0f GB/s of the op's algorithmic bytes, %.1f %% of the 6466.8 GB/s HBM peak)\n",
+               which == 0 ? "forward " : "backward", us, bytes / us / 1e3, 100.0 * bytes / us / 1e3 / 6466.8);
+    }
+    printf("last error: %s\n", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}

@@ -46,7 +46,13 @@ constexpr int kThreadsW = 256;
 constexpr int kWinW = 16;                                // window columns the band's interpolation matrix spans: 8 + 2 * 4
 constexpr int kBandRows = 12;                            // window rows a 4-row band of pixels reaches
 constexpr int kRowB = kBandRows * kWinW * 2 + 16;        // 400 B per (pixel, group): +16 B skew (ldmatrix rows on distinct banks)
-constexpr int kGrpB = 32 * kRowB + 16;                   // 12 816 B per group: +16 B so the groups' rows start on different banks
+#ifndef DCNV3_WIN_GRP_SKEW
+#define DCNV3_WIN_GRP_SKEW 16
+#endif
+// +16 B per group so the groups' rows start on different banks.  (A/B on one box, round 2: skews of 16 / 32 / 64 bytes —
+// bank group of a lane = (pixel + {1, 2, 4} x group + position) mod 8 — all gave 172.5 us at P3: the read-modify-write
+// bank conflicts of the interpolation matrix are not what bounds the kernel.)
+constexpr int kGrpB = 32 * kRowB + DCNV3_WIN_GRP_SKEW;   // per group
 constexpr int kWmB = kWarps * kGrpB;                     // 51 264 B: [group][32 pixels]
 constexpr int kGoRowB = 48;                              // grad_output rows of the band: 32 B + 16 B skew
 constexpr int kGoGrpB = 32 * kGoRowB;
@@ -278,8 +284,11 @@ __global__ void __launch_bounds__(256) zero_fill_kernel(uint4 *__restrict__ p, c
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n16; i += (size_t)gridDim.x * 256) p[i] = z;
 }
 
+#ifndef DCNV3_WIN_MIN_CTAS
+#define DCNV3_WIN_MIN_CTAS 3
+#endif
 template <typename T, bool LOGITS>
-__global__ void __launch_bounds__(kThreadsW, 3)
+__global__ void __launch_bounds__(kThreadsW, DCNV3_WIN_MIN_CTAS)
 bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
                const T *__restrict__ gout, T *__restrict__ gin, T *__restrict__ goff, T *__restrict__ gmask,
                const Geo q, const int GQ, const int tiles_x, const int bands_y) {
