@@ -601,7 +601,7 @@ def time_infer(dev, dist, world, steps, warmup, batch):
 # infrastructure, built by oracle/build_ref_cuda.py where /root/reference is mounted).  They have no
 # bf16 path (dcnv3_cuda.cu:69,147), so the comparison runs in fp16 on both sides.
 # ----------------------------------------------------------------------------------------------
-def time_reference_cuda(dev, sites, steps, warmup):
+def time_reference_cuda(dev, sites, steps, warmup, accum="tile"):
     from oracle.build_ref_cuda import load_module
     ref = load_module()
     if ref is None:
@@ -631,11 +631,12 @@ def time_reference_cuda(dev, sites, steps, warmup):
     torch.cuda.synchronize()
     ref_ms = e0.elapsed_time(e1) / steps
     del sets
-    wl = Workload(dev, dt, sites, "opmath", False)
+    wl = Workload(dev, dt, sites, accum, False)
     ours_ms = time_steps(wl, steps, warmup, None) / steps
     return {"what": "the reference's own CUDA kernels (dcnv3_im2col_cuda.cuh) rebuilt for sm_100a, same step, "
                     "fp16 (the reference has no bf16), outputs allocated inside as it does",
             "dtype": "fp16", "steps": steps, "reference_ms_per_step": ref_ms, "ours_fp16_ms_per_step": ours_ms,
+            "ours_grad_accum": accum,
             "speedup": ref_ms / ours_ms}
 
 
@@ -743,9 +744,9 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        # bounded: ~45 ms per image and site set on 16 cores -> the arm caps its own step count so that any
-        # --steps / --warmup the driver passes ends within a few minutes (the line reports the steps it ran)
-        a.steps, a.warmup = min(a.steps, 20), min(a.warmup, 3)
+        # bounded: every step runs the same fixed 2-image sample (~0.36 s on 16 cores); the arm caps its own step count
+        # so that any --steps / --warmup ends within a few minutes (the line reports the steps it ran)
+        a.steps, a.warmup = min(a.steps, 600), min(a.warmup, 10)  # ~0.36 s per step on the box's 16 cores
         gbps, ms, cores, sample, n_img = cpu_run(sites, e, a.steps, a.warmup)
         print(file=out_stream, flush=True, *[json.dumps({
             "impl": "reference", "metric": METRIC, "value": gbps, "unit": "GB/s", "n_gpus": a.gpus,
@@ -849,7 +850,7 @@ def main():
     ref_cuda = None
     if rank == 0 and not a.no_ref_cuda:
         try:
-            ref_cuda = time_reference_cuda(dev, sites, 20, 3)
+            ref_cuda = time_reference_cuda(dev, sites, 20, 3, a.grad_accum)
         except Exception as ex:  # the baseline must never take the bench down
             ref_cuda = {"error": repr(ex)[:300]}
     clk = clocks.stop() if clocks else None
