@@ -336,11 +336,15 @@ def pinned_like(t, channels_last):
     return buf
 
 
-def seg_model(dev, model_name, channels_last=True, fused_softmax=False):
+SEG_DCN_OPTS = {"fused_softmax": False, "packed_heads": False}  # --seg-fused-heads switches both on
+
+
+def seg_model(dev, model_name, channels_last=True, fused_softmax=None):
     from yolo_dual_b200 import seg
     torch.manual_seed(0)  # same initial weights on every rank
     cfg = {"yolov5seg": seg.YOLOV5_SEG, "yolov8seg": seg.YOLOV8_SEG}[model_name]
-    model = seg.SegModel(cfg, dcn="dcnv3", fused_softmax=fused_softmax).to(dev)
+    opts = dict(SEG_DCN_OPTS) if fused_softmax is None else {"fused_softmax": fused_softmax, "packed_heads": False}
+    model = seg.SegModel(cfg, dcn="dcnv3", **opts).to(dev)
     if channels_last:  # NHWC activations: the NCHW<->NHWC permutes around every DCNv3 become views
         model = model.to(memory_format=torch.channels_last)
     return model
@@ -450,7 +454,7 @@ def time_seg(dev, dist, world, steps, warmup, batch, model_name, channels_last=T
                              "into pinned memory every step and inspected one step later",
            "fused": "deferred last Upsample, fused CE+Dice loss, fused BN+SiLU, NHWC resize kernels (this repo's "
                     "segloss_b200 / bnact_b200 / resize_b200)",
-           "cuda_graph": graph_note,
+           "cuda_graph": graph_note, "dcnv3_module": dict(SEG_DCN_OPTS),
            "data_parallel": (f"DDP x{world} (NCCL all-reduce of {n_params * (2 if comp == 'bf16' else 4) / 1e6:.1f} MB {comp} grads, "
                              f"bucket_cap_mb {ddp_opts.get('bucket_cap_mb') or 25}, first bucket {ddp_opts.get('first_bucket_mb') or 1} MB)")
            if world > 1 else "single GPU"}
@@ -712,6 +716,8 @@ def main():
                     help="fixed global batch split over the GPUs (strong scaling, BASELINE configs[3]: 64)")
     ap.add_argument("--seg-model", default="yolov5seg", choices=["yolov5seg", "yolov8seg"])
     ap.add_argument("--seg-nchw", action="store_true", help="keep NCHW activations in the seg model")
+    ap.add_argument("--seg-fused-heads", action="store_true",
+                    help="seg models with DCNv3(fused_softmax=True, packed_heads=True): softmax inside the kernels, both heads one GEMM")
     ap.add_argument("--no-seg-strong", action="store_true", help="skip the configs[3] line (yolov8seg, global batch 64)")
     ap.add_argument("--seg-graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the training step as one CUDA graph (auto: on)")
@@ -725,6 +731,8 @@ def main():
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3
+    if a.seg_fused_heads:
+        SEG_DCN_OPTS.update(fused_softmax=True, packed_heads=True)
     sites = a.sites.split(",")
     dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[a.dtype]
     e = esize(dtype)
