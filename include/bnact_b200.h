@@ -37,6 +37,13 @@ int bnact_b200_forward(const void* x, void* z, const float* gamma, const float* 
                        float* running_var, float* save, float* partial, int dtype, int64_t M, int C, float eps,
                        float momentum, int act, void* cuda_stream);
 
+/* Inference: z = act((x - running_mean) * gamma / sqrt(running_var + eps) + beta) in one pass (PyTorch: transform +
+ * SiLU = two passes and a tiny invstd kernel).  The four per-channel vectors are float32 (params_in_dtype = 0) or in the
+ * activation's own 16-bit dtype (params_in_dtype = 1: a model cast with .half() / .bfloat16()).  No autograd side. */
+int bnact_b200_eval(const void* x, void* z, const void* gamma, const void* beta, const void* running_mean,
+                    const void* running_var, int dtype, int params_in_dtype, int64_t M, int C, float eps, int act,
+                    void* cuda_stream);
+
 /* coef scratch: [2][C]; dgamma, dbeta: [C] */
 int bnact_b200_backward(const void* x, const void* gz, void* dx, const float* gamma, const float* beta,
                         const float* save, float* dgamma, float* dbeta, float* coef, float* partial, int dtype,

@@ -101,3 +101,49 @@ def test_conv_block_takes_the_fused_path_only_where_it_applies(monkeypatch):
     assert not calls
     sync = nn.SyncBatchNorm.convert_sync_batchnorm(Conv(16, 32, 3)).to(DEV)
     assert not _bnact.usable(x.new_zeros(4, 32, 20, 20).contiguous(memory_format=torch.channels_last), sync.bn, sync.act)
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 40, 40), (2, 1024, 5, 5), (3, 32, 7, 9), (1, 8, 3, 3)])
+@pytest.mark.parametrize("mode", ["f32", "half_model", "bf16_model", "bf16_autocast"])
+@pytest.mark.parametrize("silu", [True, False])
+def test_eval_bn_act_one_pass_matches_torch(shape, mode, silu):
+    """Inference path (bnact_b200_eval): running statistics, one pass; parameters float32 or in the model's 16-bit dtype."""
+    n, c, h, w = shape
+    dt = {"f32": torch.float32, "half_model": torch.float16, "bf16_model": torch.bfloat16, "bf16_autocast": torch.bfloat16}[mode]
+    if not _bnact.load().bnact_b200_supported(_bnact._DTYPES[dt], c):
+        pytest.skip("channel count outside the fused kernels' range")
+    g = torch.Generator().manual_seed(c + w)
+    blk = Conv(c, c, 1, act=silu).to(DEV).eval()
+    with torch.no_grad():
+        blk.bn.weight.copy_(torch.rand(c, generator=g) + 0.5)
+        blk.bn.bias.copy_(torch.randn(c, generator=g))
+        blk.bn.running_mean.copy_(torch.randn(c, generator=g))
+        blk.bn.running_var.copy_(torch.rand(c, generator=g) + 0.25)
+    if mode in ("half_model", "bf16_model"):
+        blk = blk.to(dt)
+    blk = blk.to(memory_format=torch.channels_last)
+    y = (torch.randn(shape, generator=g) * 2).to(DEV).to(dt).contiguous(memory_format=torch.channels_last)
+    assert _bnact.usable_eval(y, blk.bn, blk.act) is False          # autograd on: not the inference path
+    with torch.no_grad():
+        assert _bnact.usable_eval(y, blk.bn, blk.act)
+        got = _bnact.bn_act_eval(y, blk.bn, blk.act)
+        p = [t.float() for t in (blk.bn.running_mean, blk.bn.running_var, blk.bn.weight, blk.bn.bias)]
+        want = F.batch_norm(y.float(), p[0], p[1], p[2], p[3], False, 0.0, blk.bn.eps)
+        want = F.silu(want) if silu else want
+    assert got.dtype == dt and got.is_contiguous(memory_format=torch.channels_last)
+    tol = dict(rtol=1e-5, atol=1e-5) if dt == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(got.float(), want, **tol)
+
+
+def test_eval_conv_block_uses_the_one_pass_kernel_and_matches_the_torch_ops(monkeypatch):
+    blk = Conv(32, 64, 3).to(DEV).half().eval().to(memory_format=torch.channels_last)
+    x = torch.randn(2, 32, 20, 20, device=DEV).half().contiguous(memory_format=torch.channels_last)
+    calls = []
+    orig = _bnact.bn_act_eval
+    monkeypatch.setattr(_bnact, "bn_act_eval", lambda *a: (calls.append(1), orig(*a))[1])
+    with torch.no_grad():
+        a = blk(x)
+        monkeypatch.setenv("YOLO_DUAL_B200_FUSED_BN", "0")
+        b = blk(x)
+    assert calls == [1]
+    torch.testing.assert_close(a.float(), b.float(), rtol=1e-2, atol=1e-2)

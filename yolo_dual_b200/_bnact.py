@@ -12,7 +12,7 @@ from torch import nn
 from .build import BNACT_LIB
 
 SYMBOLS = ("bnact_b200_version", "bnact_b200_last_error", "bnact_b200_supported", "bnact_b200_partial_floats",
-           "bnact_b200_forward", "bnact_b200_backward")
+           "bnact_b200_forward", "bnact_b200_backward", "bnact_b200_eval")
 _DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 _lib = None
 
@@ -35,6 +35,7 @@ def load() -> ctypes.CDLL:
     lib.bnact_b200_partial_floats.restype = ctypes.c_size_t
     lib.bnact_b200_forward.argtypes = [vp] * 8 + [ip, i64, ip, fl, fl, ip, vp]
     lib.bnact_b200_backward.argtypes = [vp] * 10 + [ip, i64, ip, ip, vp]
+    lib.bnact_b200_eval.argtypes = [vp] * 6 + [ip, ip, i64, ip, fl, ip, vp]
     _lib = lib
     return lib
 
@@ -113,3 +114,34 @@ def bn_act(y: torch.Tensor, bn: nn.BatchNorm2d, act: nn.Module) -> torch.Tensor:
         bn.num_batches_tracked.add_(1)
     rm, rv = (bn.running_mean, bn.running_var) if bn.track_running_stats else (None, None)
     return FusedBNAct.apply(y, bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum, isinstance(act, nn.SiLU))
+
+
+def usable_eval(y: torch.Tensor, bn: nn.Module, act: nn.Module) -> bool:
+    """True when `act(bn(y))` is an inference call the one-pass kernel covers: CUDA, no autograd, eval-mode plain
+    BatchNorm2d with running statistics and affine parameters (float32 or y's own 16-bit dtype), SiLU or no
+    activation, NHWC-contiguous y with a supported channel count."""
+    if not (y.is_cuda and not bn.training and enabled()) or torch.is_grad_enabled():
+        return False
+    if type(bn) is not nn.BatchNorm2d or not bn.affine or bn.running_mean is None:
+        return False
+    if not isinstance(act, (nn.SiLU, nn.Identity)):
+        return False
+    if y.dim() != 4 or y.dtype not in _DTYPES or not y.is_contiguous(memory_format=torch.channels_last):
+        return False
+    pd = bn.weight.dtype
+    if not (pd == bn.bias.dtype == bn.running_mean.dtype == bn.running_var.dtype) or pd not in (torch.float32, y.dtype):
+        return False
+    return bool(load().bnact_b200_supported(_DTYPES[y.dtype], y.size(1)))
+
+
+def bn_act_eval(y: torch.Tensor, bn: nn.BatchNorm2d, act: nn.Module) -> torch.Tensor:
+    """act(bn(y)) with running statistics, one pass (callers check `usable_eval` first)."""
+    n, c, h, w = y.shape
+    z = torch.empty_like(y)
+    with torch.cuda.device_of(y):
+        _check(load().bnact_b200_eval(y.data_ptr(), z.data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(),
+                                      bn.running_mean.data_ptr(), bn.running_var.data_ptr(), _DTYPES[y.dtype],
+                                      int(bn.weight.dtype != torch.float32), n * h * w, c, float(bn.eps),
+                                      int(isinstance(act, nn.SiLU)), torch.cuda.current_stream().cuda_stream),
+               "bnact_b200_eval")
+    return z

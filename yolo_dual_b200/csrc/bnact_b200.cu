@@ -229,6 +229,59 @@ apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ z, const float* __
     }
 }
 
+// Inference (running statistics): z = act((x - mean) * gamma / sqrt(var + eps) + beta) in ONE pass.  The per-channel
+// parameters come in float32 or in the activation's own 16-bit dtype (a model cast with .half() has half BatchNorm
+// parameters and buffers); scale / shift are formed in float per thread (a thread owns one 16-byte channel vector).
+template <typename T, typename P, int N>
+__device__ __forceinline__ void load_params(const P* __restrict__ p, int c0, float (&f)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) f[i] = (float)__ldg(p + c0 + i);
+}
+template <typename T, typename P, bool SILU>
+__global__ void __launch_bounds__(THREADS)
+eval_kernel(const uint4* __restrict__ x, uint4* __restrict__ z, const P* __restrict__ gamma, const P* __restrict__ beta,
+            const P* __restrict__ mean, const P* __restrict__ var, float eps, int64_t M, int C) {
+    constexpr int N = Vec<T>::N;
+    const int CV = C / N;
+    const int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x;
+    const int cv = (int)(g % CV);
+    const int64_t rs = (int64_t)gridDim.x * THREADS / CV;
+    float sc[N], sh[N];
+    {
+        float ga[N], be[N], mu[N], va[N];
+        load_params<T, P, N>(gamma, cv * N, ga);
+        load_params<T, P, N>(beta, cv * N, be);
+        load_params<T, P, N>(mean, cv * N, mu);
+        load_params<T, P, N>(var, cv * N, va);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            sc[i] = ga[i] / sqrtf(va[i] + eps);
+            sh[i] = fmaf(-mu[i], sc[i], be[i]);
+        }
+    }
+    int64_t r = g / CV;
+    for (; r + (UNROLL - 1) * rs < M; r += UNROLL * rs) {
+        uint4 v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) v[u] = ldg_stream(x + (r + u * rs) * CV + cv);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            float f[N];
+            Vec<T>::unpack(v[u], f);
+#pragma unroll
+            for (int i = 0; i < N; ++i) { const float y = fmaf(f[i], sc[i], sh[i]); f[i] = SILU ? silu_f(y) : y; }
+            z[(r + u * rs) * CV + cv] = Vec<T>::pack(f);
+        }
+    }
+    for (; r < M; r += rs) {
+        float f[N];
+        Vec<T>::unpack(__ldg(x + r * CV + cv), f);
+#pragma unroll
+        for (int i = 0; i < N; ++i) { const float y = fmaf(f[i], sc[i], sh[i]); f[i] = SILU ? silu_f(y) : y; }
+        z[r * CV + cv] = Vec<T>::pack(f);
+    }
+}
+
 // sums over rows of gy and gy * (x - mean), gy = gz * act'(y)
 template <typename T, bool SILU>
 __global__ void __launch_bounds__(THREADS)
@@ -394,9 +447,36 @@ int backward_t(const void* x, const void* gz, void* dx, const float* beta, const
     return e == cudaSuccess ? 0 : fail((int)e, cudaGetErrorString(e));
 }
 
+template <typename T, typename P>
+int eval_t(const void* x, void* z, const void* gamma, const void* beta, const void* mean, const void* var, int dtype,
+           int64_t M, int C, float eps, int act, cudaStream_t st) {
+    const int nblk = blocks_for(dtype, M, C);
+    if (act) eval_kernel<T, P, true><<<nblk, THREADS, 0, st>>>((const uint4*)x, (uint4*)z, (const P*)gamma, (const P*)beta, (const P*)mean, (const P*)var, eps, M, C);
+    else eval_kernel<T, P, false><<<nblk, THREADS, 0, st>>>((const uint4*)x, (uint4*)z, (const P*)gamma, (const P*)beta, (const P*)mean, (const P*)var, eps, M, C);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail((int)e, cudaGetErrorString(e));
+}
+
 }  // namespace
 
 extern "C" {
+
+int bnact_b200_eval(const void* x, void* z, const void* gamma, const void* beta, const void* running_mean,
+                    const void* running_var, int dtype, int params_in_dtype, int64_t M, int C, float eps, int act,
+                    void* cuda_stream) {
+    if (!x || !z || !gamma || !beta || !running_mean || !running_var) return fail(-2, "null pointer");
+    if (int rc = check_common(dtype, M, C, act)) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const bool pt = params_in_dtype != 0 && dtype != 0;
+    switch (dtype) {
+        case 0: return eval_t<float, float>(x, z, gamma, beta, running_mean, running_var, dtype, M, C, eps, act, st);
+        case 1: return pt ? eval_t<__half, __half>(x, z, gamma, beta, running_mean, running_var, dtype, M, C, eps, act, st)
+                          : eval_t<__half, float>(x, z, gamma, beta, running_mean, running_var, dtype, M, C, eps, act, st);
+        default: return pt ? eval_t<__nv_bfloat16, __nv_bfloat16>(x, z, gamma, beta, running_mean, running_var, dtype, M, C, eps, act, st)
+                           : eval_t<__nv_bfloat16, float>(x, z, gamma, beta, running_mean, running_var, dtype, M, C, eps, act, st);
+    }
+}
+
 
 int bnact_b200_version(void) { return BNACT_B200_VERSION; }
 const char* bnact_b200_last_error(void) { return g_err; }

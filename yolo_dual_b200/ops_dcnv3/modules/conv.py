@@ -32,10 +32,13 @@ class Conv(nn.Module):
 
     def forward(self, x):
         y = self.conv(x)
-        if y.is_cuda and self.training:
-            from ... import _bnact   # fused batch-statistics BatchNorm + SiLU (csrc/bnact_b200.cu) where it applies
-            if _bnact.usable(y, self.bn, self.act):
-                return _bnact.bn_act(y, self.bn, self.act)
+        if y.is_cuda:
+            from ... import _bnact   # fused BatchNorm + SiLU (csrc/bnact_b200.cu) where it applies
+            if self.training:        # batch statistics, with autograd
+                if _bnact.usable(y, self.bn, self.act):
+                    return _bnact.bn_act(y, self.bn, self.act)
+            elif _bnact.usable_eval(y, self.bn, self.act):   # inference: running statistics, one pass
+                return _bnact.bn_act_eval(y, self.bn, self.act)
         return self.act(self.bn(y))
 
     def forward_fuse(self, x):  # after conv+bn folding
