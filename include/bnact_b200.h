@@ -49,6 +49,12 @@ int bnact_b200_backward(const void* x, const void* gz, void* dx, const float* ga
                         const float* save, float* dgamma, float* dbeta, float* coef, float* partial, int dtype,
                         int64_t M, int C, int act, void* cuda_stream);
 
+/* Same, with gz read at a row pitch of gz_pitch elements (>= C, a whole number of 16-byte vectors): the gradient of a
+ * channel slice of a wider NHWC tensor — what torch.cat's backward hands to each of its inputs — without a copy. */
+int bnact_b200_backward_pitched(const void* x, const void* gz, void* dx, const float* gamma, const float* beta,
+                                const float* save, float* dgamma, float* dbeta, float* coef, float* partial, int dtype,
+                                int64_t M, int C, int act, int64_t gz_pitch, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

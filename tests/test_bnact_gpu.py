@@ -147,3 +147,42 @@ def test_eval_conv_block_uses_the_one_pass_kernel_and_matches_the_torch_ops(monk
         b = blk(x)
     assert calls == [1]
     torch.testing.assert_close(a.float(), b.float(), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_backward_reads_the_gradient_of_a_cat_slice_in_place(dtype, monkeypatch):
+    """torch.cat's backward hands each input a channel-slice VIEW of the concatenated gradient; the fused backward reads
+    it at its row pitch (bnact_b200_backward_pitched) instead of copying it.  Same gradients as the torch ops."""
+    torch.manual_seed(0)
+    a, b = Conv(16, 32, 1).to(DEV), Conv(16, 64, 3).to(DEV)
+    for m in (a, b):
+        m.to(memory_format=torch.channels_last).train()
+    x = torch.randn(4, 16, 12, 10, device=DEV).contiguous(memory_format=torch.channels_last)
+    wgt = torch.randn(4, 96, 12, 10, device=DEV).contiguous(memory_format=torch.channels_last)
+    seen = []
+    lib = _bnact.load()
+    orig = lib.bnact_b200_backward_pitched
+
+    class Spy:
+        def __call__(self, *args):
+            seen.append((args[12], args[14]))   # (C, gz_pitch)
+            return orig(*args)
+    monkeypatch.setattr(lib, "bnact_b200_backward_pitched", Spy())
+
+    def run():
+        for m in (a, b):
+            m.zero_grad(set_to_none=True)
+        xi = x.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=dtype, enabled=dtype != torch.float32):
+            y = torch.cat((a(xi), b(xi)), 1)
+        (y.float() * wgt).sum().backward()
+        return [xi.grad.clone()] + [p.grad.clone() for m in (a, b) for p in m.parameters()]
+
+    got = run()
+    assert sorted(seen) == [(32, 96), (64, 96)], seen    # both slices were read at the cat's pitch: no copy
+    monkeypatch.setenv("YOLO_DUAL_B200_FUSED_BN", "0")
+    want = run()
+    tol = dict(rtol=1e-4, atol=1e-4) if dtype == torch.float32 else dict(rtol=3e-2, atol=3e-2)
+    for g, w_ in zip(got, want):
+        s = max(1.0, float(w_.abs().max()))
+        torch.testing.assert_close(g / s, w_ / s, **tol)

@@ -12,7 +12,7 @@ from torch import nn
 from .build import BNACT_LIB
 
 SYMBOLS = ("bnact_b200_version", "bnact_b200_last_error", "bnact_b200_supported", "bnact_b200_partial_floats",
-           "bnact_b200_forward", "bnact_b200_backward", "bnact_b200_eval")
+           "bnact_b200_forward", "bnact_b200_backward", "bnact_b200_backward_pitched", "bnact_b200_eval")
 _DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 _lib = None
 
@@ -36,6 +36,7 @@ def load() -> ctypes.CDLL:
     lib.bnact_b200_forward.argtypes = [vp] * 8 + [ip, i64, ip, fl, fl, ip, vp]
     lib.bnact_b200_backward.argtypes = [vp] * 10 + [ip, i64, ip, ip, vp]
     lib.bnact_b200_eval.argtypes = [vp] * 6 + [ip, ip, i64, ip, fl, ip, vp]
+    lib.bnact_b200_backward_pitched.argtypes = [vp] * 10 + [ip, i64, ip, ip, i64, vp]
     _lib = lib
     return lib
 
@@ -96,15 +97,25 @@ class FusedBNAct(torch.autograd.Function):
         m = n * h * w
         dt = _DTYPES[x.dtype]
         lib = load()
-        gz = gz.to(x.dtype).contiguous(memory_format=torch.channels_last)
+        # The gradient of a channel slice of a wider channels-last tensor (what torch.cat's backward hands to each input:
+        # strides (H*W*Ct, 1, W*Ct, Ct)) is read in place at its row pitch; anything else is made NHWC-contiguous.
+        if gz.dtype != x.dtype:
+            gz = gz.to(x.dtype)
+        pitch = c
+        st = gz.stride()
+        if (not gz.is_contiguous(memory_format=torch.channels_last) and st[1] == 1 and st[3] >= c and st[2] == w * st[3]
+                and st[0] == h * st[2] and st[3] % (16 // gz.element_size()) == 0 and gz.data_ptr() % 16 == 0):
+            pitch = st[3]
+        else:
+            gz = gz.contiguous(memory_format=torch.channels_last)
         dx = torch.empty_like(x)
         small = torch.empty(4 * c, dtype=torch.float32, device=x.device)   # dgamma, dbeta, coef[2]
         partial = torch.empty(lib.bnact_b200_partial_floats(dt, m, c), dtype=torch.float32, device=x.device)
         with torch.cuda.device_of(x):
-            _check(lib.bnact_b200_backward(
+            _check(lib.bnact_b200_backward_pitched(
                 x.data_ptr(), gz.data_ptr(), dx.data_ptr(), gamma.data_ptr(), beta.data_ptr(), save.data_ptr(),
                 small.data_ptr(), small[c:].data_ptr(), small[2 * c:].data_ptr(), partial.data_ptr(), dt, m, c,
-                ctx.silu, torch.cuda.current_stream().cuda_stream), "bnact_b200_backward")
+                ctx.silu, pitch, torch.cuda.current_stream().cuda_stream), "bnact_b200_backward")
         return dx, small[:c], small[c:2 * c], None, None, None, None, None
 
 

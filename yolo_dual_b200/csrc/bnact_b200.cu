@@ -286,7 +286,7 @@ eval_kernel(const uint4* __restrict__ x, uint4* __restrict__ z, const P* __restr
 template <typename T, bool SILU>
 __global__ void __launch_bounds__(THREADS)
 bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gz, const float* __restrict__ save,
-                  const float* __restrict__ beta, float* __restrict__ partial, int64_t M, int C) {
+                  const float* __restrict__ beta, float* __restrict__ partial, int64_t M, int C, int64_t GV) {
     constexpr int N = Vec<T>::N;
     const int CV = C / N;
     const int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x;
@@ -306,7 +306,7 @@ bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gz, con
     for (int u = 0; u < U; ++u) {
         const bool in = r + u * rs < M;
         cx[u] = in ? ldg_stream(x + (r + u * rs) * CV + cv) : zero;
-        cg[u] = in ? ldg_stream(gz + (r + u * rs) * CV + cv) : zero;
+        cg[u] = in ? ldg_stream(gz + (r + u * rs) * GV + cv) : zero;
     }
     while (r < M) {
         const int64_t rn = r + U * rs;
@@ -314,7 +314,7 @@ bwd_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gz, con
         for (int u = 0; u < U; ++u) {
             const bool in = rn + u * rs < M;
             nx[u] = in ? ldg_stream(x + (rn + u * rs) * CV + cv) : zero;
-            ng[u] = in ? ldg_stream(gz + (rn + u * rs) * CV + cv) : zero;
+            ng[u] = in ? ldg_stream(gz + (rn + u * rs) * GV + cv) : zero;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -356,7 +356,7 @@ template <typename T, bool SILU>
 __global__ void __launch_bounds__(THREADS)
 bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gz, uint4* __restrict__ dx,
                  const float* __restrict__ save, const float* __restrict__ beta, const float* __restrict__ coef,
-                 int64_t M, int C) {
+                 int64_t M, int C, int64_t GV) {
     constexpr int N = Vec<T>::N;
     const int CV = C / N;
     const int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x;
@@ -374,7 +374,7 @@ bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gz, uint
         uint4 vx[U], vg[U];
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            if (r + u * rs < M) { vx[u] = __ldg(x + (r + u * rs) * CV + cv); vg[u] = __ldg(gz + (r + u * rs) * CV + cv); }
+            if (r + u * rs < M) { vx[u] = __ldg(x + (r + u * rs) * CV + cv); vg[u] = __ldg(gz + (r + u * rs) * GV + cv); }
 #pragma unroll
         for (int u = 0; u < U; ++u)
             if (r + u * rs < M) {
@@ -436,13 +436,15 @@ int forward_t(const void* x, void* z, const float* gamma, const float* beta, flo
 
 template <typename T>
 int backward_t(const void* x, const void* gz, void* dx, const float* beta, const float* save, float* dgamma,
-               float* dbeta, float* coef, float* partial, int dtype, int64_t M, int C, int act, cudaStream_t st) {
+               float* dbeta, float* coef, float* partial, int dtype, int64_t M, int C, int act, cudaStream_t st,
+               int64_t gz_pitch) {
     const int nblk = blocks_for(dtype, M, C);
-    if (act) bwd_reduce_kernel<T, true><<<nblk, THREADS, 0, st>>>((const uint4*)x, (const uint4*)gz, save, beta, partial, M, C);
-    else bwd_reduce_kernel<T, false><<<nblk, THREADS, 0, st>>>((const uint4*)x, (const uint4*)gz, save, beta, partial, M, C);
+    const int64_t GV = gz_pitch / vec_of(dtype);  // row pitch of gz in 16-byte vectors
+    if (act) bwd_reduce_kernel<T, true><<<nblk, THREADS, 0, st>>>((const uint4*)x, (const uint4*)gz, save, beta, partial, M, C, GV);
+    else bwd_reduce_kernel<T, false><<<nblk, THREADS, 0, st>>>((const uint4*)x, (const uint4*)gz, save, beta, partial, M, C, GV);
     bwd_finalize_kernel<<<(C + FIN_CH - 1) / FIN_CH, FIN_CH * FIN_LANES, 0, st>>>(partial, nblk, save, dgamma, dbeta, coef, M, C);
-    if (act) bwd_apply_kernel<T, true><<<nblk, THREADS, 0, st>>>((const uint4*)x, (const uint4*)gz, (uint4*)dx, save, beta, coef, M, C);
-    else bwd_apply_kernel<T, false><<<nblk, THREADS, 0, st>>>((const uint4*)x, (const uint4*)gz, (uint4*)dx, save, beta, coef, M, C);
+    if (act) bwd_apply_kernel<T, true><<<nblk, THREADS, 0, st>>>((const uint4*)x, (const uint4*)gz, (uint4*)dx, save, beta, coef, M, C, GV);
+    else bwd_apply_kernel<T, false><<<nblk, THREADS, 0, st>>>((const uint4*)x, (const uint4*)gz, (uint4*)dx, save, beta, coef, M, C, GV);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail((int)e, cudaGetErrorString(e));
 }
@@ -500,18 +502,27 @@ int bnact_b200_forward(const void* x, void* z, const float* gamma, const float* 
     }
 }
 
-int bnact_b200_backward(const void* x, const void* gz, void* dx, const float* gamma, const float* beta,
-                        const float* save, float* dgamma, float* dbeta, float* coef, float* partial, int dtype,
-                        int64_t M, int C, int act, void* cuda_stream) {
+int bnact_b200_backward_pitched(const void* x, const void* gz, void* dx, const float* gamma, const float* beta,
+                                const float* save, float* dgamma, float* dbeta, float* coef, float* partial, int dtype,
+                                int64_t M, int C, int act, int64_t gz_pitch, void* cuda_stream) {
     (void)gamma;
     if (!x || !gz || !dx || !beta || !save || !dgamma || !dbeta || !coef || !partial) return fail(-2, "null pointer");
     if (int rc = check_common(dtype, M, C, act)) return rc;
+    if (gz_pitch < C || gz_pitch % vec_of(dtype) || (reinterpret_cast<uintptr_t>(gz) & 15u))
+        return fail(-1, "gz_pitch must be >= C and a whole number of 16-byte vectors, gz 16-byte aligned");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     switch (dtype) {
-        case 0: return backward_t<float>(x, gz, dx, beta, save, dgamma, dbeta, coef, partial, dtype, M, C, act, st);
-        case 1: return backward_t<__half>(x, gz, dx, beta, save, dgamma, dbeta, coef, partial, dtype, M, C, act, st);
-        default: return backward_t<__nv_bfloat16>(x, gz, dx, beta, save, dgamma, dbeta, coef, partial, dtype, M, C, act, st);
+        case 0: return backward_t<float>(x, gz, dx, beta, save, dgamma, dbeta, coef, partial, dtype, M, C, act, st, gz_pitch);
+        case 1: return backward_t<__half>(x, gz, dx, beta, save, dgamma, dbeta, coef, partial, dtype, M, C, act, st, gz_pitch);
+        default: return backward_t<__nv_bfloat16>(x, gz, dx, beta, save, dgamma, dbeta, coef, partial, dtype, M, C, act, st, gz_pitch);
     }
+}
+
+int bnact_b200_backward(const void* x, const void* gz, void* dx, const float* gamma, const float* beta,
+                        const float* save, float* dgamma, float* dbeta, float* coef, float* partial, int dtype,
+                        int64_t M, int C, int act, void* cuda_stream) {
+    return bnact_b200_backward_pitched(x, gz, dx, gamma, beta, save, dgamma, dbeta, coef, partial, dtype, M, C, act, C,
+                                       cuda_stream);
 }
 
 }  // extern "C"
