@@ -44,6 +44,12 @@ int bnact_b200_eval(const void* x, void* z, const void* gamma, const void* beta,
                     const void* running_var, int dtype, int params_in_dtype, int64_t M, int C, float eps, int act,
                     void* cuda_stream);
 
+/* Same, writing z at a row pitch of z_pitch elements: straight into a channel slice of a wider NHWC tensor (the buffer a
+ * torch.cat would otherwise fill with a copy). */
+int bnact_b200_eval_pitched(const void* x, void* z, const void* gamma, const void* beta, const void* running_mean,
+                            const void* running_var, int dtype, int params_in_dtype, int64_t M, int C, float eps, int act,
+                            int64_t z_pitch, void* cuda_stream);
+
 /* coef scratch: [2][C]; dgamma, dbeta: [C] */
 int bnact_b200_backward(const void* x, const void* gz, void* dx, const float* gamma, const float* beta,
                         const float* save, float* dgamma, float* dbeta, float* coef, float* partial, int dtype,

@@ -58,3 +58,24 @@ def test_channels_last_model_feeds_dcnv3_without_layout_copies():
         y = blk(x)
     assert seen["inp"].is_contiguous() and seen["inp"].shape == (2, 16, 16, 64)      # NHWC, dense: no copy was needed
     assert y.data_ptr() == seen["out"].data_ptr() and y.is_contiguous(memory_format=torch.channels_last)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32], ids=["f16", "f32"])
+def test_cat_free_inference_blocks_match_the_cat_path(dtype):
+    """Under no_grad the C3 / C3_DCNV3 blocks let their Conv branches write straight into the concatenated buffer
+    (bnact_b200_eval_pitched); with autograd on they take torch.cat.  Same numbers."""
+    from yolo_dual_b200 import seg
+    from yolo_dual_b200.blocks import C3_DCNV3
+    torch.manual_seed(0)
+    for blk in (seg.C3(64, 64, n=2), seg.C3(64, 128, n=0), C3_DCNV3(64, 64, n=1, dcn_group="gc16")):
+        blk = blk.to(DEV).to(dtype).eval().to(memory_format=torch.channels_last)
+        for m in blk.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.5)
+                m.running_var.uniform_(0.5, 1.5)
+        x = torch.randn(2, 64, 24, 20, device=DEV).to(dtype).contiguous(memory_format=torch.channels_last)
+        with torch.no_grad():
+            a = blk(x)                                   # cat-free path
+        b = blk(x.clone().requires_grad_(True)).detach()  # autograd on: torch.cat path
+        tol = dict(rtol=1e-2, atol=1e-2) if dtype == torch.float16 else dict(rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(a.float(), b.float(), **tol)

@@ -12,7 +12,7 @@ from torch import nn
 from .build import BNACT_LIB
 
 SYMBOLS = ("bnact_b200_version", "bnact_b200_last_error", "bnact_b200_supported", "bnact_b200_partial_floats",
-           "bnact_b200_forward", "bnact_b200_backward", "bnact_b200_backward_pitched", "bnact_b200_eval")
+           "bnact_b200_forward", "bnact_b200_backward", "bnact_b200_backward_pitched", "bnact_b200_eval", "bnact_b200_eval_pitched")
 _DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 _lib = None
 
@@ -37,6 +37,7 @@ def load() -> ctypes.CDLL:
     lib.bnact_b200_backward.argtypes = [vp] * 10 + [ip, i64, ip, ip, vp]
     lib.bnact_b200_eval.argtypes = [vp] * 6 + [ip, ip, i64, ip, fl, ip, vp]
     lib.bnact_b200_backward_pitched.argtypes = [vp] * 10 + [ip, i64, ip, ip, i64, vp]
+    lib.bnact_b200_eval_pitched.argtypes = [vp] * 6 + [ip, ip, i64, ip, fl, ip, i64, vp]
     _lib = lib
     return lib
 
@@ -101,13 +102,10 @@ class FusedBNAct(torch.autograd.Function):
         # strides (H*W*Ct, 1, W*Ct, Ct)) is read in place at its row pitch; anything else is made NHWC-contiguous.
         if gz.dtype != x.dtype:
             gz = gz.to(x.dtype)
-        pitch = c
-        st = gz.stride()
-        if (not gz.is_contiguous(memory_format=torch.channels_last) and st[1] == 1 and st[3] >= c and st[2] == w * st[3]
-                and st[0] == h * st[2] and st[3] % (16 // gz.element_size()) == 0 and gz.data_ptr() % 16 == 0):
-            pitch = st[3]
-        else:
+        pitch = slice_pitch(gz)
+        if pitch is None:
             gz = gz.contiguous(memory_format=torch.channels_last)
+            pitch = c
         dx = torch.empty_like(x)
         small = torch.empty(4 * c, dtype=torch.float32, device=x.device)   # dgamma, dbeta, coef[2]
         partial = torch.empty(lib.bnact_b200_partial_floats(dt, m, c), dtype=torch.float32, device=x.device)
@@ -145,14 +143,31 @@ def usable_eval(y: torch.Tensor, bn: nn.Module, act: nn.Module) -> bool:
     return bool(load().bnact_b200_supported(_DTYPES[y.dtype], y.size(1)))
 
 
-def bn_act_eval(y: torch.Tensor, bn: nn.BatchNorm2d, act: nn.Module) -> torch.Tensor:
-    """act(bn(y)) with running statistics, one pass (callers check `usable_eval` first)."""
+def slice_pitch(t: torch.Tensor):
+    """Row pitch (elements) of `t` if it is a channel slice of a channels-last tensor the kernels can address in place
+    (strides (H*W*Ct, 1, W*Ct, Ct), 16-byte aligned rows), the channel count for a dense NHWC tensor, else None."""
+    n, c, h, w = t.shape
+    if t.is_contiguous(memory_format=torch.channels_last):
+        return c
+    st = t.stride()
+    vec = 16 // t.element_size()
+    if st[1] == 1 and st[3] >= c and st[2] == w * st[3] and st[0] == h * st[2] and st[3] % vec == 0 and t.data_ptr() % 16 == 0:
+        return st[3]
+    return None
+
+
+def bn_act_eval(y: torch.Tensor, bn: nn.BatchNorm2d, act: nn.Module, out: torch.Tensor = None) -> torch.Tensor:
+    """act(bn(y)) with running statistics, one pass (callers check `usable_eval` first).  `out`: write the result into
+    this tensor — a dense NHWC tensor or a channel slice of a wider one (the destination of a would-be torch.cat)."""
     n, c, h, w = y.shape
-    z = torch.empty_like(y)
+    z = torch.empty_like(y) if out is None else out
+    pitch = slice_pitch(z)
+    if pitch is None or z.shape != y.shape or z.dtype != y.dtype:
+        raise ValueError("out must be a dense NHWC tensor or a channel slice of one, same shape and dtype as the input")
     with torch.cuda.device_of(y):
-        _check(load().bnact_b200_eval(y.data_ptr(), z.data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(),
-                                      bn.running_mean.data_ptr(), bn.running_var.data_ptr(), _DTYPES[y.dtype],
-                                      int(bn.weight.dtype != torch.float32), n * h * w, c, float(bn.eps),
-                                      int(isinstance(act, nn.SiLU)), torch.cuda.current_stream().cuda_stream),
+        _check(load().bnact_b200_eval_pitched(y.data_ptr(), z.data_ptr(), bn.weight.data_ptr(), bn.bias.data_ptr(),
+                                              bn.running_mean.data_ptr(), bn.running_var.data_ptr(), _DTYPES[y.dtype],
+                                              int(bn.weight.dtype != torch.float32), n * h * w, c, float(bn.eps),
+                                              int(isinstance(act, nn.SiLU)), pitch, torch.cuda.current_stream().cuda_stream),
                "bnact_b200_eval")
     return z

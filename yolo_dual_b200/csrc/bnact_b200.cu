@@ -240,7 +240,7 @@ __device__ __forceinline__ void load_params(const P* __restrict__ p, int c0, flo
 template <typename T, typename P, bool SILU>
 __global__ void __launch_bounds__(THREADS)
 eval_kernel(const uint4* __restrict__ x, uint4* __restrict__ z, const P* __restrict__ gamma, const P* __restrict__ beta,
-            const P* __restrict__ mean, const P* __restrict__ var, float eps, int64_t M, int C) {
+            const P* __restrict__ mean, const P* __restrict__ var, float eps, int64_t M, int C, int64_t ZV) {
     constexpr int N = Vec<T>::N;
     const int CV = C / N;
     const int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x;
@@ -270,7 +270,7 @@ eval_kernel(const uint4* __restrict__ x, uint4* __restrict__ z, const P* __restr
             Vec<T>::unpack(v[u], f);
 #pragma unroll
             for (int i = 0; i < N; ++i) { const float y = fmaf(f[i], sc[i], sh[i]); f[i] = SILU ? silu_f(y) : y; }
-            z[(r + u * rs) * CV + cv] = Vec<T>::pack(f);
+            z[(r + u * rs) * ZV + cv] = Vec<T>::pack(f);
         }
     }
     for (; r < M; r += rs) {
@@ -278,7 +278,7 @@ eval_kernel(const uint4* __restrict__ x, uint4* __restrict__ z, const P* __restr
         Vec<T>::unpack(__ldg(x + r * CV + cv), f);
 #pragma unroll
         for (int i = 0; i < N; ++i) { const float y = fmaf(f[i], sc[i], sh[i]); f[i] = SILU ? silu_f(y) : y; }
-        z[r * CV + cv] = Vec<T>::pack(f);
+        z[r * ZV + cv] = Vec<T>::pack(f);
     }
 }
 
@@ -451,10 +451,11 @@ int backward_t(const void* x, const void* gz, void* dx, const float* beta, const
 
 template <typename T, typename P>
 int eval_t(const void* x, void* z, const void* gamma, const void* beta, const void* mean, const void* var, int dtype,
-           int64_t M, int C, float eps, int act, cudaStream_t st) {
+           int64_t M, int C, float eps, int act, cudaStream_t st, int64_t z_pitch) {
     const int nblk = blocks_for(dtype, M, C);
-    if (act) eval_kernel<T, P, true><<<nblk, THREADS, 0, st>>>((const uint4*)x, (uint4*)z, (const P*)gamma, (const P*)beta, (const P*)mean, (const P*)var, eps, M, C);
-    else eval_kernel<T, P, false><<<nblk, THREADS, 0, st>>>((const uint4*)x, (uint4*)z, (const P*)gamma, (const P*)beta, (const P*)mean, (const P*)var, eps, M, C);
+    const int64_t ZV = z_pitch / vec_of(dtype);
+    if (act) eval_kernel<T, P, true><<<nblk, THREADS, 0, st>>>((const uint4*)x, (uint4*)z, (const P*)gamma, (const P*)beta, (const P*)mean, (const P*)var, eps, M, C, ZV);
+    else eval_kernel<T, P, false><<<nblk, THREADS, 0, st>>>((const uint4*)x, (uint4*)z, (const P*)gamma, (const P*)beta, (const P*)mean, (const P*)var, eps, M, C, ZV);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail((int)e, cudaGetErrorString(e));
 }
@@ -463,43 +464,29 @@ int eval_t(const void* x, void* z, const void* gamma, const void* beta, const vo
 
 extern "C" {
 
-int bnact_b200_eval(const void* x, void* z, const void* gamma, const void* beta, const void* running_mean,
-                    const void* running_var, int dtype, int params_in_dtype, int64_t M, int C, float eps, int act,
-                    void* cuda_stream) {
+int bnact_b200_eval_pitched(const void* x, void* z, const void* gamma, const void* beta, const void* running_mean,
+                            const void* running_var, int dtype, int params_in_dtype, int64_t M, int C, float eps, int act,
+                            int64_t z_pitch, void* cuda_stream) {
     if (!x || !z || !gamma || !beta || !running_mean || !running_var) return fail(-2, "null pointer");
     if (int rc = check_common(dtype, M, C, act)) return rc;
+    if (z_pitch < C || z_pitch % vec_of(dtype) || (reinterpret_cast<uintptr_t>(z) & 15u))
+        return fail(-1, "z_pitch must be >= C and a whole number of 16-byte vectors, z 16-byte aligned");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const bool pt = params_in_dtype != 0 && dtype != 0;
     switch (dtype) {
-        case 0: return eval_t<float, float>(x, z, gamma, beta, running_mean, running_var, dtype, M, C, eps, act, st);
-        case 1: return pt ? eval_t<__half, __half>(x, z, gamma, beta, running_mean, running_var, dtype, M, C, eps, act, st)
-                          : eval_t<__half, float>(x, z, gamma, beta, running_mean, running_var, dtype, M, C, eps, act, st);
-        default: return pt ? eval_t<__nv_bfloat16, __nv_bfloat16>(x, z, gamma, beta, running_mean, running_var, dtype, M, C, eps, act, st)
-                           : eval_t<__nv_bfloat16, float>(x, z, gamma, beta, running_mean, running_var, dtype, M, C, eps, act, st);
+        case 0: return eval_t<float, float>(x, z, gamma, beta, running_mean, running_var, dtype, M, C, eps, act, st, z_pitch);
+        case 1: return pt ? eval_t<__half, __half>(x, z, gamma, beta, running_mean, running_var, dtype, M, C, eps, act, st, z_pitch)
+                          : eval_t<__half, float>(x, z, gamma, beta, running_mean, running_var, dtype, M, C, eps, act, st, z_pitch);
+        default: return pt ? eval_t<__nv_bfloat16, __nv_bfloat16>(x, z, gamma, beta, running_mean, running_var, dtype, M, C, eps, act, st, z_pitch)
+                           : eval_t<__nv_bfloat16, float>(x, z, gamma, beta, running_mean, running_var, dtype, M, C, eps, act, st, z_pitch);
     }
 }
 
-
-int bnact_b200_version(void) { return BNACT_B200_VERSION; }
-const char* bnact_b200_last_error(void) { return g_err; }
-int bnact_b200_supported(int dtype, int C) { return supported(dtype, C) ? 1 : 0; }
-
-size_t bnact_b200_partial_floats(int dtype, int64_t M, int C) {
-    if (!supported(dtype, C) || M <= 0) return 0;
-    return (size_t)blocks_for(dtype, M, C) * 2 * (size_t)C;
-}
-
-int bnact_b200_forward(const void* x, void* z, const float* gamma, const float* beta, float* running_mean,
-                       float* running_var, float* save, float* partial, int dtype, int64_t M, int C, float eps,
-                       float momentum, int act, void* cuda_stream) {
-    if (!x || !z || !gamma || !beta || !save || !partial) return fail(-2, "null pointer");
-    if (int rc = check_common(dtype, M, C, act)) return rc;
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    switch (dtype) {
-        case 0: return forward_t<float>(x, z, gamma, beta, running_mean, running_var, save, partial, dtype, M, C, eps, momentum, act, st);
-        case 1: return forward_t<__half>(x, z, gamma, beta, running_mean, running_var, save, partial, dtype, M, C, eps, momentum, act, st);
-        default: return forward_t<__nv_bfloat16>(x, z, gamma, beta, running_mean, running_var, save, partial, dtype, M, C, eps, momentum, act, st);
-    }
+int bnact_b200_eval(const void* x, void* z, const void* gamma, const void* beta, const void* running_mean,
+                    const void* running_var, int dtype, int params_in_dtype, int64_t M, int C, float eps, int act,
+                    void* cuda_stream) {
+    return bnact_b200_eval_pitched(x, z, gamma, beta, running_mean, running_var, dtype, params_in_dtype, M, C, eps, act, C,
+                                   cuda_stream);
 }
 
 int bnact_b200_backward_pitched(const void* x, const void* gz, void* dx, const float* gamma, const float* beta,

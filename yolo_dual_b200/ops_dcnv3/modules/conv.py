@@ -30,16 +30,23 @@ class Conv(nn.Module):
         else:
             self.act = act if isinstance(act, nn.Module) else nn.Identity()
 
-    def forward(self, x):
+    def forward(self, x, out=None):
+        """`out` (inference only): a channel slice of a wider channels-last tensor to write the result into, so that the
+        caller's torch.cat of this block's output costs nothing."""
         y = self.conv(x)
         if y.is_cuda:
             from ... import _bnact   # fused BatchNorm + SiLU (csrc/bnact_b200.cu) where it applies
             if self.training:        # batch statistics, with autograd
-                if _bnact.usable(y, self.bn, self.act):
+                if out is None and _bnact.usable(y, self.bn, self.act):
                     return _bnact.bn_act(y, self.bn, self.act)
             elif _bnact.usable_eval(y, self.bn, self.act):   # inference: running statistics, one pass
-                return _bnact.bn_act_eval(y, self.bn, self.act)
-        return self.act(self.bn(y))
+                if out is None or _bnact.slice_pitch(out) is not None:
+                    return _bnact.bn_act_eval(y, self.bn, self.act, out)
+        z = self.act(self.bn(y))
+        if out is not None:
+            out.copy_(z)
+            return out
+        return z
 
     def forward_fuse(self, x):  # after conv+bn folding
         return self.act(self.conv(x))

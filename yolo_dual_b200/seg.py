@@ -82,6 +82,11 @@ CAMVID_CLASS_WEIGHTS = [1.0, 2.0, 25.0, 2.0, 10.0, 3.0, 25.0, 10.0, 5.0, 15.0, 2
 # ---------------------------------------------------------------------------------------------
 # plain blocks of the seg scripts (outer residual when c1 == c2; no inner bottleneck residual)
 # ---------------------------------------------------------------------------------------------
+def _cat_free(x: torch.Tensor) -> bool:
+    """Inference on a channels-last CUDA activation: `Conv(x, out=slice)` can fill a concatenated buffer in place."""
+    return x.is_cuda and not torch.is_grad_enabled() and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
+
+
 class C3(nn.Module):
     """seg_diceloss_yolov5.py:415-428"""
 
@@ -95,7 +100,18 @@ class C3(nn.Module):
         self.add = shortcut and c1 == c2
 
     def forward(self, x):
-        y = self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), 1))
+        if _cat_free(x):  # inference: both branches end in a Conv block, which writes straight into its half of the
+            c_ = self.cv2.conv.out_channels   # concatenated tensor (no torch.cat copy)
+            buf = x.new_empty((x.shape[0], 2 * c_, x.shape[2], x.shape[3])).contiguous(memory_format=torch.channels_last)
+            convs = [self.cv1] + list(self.m)
+            t = x
+            for conv in convs[:-1]:
+                t = conv(t)
+            convs[-1](t, out=buf[:, :c_])
+            self.cv2(x, out=buf[:, c_:])
+            y = self.cv3(buf)
+        else:
+            y = self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), 1))
         return y + x if self.add else y
 
 
