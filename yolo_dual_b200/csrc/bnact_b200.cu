@@ -489,6 +489,28 @@ int bnact_b200_eval(const void* x, void* z, const void* gamma, const void* beta,
                                    cuda_stream);
 }
 
+int bnact_b200_version(void) { return BNACT_B200_VERSION; }
+const char* bnact_b200_last_error(void) { return g_err; }
+int bnact_b200_supported(int dtype, int C) { return supported(dtype, C) ? 1 : 0; }
+
+size_t bnact_b200_partial_floats(int dtype, int64_t M, int C) {
+    if (!supported(dtype, C) || M <= 0) return 0;
+    return (size_t)blocks_for(dtype, M, C) * 2 * (size_t)C;
+}
+
+int bnact_b200_forward(const void* x, void* z, const float* gamma, const float* beta, float* running_mean,
+                       float* running_var, float* save, float* partial, int dtype, int64_t M, int C, float eps,
+                       float momentum, int act, void* cuda_stream) {
+    if (!x || !z || !gamma || !beta || !save || !partial) return fail(-2, "null pointer");
+    if (int rc = check_common(dtype, M, C, act)) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    switch (dtype) {
+        case 0: return forward_t<float>(x, z, gamma, beta, running_mean, running_var, save, partial, dtype, M, C, eps, momentum, act, st);
+        case 1: return forward_t<__half>(x, z, gamma, beta, running_mean, running_var, save, partial, dtype, M, C, eps, momentum, act, st);
+        default: return forward_t<__nv_bfloat16>(x, z, gamma, beta, running_mean, running_var, save, partial, dtype, M, C, eps, momentum, act, st);
+    }
+}
+
 int bnact_b200_backward_pitched(const void* x, const void* gz, void* dx, const float* gamma, const float* beta,
                                 const float* save, float* dgamma, float* dbeta, float* coef, float* partial, int dtype,
                                 int64_t M, int C, int act, int64_t gz_pitch, void* cuda_stream) {
