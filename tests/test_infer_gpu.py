@@ -62,8 +62,9 @@ def test_channels_last_model_feeds_dcnv3_without_layout_copies():
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32], ids=["f16", "f32"])
 def test_cat_free_inference_blocks_match_the_cat_path(dtype):
-    """Under no_grad the C3 / C3_DCNV3 blocks let their Conv branches write straight into the concatenated buffer
-    (bnact_b200_eval_pitched); with autograd on they take torch.cat.  Same numbers."""
+    """Under no_grad the plain C3 blocks let their Conv branches write straight into the concatenated buffer
+    (bnact_b200_eval_pitched); with autograd on they take torch.cat.  Same numbers.  (C3_DCNV3 keeps torch.cat: its DCNv3
+    branch would need a strided copy that is slower than cat's own kernel.)"""
     from yolo_dual_b200 import seg
     from yolo_dual_b200.blocks import C3_DCNV3
     torch.manual_seed(0)

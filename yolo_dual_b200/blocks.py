@@ -81,14 +81,6 @@ class C3_DCNV3(nn.Module):
                                                   fused_softmax=fused_softmax, packed_heads=packed_heads) for _ in range(n)))
 
     def forward(self, x):
-        if x.is_cuda and not torch.is_grad_enabled() and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last):
-            # inference: cv2 writes straight into its half of the concatenated tensor, the DCNv3 branch is copied into the
-            # other half (what torch.cat would do for it anyway)
-            c_ = self.cv2.conv.out_channels
-            buf = x.new_empty((x.shape[0], 2 * c_, x.shape[2], x.shape[3])).contiguous(memory_format=torch.channels_last)
-            buf[:, :c_].copy_(self.m(self.cv1(x)))
-            self.cv2(x, out=buf[:, c_:])
-            return self.cv3(buf)
         return self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), 1))
 
 

@@ -102,7 +102,8 @@ class C3(nn.Module):
     def forward(self, x):
         if _cat_free(x):  # inference: both branches end in a Conv block, which writes straight into its half of the
             c_ = self.cv2.conv.out_channels   # concatenated tensor (no torch.cat copy)
-            buf = x.new_empty((x.shape[0], 2 * c_, x.shape[2], x.shape[3])).contiguous(memory_format=torch.channels_last)
+            buf = torch.empty((x.shape[0], 2 * c_, x.shape[2], x.shape[3]), dtype=x.dtype, device=x.device,
+                              memory_format=torch.channels_last)
             convs = [self.cv1] + list(self.m)
             t = x
             for conv in convs[:-1]:
