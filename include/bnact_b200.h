@@ -37,6 +37,11 @@ int bnact_b200_forward(const void* x, void* z, const float* gamma, const float* 
                        float* running_var, float* save, float* partial, int dtype, int64_t M, int C, float eps,
                        float momentum, int act, void* cuda_stream);
 
+/* bnact_b200_forward writing z at a row pitch of z_pitch elements (a channel slice of a wider NHWC tensor). */
+int bnact_b200_forward_pitched(const void* x, void* z, const float* gamma, const float* beta, float* running_mean,
+                               float* running_var, float* save, float* partial, int dtype, int64_t M, int C, float eps,
+                               float momentum, int act, int64_t z_pitch, void* cuda_stream);
+
 /* Inference: z = act((x - running_mean) * gamma / sqrt(running_var + eps) + beta) in one pass (PyTorch: transform +
  * SiLU = two passes and a tiny invstd kernel).  The four per-channel vectors are float32 (params_in_dtype = 0) or in the
  * activation's own 16-bit dtype (params_in_dtype = 1: a model cast with .half() / .bfloat16()).  No autograd side. */

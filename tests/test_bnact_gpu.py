@@ -186,3 +186,44 @@ def test_backward_reads_the_gradient_of_a_cat_slice_in_place(dtype, monkeypatch)
     for g, w_ in zip(got, want):
         s = max(1.0, float(w_.abs().max()))
         torch.testing.assert_close(g / s, w_ / s, **tol)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n", [0, 2])
+def test_training_c3_without_cat_matches_the_cat_path(dtype, n, monkeypatch):
+    """seg.C3 in training: both branches' Conv blocks write into one buffer (FusedBNActInto chained through it, no
+    torch.cat, the backward reads the slices of the buffer's gradient in place) — same outputs, gradients and running
+    statistics as the torch.cat path on the torch ops."""
+    from yolo_dual_b200 import seg
+    torch.manual_seed(0)
+    blk = seg.C3(32, 64, n=n).to(DEV).to(memory_format=torch.channels_last).train()
+    ref = seg.C3(32, 64, n=n).to(DEV).to(memory_format=torch.channels_last).train()
+    ref.load_state_dict(blk.state_dict())
+    x = torch.randn(4, 32, 16, 12, device=DEV).contiguous(memory_format=torch.channels_last)
+    wgt = torch.randn(4, 64, 16, 12, device=DEV)
+    used = []
+    orig = _bnact.bn_act_into
+    monkeypatch.setattr(_bnact, "bn_act_into", lambda *a: (used.append(a[4]), orig(*a))[1])
+
+    def run(m):
+        xi = x.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=dtype, enabled=dtype != torch.float32):
+            y = m(xi)
+        (y.float() * wgt).sum().backward()
+        return y.detach().float(), xi.grad, [p.grad for p in m.parameters()], [b.clone() for b in m.buffers()]
+
+    ya, gxa, gpa, bufa = run(blk)
+    assert used == [0, 32], used                      # two slice writers, channel offsets 0 and c_
+    monkeypatch.setenv("YOLO_DUAL_B200_FUSED_BN", "0")
+    yb, gxb, gpb, bufb = run(ref)
+    tol = dict(rtol=1e-4, atol=1e-4) if dtype == torch.float32 else dict(rtol=3e-2, atol=3e-2)
+
+    def close(a_, b_):
+        s_ = max(1.0, float(b_.float().abs().max()))
+        torch.testing.assert_close(a_.float() / s_, b_.float() / s_, **tol)
+    close(ya, yb)
+    close(gxa, gxb)
+    for a_, b_ in zip(gpa, gpb):
+        close(a_, b_)
+    for a_, b_ in zip(bufa, bufb):
+        close(a_, b_)

@@ -12,7 +12,7 @@ from torch import nn
 from .build import BNACT_LIB
 
 SYMBOLS = ("bnact_b200_version", "bnact_b200_last_error", "bnact_b200_supported", "bnact_b200_partial_floats",
-           "bnact_b200_forward", "bnact_b200_backward", "bnact_b200_backward_pitched", "bnact_b200_eval", "bnact_b200_eval_pitched")
+           "bnact_b200_forward", "bnact_b200_forward_pitched", "bnact_b200_backward", "bnact_b200_backward_pitched", "bnact_b200_eval", "bnact_b200_eval_pitched")
 _DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 _lib = None
 
@@ -34,6 +34,7 @@ def load() -> ctypes.CDLL:
     lib.bnact_b200_partial_floats.argtypes = [ip, i64, ip]
     lib.bnact_b200_partial_floats.restype = ctypes.c_size_t
     lib.bnact_b200_forward.argtypes = [vp] * 8 + [ip, i64, ip, fl, fl, ip, vp]
+    lib.bnact_b200_forward_pitched.argtypes = [vp] * 8 + [ip, i64, ip, fl, fl, ip, i64, vp]
     lib.bnact_b200_backward.argtypes = [vp] * 10 + [ip, i64, ip, ip, vp]
     lib.bnact_b200_eval.argtypes = [vp] * 6 + [ip, ip, i64, ip, fl, ip, vp]
     lib.bnact_b200_backward_pitched.argtypes = [vp] * 10 + [ip, i64, ip, ip, i64, vp]
@@ -115,6 +116,70 @@ class FusedBNAct(torch.autograd.Function):
                 small.data_ptr(), small[c:].data_ptr(), small[2 * c:].data_ptr(), partial.data_ptr(), dt, m, c,
                 ctx.silu, pitch, torch.cuda.current_stream().cuda_stream), "bnact_b200_backward")
         return dx, small[:c], small[c:2 * c], None, None, None, None, None
+
+
+class FusedBNActInto(torch.autograd.Function):
+    """FusedBNAct whose result lands in channels [c0, c0 + C) of `buf`, a dense channels-last tensor that stands for the
+    torch.cat of several such results: forward writes the slice in place and returns `buf` (marked dirty), backward reads
+    ITS slice of buf's gradient at the row pitch and passes the whole gradient on to the previous writer.  Chaining
+    `buf = FusedBNActInto.apply(y1, ..., buf, 0); buf = FusedBNActInto.apply(y2, ..., buf, C1)` builds cat((z1, z2), 1)
+    with no copy in either direction."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum, silu, buf, c0):
+        n, c, h, w = x.shape
+        m = n * h * w
+        dt = _DTYPES[x.dtype]
+        lib = load()
+        z = buf[:, c0:c0 + c]
+        pitch = slice_pitch(z)
+        if pitch is None or z.shape != x.shape or buf.dtype != x.dtype or not buf.is_contiguous(memory_format=torch.channels_last):
+            raise ValueError("buf must be a dense channels-last tensor of x's dtype with room for x's channels at c0")
+        save = torch.empty(4 * c, dtype=torch.float32, device=x.device)
+        partial = torch.empty(lib.bnact_b200_partial_floats(dt, m, c), dtype=torch.float32, device=x.device)
+        with torch.cuda.device_of(x):
+            _check(lib.bnact_b200_forward_pitched(
+                x.data_ptr(), z.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                running_mean.data_ptr() if running_mean is not None else None,
+                running_var.data_ptr() if running_var is not None else None,
+                save.data_ptr(), partial.data_ptr(), dt, m, c, float(eps), float(momentum), int(silu), pitch,
+                torch.cuda.current_stream().cuda_stream), "bnact_b200_forward")
+        ctx.save_for_backward(x, gamma, beta, save)
+        ctx.silu, ctx.c0 = int(silu), int(c0)
+        ctx.mark_dirty(buf)
+        return buf
+
+    @staticmethod
+    def backward(ctx, gbuf):
+        x, gamma, beta, save = ctx.saved_tensors
+        n, c, h, w = x.shape
+        m = n * h * w
+        dt = _DTYPES[x.dtype]
+        lib = load()
+        if gbuf.dtype != x.dtype:
+            gbuf = gbuf.to(x.dtype)
+        gz = gbuf[:, ctx.c0:ctx.c0 + c]
+        pitch = slice_pitch(gz)
+        if pitch is None:
+            gz = gz.contiguous(memory_format=torch.channels_last)
+            pitch = c
+        dx = torch.empty_like(x)
+        small = torch.empty(4 * c, dtype=torch.float32, device=x.device)
+        partial = torch.empty(lib.bnact_b200_partial_floats(dt, m, c), dtype=torch.float32, device=x.device)
+        with torch.cuda.device_of(x):
+            _check(lib.bnact_b200_backward_pitched(
+                x.data_ptr(), gz.data_ptr(), dx.data_ptr(), gamma.data_ptr(), beta.data_ptr(), save.data_ptr(),
+                small.data_ptr(), small[c:].data_ptr(), small[2 * c:].data_ptr(), partial.data_ptr(), dt, m, c,
+                ctx.silu, pitch, torch.cuda.current_stream().cuda_stream), "bnact_b200_backward")
+        return dx, small[:c], small[c:2 * c], None, None, None, None, None, gbuf, None
+
+
+def bn_act_into(y: torch.Tensor, bn: nn.BatchNorm2d, act: nn.Module, buf: torch.Tensor, c0: int) -> torch.Tensor:
+    """act(bn(y)) written into channels [c0, c0 + C) of `buf`; returns `buf` (callers check `usable` first)."""
+    if bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    rm, rv = (bn.running_mean, bn.running_var) if bn.track_running_stats else (None, None)
+    return FusedBNActInto.apply(y, bn.weight, bn.bias, rm, rv, bn.eps, bn.momentum, isinstance(act, nn.SiLU), buf, c0)
 
 
 def bn_act(y: torch.Tensor, bn: nn.BatchNorm2d, act: nn.Module) -> torch.Tensor:

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(FIN_CH * FIN_LANES) stats_finalize_kernel(cons
 
 template <typename T, bool SILU>
 __global__ void __launch_bounds__(THREADS)
-apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ z, const float* __restrict__ save, int64_t M, int C) {
+apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ z, const float* __restrict__ save, int64_t M, int C, int64_t ZV) {
     constexpr int N = Vec<T>::N;
     const int CV = C / N;
     const int64_t g = (int64_t)blockIdx.x * THREADS + threadIdx.x;
@@ -217,7 +217,7 @@ apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ z, const float* __
             Vec<T>::unpack(v[u], f);
 #pragma unroll
             for (int i = 0; i < N; ++i) { const float y = fmaf(f[i], sc[i], sh[i]); f[i] = SILU ? silu_f(y) : y; }
-            z[(r + u * rs) * CV + cv] = Vec<T>::pack(f);
+            z[(r + u * rs) * ZV + cv] = Vec<T>::pack(f);
         }
     }
     for (; r < M; r += rs) {
@@ -225,7 +225,7 @@ apply_kernel(const uint4* __restrict__ x, uint4* __restrict__ z, const float* __
         Vec<T>::unpack(__ldg(x + r * CV + cv), f);
 #pragma unroll
         for (int i = 0; i < N; ++i) { const float y = fmaf(f[i], sc[i], sh[i]); f[i] = SILU ? silu_f(y) : y; }
-        z[r * CV + cv] = Vec<T>::pack(f);
+        z[r * ZV + cv] = Vec<T>::pack(f);
     }
 }
 
@@ -423,13 +423,15 @@ int check_common(int dtype, int64_t M, int C, int act) {
 
 template <typename T>
 int forward_t(const void* x, void* z, const float* gamma, const float* beta, float* rm, float* rv, float* save,
-              float* partial, int dtype, int64_t M, int C, float eps, float momentum, int act, cudaStream_t st) {
+              float* partial, int dtype, int64_t M, int C, float eps, float momentum, int act, cudaStream_t st,
+              int64_t z_pitch) {
     const int nblk = blocks_for(dtype, M, C);
+    const int64_t ZV = z_pitch / vec_of(dtype);
     stats_kernel<T><<<nblk, THREADS, 0, st>>>((const uint4*)x, partial, M, C);
     stats_finalize_kernel<T><<<(C + FIN_CH - 1) / FIN_CH, FIN_CH * FIN_LANES, 0, st>>>((const T*)x, partial, nblk, gamma, beta, rm, rv, save, M, C,
                                                              eps, momentum);
-    if (act) apply_kernel<T, true><<<nblk, THREADS, 0, st>>>((const uint4*)x, (uint4*)z, save, M, C);
-    else apply_kernel<T, false><<<nblk, THREADS, 0, st>>>((const uint4*)x, (uint4*)z, save, M, C);
+    if (act) apply_kernel<T, true><<<nblk, THREADS, 0, st>>>((const uint4*)x, (uint4*)z, save, M, C, ZV);
+    else apply_kernel<T, false><<<nblk, THREADS, 0, st>>>((const uint4*)x, (uint4*)z, save, M, C, ZV);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : fail((int)e, cudaGetErrorString(e));
 }
@@ -498,17 +500,26 @@ size_t bnact_b200_partial_floats(int dtype, int64_t M, int C) {
     return (size_t)blocks_for(dtype, M, C) * 2 * (size_t)C;
 }
 
+int bnact_b200_forward_pitched(const void* x, void* z, const float* gamma, const float* beta, float* running_mean,
+                               float* running_var, float* save, float* partial, int dtype, int64_t M, int C, float eps,
+                               float momentum, int act, int64_t z_pitch, void* cuda_stream) {
+    if (!x || !z || !gamma || !beta || !save || !partial) return fail(-2, "null pointer");
+    if (int rc = check_common(dtype, M, C, act)) return rc;
+    if (z_pitch < C || z_pitch % vec_of(dtype) || (reinterpret_cast<uintptr_t>(z) & 15u))
+        return fail(-1, "z_pitch must be >= C and a whole number of 16-byte vectors, z 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    switch (dtype) {
+        case 0: return forward_t<float>(x, z, gamma, beta, running_mean, running_var, save, partial, dtype, M, C, eps, momentum, act, st, z_pitch);
+        case 1: return forward_t<__half>(x, z, gamma, beta, running_mean, running_var, save, partial, dtype, M, C, eps, momentum, act, st, z_pitch);
+        default: return forward_t<__nv_bfloat16>(x, z, gamma, beta, running_mean, running_var, save, partial, dtype, M, C, eps, momentum, act, st, z_pitch);
+    }
+}
+
 int bnact_b200_forward(const void* x, void* z, const float* gamma, const float* beta, float* running_mean,
                        float* running_var, float* save, float* partial, int dtype, int64_t M, int C, float eps,
                        float momentum, int act, void* cuda_stream) {
-    if (!x || !z || !gamma || !beta || !save || !partial) return fail(-2, "null pointer");
-    if (int rc = check_common(dtype, M, C, act)) return rc;
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    switch (dtype) {
-        case 0: return forward_t<float>(x, z, gamma, beta, running_mean, running_var, save, partial, dtype, M, C, eps, momentum, act, st);
-        case 1: return forward_t<__half>(x, z, gamma, beta, running_mean, running_var, save, partial, dtype, M, C, eps, momentum, act, st);
-        default: return forward_t<__nv_bfloat16>(x, z, gamma, beta, running_mean, running_var, save, partial, dtype, M, C, eps, momentum, act, st);
-    }
+    return bnact_b200_forward_pitched(x, z, gamma, beta, running_mean, running_var, save, partial, dtype, M, C, eps,
+                                      momentum, act, C, cuda_stream);
 }
 
 int bnact_b200_backward_pitched(const void* x, const void* gz, void* dx, const float* gamma, const float* beta,

@@ -48,5 +48,19 @@ class Conv(nn.Module):
             return out
         return z
 
+    def forward_into(self, x, buf, c0):
+        """Training-time counterpart of `forward(x, out=...)`: the block's result becomes channels [c0, c0 + c2) of `buf`
+        (a dense channels-last tensor standing for a torch.cat), with autograd; returns the tensor to use as `buf` from
+        here on."""
+        y = self.conv(x)
+        if y.is_cuda and self.training:
+            from ... import _bnact
+            if _bnact.usable(y, self.bn, self.act) and buf.dtype == y.dtype:
+                return _bnact.bn_act_into(y, self.bn, self.act, buf, c0)
+        z = self.act(self.bn(y))           # anything the fused kernels do not take: autograd's own slice assignment
+        buf = buf.clone() if buf.requires_grad and buf.is_leaf else buf
+        buf[:, c0:c0 + z.shape[1]] = z.to(buf.dtype)
+        return buf
+
     def forward_fuse(self, x):  # after conv+bn folding
         return self.act(self.conv(x))

@@ -87,6 +87,13 @@ def _cat_free(x: torch.Tensor) -> bool:
     return x.is_cuda and not torch.is_grad_enabled() and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
 
 
+def _cat_free_train(block: nn.Module, x: torch.Tensor) -> bool:
+    """Training on a channels-last CUDA activation with the fused BatchNorm + SiLU in use."""
+    from . import _bnact
+    return (x.is_cuda and block.training and torch.is_grad_enabled() and x.dim() == 4 and _bnact.enabled()
+            and x.is_contiguous(memory_format=torch.channels_last) and x.dtype in (torch.float32, torch.float16, torch.bfloat16))
+
+
 class C3(nn.Module):
     """seg_diceloss_yolov5.py:415-428"""
 
@@ -110,6 +117,18 @@ class C3(nn.Module):
                 t = conv(t)
             convs[-1](t, out=buf[:, :c_])
             self.cv2(x, out=buf[:, c_:])
+            y = self.cv3(buf)
+        elif _cat_free_train(self, x):  # training: the same, with autograd (FusedBNActInto chains through the buffer)
+            c_ = self.cv2.conv.out_channels
+            dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+            buf = torch.empty((x.shape[0], 2 * c_, x.shape[2], x.shape[3]), dtype=dt, device=x.device,
+                              memory_format=torch.channels_last)
+            convs = [self.cv1] + list(self.m)
+            t = x
+            for conv in convs[:-1]:
+                t = conv(t)
+            buf = convs[-1].forward_into(t, buf, 0)
+            buf = self.cv2.forward_into(x, buf, c_)
             y = self.cv3(buf)
         else:
             y = self.cv3(torch.cat((self.m(self.cv1(x)), self.cv2(x)), 1))
