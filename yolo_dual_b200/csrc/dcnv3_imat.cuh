@@ -1222,8 +1222,11 @@ __device__ __forceinline__ void corner16(float2 (&acc)[8], uint32_t a0, uint32_t
 // chunk 2g + 1 - h second, so in either LDS.128 the eight lanes of a quarter-warp still touch eight different
 // bank groups; one shuffle exchange per pixel merges the halves.  4.5 locates per lane instead of 9.
 // (The same split over L1 — fwd_pts_kernel — lost: there a 32-byte request costs L1 two passes.)
+#ifndef DCNV3_FWD_MIN_CTAS
+#define DCNV3_FWD_MIN_CTAS 3  // A/B on one box (round 2): 4 CTAs per SM at 64 registers — see profiles/r02_fwd_occupancy.md
+#endif
 template <typename T, bool LOGITS>
-__global__ void __launch_bounds__(kFwdTileThreads, 3)
+__global__ void __launch_bounds__(kFwdTileThreads, DCNV3_FWD_MIN_CTAS)
 fwd_tile_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
                 T *__restrict__ out, const Geo q, const int GQ) {
     extern __shared__ __align__(128) unsigned char smem[];
