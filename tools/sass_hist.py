@@ -14,7 +14,7 @@ for line in sass.splitlines():
         cur = m.group(1)
         hist[cur] = collections.Counter()
         continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", line)
+    m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", line)
     if m and cur:
         op = m.group(1)
         key = op if op.startswith(("LDS", "STS", "LDSM", "STSM", "LDG", "STG", "RED", "ATOM", "HMMA", "LDGSTS", "FHFMA", "UTC", "LDTM", "STTM", "UTMA", "BAR", "SHFL")) else op.split(".")[0]
