@@ -97,7 +97,7 @@ def main():
                             N, HW, HW, G * P).to(dtype).contiguous()
                         go = torch.randn(N, HW, HW, C, device=dev, generator=g).to(dtype)
                         out, gi, goff, gm = (torch.empty_like(t) for t in (x, x, off, m))
-                        wsb = lib.dcnv3_b200_backward_workspace_bytes(dt, ctypes.byref(geo), 0)
+                        wsb = lib.dcnv3_b200_backward_workspace_bytes(dt, ctypes.byref(geo), _lib.ACC_TILE)
                         ws = torch.empty(max(wsb, 16), dtype=torch.uint8, device=dev)
                         sets.append((x, off, m, go, out, gi, goff, gm, ws, wsb))
 
@@ -110,7 +110,7 @@ def main():
                         x, off, m, go, out, gi, goff, gm, ws, wsb = sets[k % nset]
                         _lib.check(lib.dcnv3_b200_backward(x.data_ptr(), off.data_ptr(), m.data_ptr(), go.data_ptr(),
                                                            gi.data_ptr(), goff.data_ptr(), gm.data_ptr(), ws.data_ptr(),
-                                                           wsb, dt, ctypes.byref(geo), 0, 0, st), "bwd")
+                                                           wsb, dt, ctypes.byref(geo), 0, _lib.ACC_TILE, st), "bwd")
 
                     res = []
                     for f in (fwd, bwd):
@@ -127,8 +127,8 @@ def main():
                     vec = gc % (16 // e) == 0 and (gc // (16 // e)) & (gc // (16 // e) - 1) == 0 and gc // (16 // e) <= 32
                     name = {torch.float32: "fp32", torch.float16: "fp16", torch.bfloat16: "bf16"}[dtype]
                     fg, bg = fwd_b / res[0] / 1e3, bwd_b / res[1] / 1e3
-                    win = e == 2 and gc == 16 and G % 4 == 0  # staged-window forward + interpolation-matrix backward
-                    print(f"| {C} | {G} | {gc} | {HW}x{HW} | {name} | {'win/imat' if win else 'vec' if vec else '(generic)'} | {res[0]:.1f} | "
+                    win = e == 2 and gc == 16 and G % 4 == 0  # staged-window forward + window backward (grad_accum 'tile')
+                    print(f"| {C} | {G} | {gc} | {HW}x{HW} | {name} | {'win' if win else 'vec' if vec else '(generic)'} | {res[0]:.1f} | "
                           f"{fg:.0f} | {100 * fg / peak:.1f} | {res[1]:.1f} | {bg:.0f} | {100 * bg / peak:.1f} |", flush=True)
                     del sets
                     torch.cuda.empty_cache()
