@@ -559,6 +559,9 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         }
     }
     __syncthreads();  // barrier D: the interpolation matrix is zero
+#ifdef DCNV3_WIN_RMW_PIPE
+    uint32_t ent_e[9], ent_w[9], ent_on = 0u;
+#endif
     uint32_t slowmask = 0u;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
@@ -576,6 +579,15 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         const float hm = hh * mk[k], lm = t.lh * mk[k];
         const uint32_t top = imat::pack2<__half>(hm * hw, hm * t.lw), bot = imat::pack2<__half>(lm * hw, lm * t.lw);
         const bool keep_top = ((vb & 1u) == (unsigned)h);
+#ifdef DCNV3_WIN_RMW_PIPE
+        ent_e[2 * k] = keep_top ? e : e + kWinW; ent_w[2 * k] = keep_top ? top : bot; ent_on |= (fast ? 1u : 0u) << (2 * k);
+        if (k < 4) {
+            const uint32_t se = (keep_top ? e + kWinW : e) | (fast ? 256u : 0u);
+            const uint32_t re = __shfl_xor_sync(0xffffffffu, se, 1);
+            ent_w[2 * k + 1] = __shfl_xor_sync(0xffffffffu, keep_top ? bot : top, 1);
+            ent_e[2 * k + 1] = re & 255u; ent_on |= ((re >> 8) & 1u) << (2 * k + 1);
+        }
+#else
         wm_add(row_s, keep_top ? e : e + kWinW, keep_top ? top : bot, fast);
         if (k < 4) {
             const uint32_t se = (keep_top ? e + kWinW : e) | (fast ? 256u : 0u);
@@ -583,7 +595,38 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
             const uint32_t rw = __shfl_xor_sync(0xffffffffu, keep_top ? bot : top, 1);
             wm_add(row_s, re & 255u, rw, (re & 256u) != 0u);
         }
+#endif
     }
+#ifdef DCNV3_WIN_RMW_PIPE
+    {   // the nine read-modify-writes as a software pipeline: entry i + 1's two words are loaded BEFORE entry i's stores
+        // (its shared-memory latency overlaps entry i's adds and stores); if it touches a word entry i has just rewritten,
+        // the new value is forwarded in registers.  Entries further apart are ordered by the hardware (same thread,
+        // same address, program order).
+        uint32_t wa = row_s + ((ent_e[0] >> 1) << 2);
+        uint32_t w0 = lds32(wa), w1 = lds32(wa + 4);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            uint32_t wan = 0u, n0 = 0u, n1 = 0u;
+            if (i < 8) {
+                wan = row_s + ((ent_e[i + 1] >> 1) << 2);
+                n0 = lds32(wan); n1 = lds32(wan + 4);
+            }
+            const bool on = (ent_on >> i) & 1u, odd = (ent_e[i] & 1u) != 0u;
+            const uint32_t r0 = imat::add2<__half>(w0, odd ? (ent_w[i] << 16) : ent_w[i]);
+            const uint32_t r1 = imat::add2<__half>(w1, ent_w[i] >> 16);
+            sts32(wa, r0, on);
+            sts32(wa + 4, r1, on && odd);
+            if (i < 8) {
+                if (on) {
+                    if (wan == wa) { n0 = r0; if (odd) n1 = r1; }
+                    else if (wan == wa + 4) { if (odd) n0 = r1; }
+                    else if (wan + 4 == wa) { n1 = r0; }
+                }
+                wa = wan; w0 = n0; w1 = n1;
+            }
+        }
+    }
+#endif
     if (slowmask) {  // rare: points inside the map but outside the band's window (|offset * scale| >= 3 px)
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
