@@ -1,31 +1,31 @@
-// dcnv3_b200 — round-2 default backward for 16-bit storage, group_channels = 16, 3x3 s1 d1 (ACC_TILE): two lean kernels
-// instead of the four-launch chain zero_select -> bwd_imat -> guarded bwd_vec -> cast (no fp32 workspace, no selector
-// kernel, no cast).  A fused single kernel was built first and measured (profiles/r02_bwd_kernel_history.md): window +
-// interpolation matrix + grad_output need 90 KB of shared memory per CTA, i.e. two CTAs = 16 warps per SM, and the
-// phases (gather/dots -> barrier -> tensor cores -> flush) serialise: 195 us at P3 with the issue slots 46 % busy.
-// Split, each half fits three CTAs per SM and overlaps with the other under programmatic dependent launch:
+// dcnv3_b200 — round-2 default backward for 16-bit storage, group_channels = 16, 3x3 s1 d1 (ACC_TILE): ONE kernel
+// (behind a zero fill of grad_input) instead of the four-launch chain zero_select -> bwd_imat -> guarded bwd_vec -> cast:
+// no fp32 workspace, no selector kernel, no cast.  profiles/r02_bwd_kernel_history.md has every variant that was built
+// and measured on the way (fused with everything resident at two CTAs per SM, split in two kernels, two roles in one
+// launch, persistent with prefetch, phases aliased over one buffer, ...).
 //
-//   win::bwd_dots_kernel     grad_offset / grad_mask.  The forward's structure: a CTA stages the 20x20-cell x 64-channel
-//     window of an (8x8 tile, 4 groups) once (cp.async, zero fill outside the map = the reference's per-corner
-//     validity, dcnv3_im2col_cuda.cuh:57-75), unswizzled, so that the eight lanes of a pixel (4 groups x 2 halves) hit
-//     eight different bank groups whatever cells they sample (conflict-free LDS.128).  The two lanes of a (pixel,
-//     group) split the nine POINTS; the four corner dots d_k = sum_c go[c] * x_k[c] of a point are EXACT mixed-precision
-//     FMAs (PTX fma.rn.f32.bf16 / .f16 -> FHFMA: 16-bit operands straight from the halves of the loaded registers,
-//     fp32 accumulation, no unpack instructions) and give
+// win::bwd_win_kernel.  One CTA per unit = (image, 4-row x 8-column band of output pixels, 4 groups), 256 threads = 32
+// pixels x 4 groups x 2 point halves.  The CTA stages the band's 12x16-cell x 64-channel window once (cp.async, zero fill
+// outside the map = the reference's per-corner validity, dcnv3_im2col_cuda.cuh:57-75), unswizzled, so that the eight lanes
+// of a pixel (4 groups x 2 halves) hit eight different bank groups whatever cells they sample (conflict-free LDS.128); each
+// warp stages the offsets / masks of its own four pixels as whole 16- / 8-byte chunks.  Then, per sampling point, ONE
+// location (locate_lean) feeds
+//   * grad_offset / grad_mask: the four corner dots d_k = sum_c go[c] * x_k[c] as EXACT mixed-precision FMAs (PTX
+//     fma.rn.f32.bf16 / .f16 -> FHFMA: 16-bit operands straight from the halves of the loaded registers, fp32 accumulation)
 //         grad_mask   = sum_k w_k d_k                                                            (cuh:144)
 //         grad_offset = scale * m * (hh (d2 - d1) + lh (d4 - d3), hw (d3 - d1) + lw (d4 - d2))   (cuh:114-139,145-146)
-//   win::bwd_scatter_kernel  grad_input.  A CTA owns a 4-row x 8-column band of output pixels and 4 groups and needs no
-//     window: a lane adds w_k * m as packed fp16 pairs into its pixel's private row of the interpolation matrix
-//     Wm[pixel][12 band rows][16 window columns] (the two lanes of a pixel own the rows of even / odd parity, one
-//     shuffle exchange, no atomics) and the tensor cores expand it:
+//   * grad_input: the lane adds w_k * m as packed fp16 pairs into its pixel's private row of the interpolation matrix
+//     Wm[pixel][9 band rows relative to the pixel's own][16 window columns] (the two lanes of a pixel own the rows of even
+//     / odd parity, one shuffle exchange, no atomics).
+// After one CTA barrier the tensor cores expand the matrix,
 //         GW[cell][ch] = sum_pixel Wm[pixel][cell] * go[pixel][ch]       mma.sync m16n8k16, fp32 accumulators
-//     then the band's 12x16-cell window leaves the SM once as packed 16-bit vector reductions
-//     (red.global.add.noftz.v4.bf16x2 / .f16x2) into the zero-filled grad_input: every partial is an fp32 sum of all
-//     the band's contributions to that cell, and a cell sees at most six of them.
-//   A band whose offsets are large (more than 1 lane in 4 with an offset coordinate of 3 px or more) is skipped by
-//   the dots kernel and runs the vector family's lane body in the scatter kernel (bwd_vec_lane: all three gradients,
-//   packed 16-bit reductions per contribution); a single point that leaves the window takes a per-point slow path
-//   in each kernel (global gathers for the dots, reductions for that point only).
+// and the band's 12x16-cell window leaves the SM once as packed 16-bit vector reductions (red.global.add.noftz.v4.bf16x2 /
+// .f16x2) into the zero-filled grad_input: every partial is an fp32 sum of all the band's contributions to that cell, and a
+// cell sees at most six of them.
+// A band whose offsets are large (more than 1 lane in 4 with an offset coordinate of 3 px or more) runs the vector
+// family's lane body instead (bwd_vec_lane: all three gradients, packed 16-bit reductions per contribution); a single
+// point that leaves the window / the pixel's reach takes a per-point slow path (global gathers for the dots, reductions for
+// that point only).
 //
 // Location arithmetic is the shared locate() sequence (locate_lean: same operations in the same order), so the
 // integer contract is unchanged.  Reference semantics: dcnv3_col2im_gpu_kernel_* :278-839 + dcnv3_col2im_bilinear :82-147.
@@ -45,20 +45,20 @@ using imat::TileCoord;
 constexpr int kThreadsW = 256;
 constexpr int kWinW = 16;                                // window columns the band's interpolation matrix spans: 8 + 2 * 4
 constexpr int kBandRows = 12;                            // window rows a 4-row band of pixels reaches
-constexpr int kRowB = kBandRows * kWinW * 2 + 16;        // 400 B per (pixel, group): +16 B skew (ldmatrix rows on distinct banks)
+constexpr int kRelRows = 9;                              // band rows a pixel can reach: its own band row r .. r + 8 (|offset * scale| < 3 px)
+constexpr int kRowB = kRelRows * kWinW * 2 + 16;         // 304 B per (pixel, group): 9 RELATIVE band rows x 16 window columns x 2 B + 16 B
+                                                         // skew (76 words = 12 mod 32: the 8 rows of an ldmatrix hit distinct banks)
 #ifndef DCNV3_WIN_GRP_SKEW
 #define DCNV3_WIN_GRP_SKEW 16
 #endif
-// +16 B per group so the groups' rows start on different banks.  (A/B on one box, round 2: skews of 16 / 32 / 64 bytes —
-// bank group of a lane = (pixel + {1, 2, 4} x group + position) mod 8 — all gave 172.5 us at P3: the read-modify-write
-// bank conflicts of the interpolation matrix are not what bounds the kernel.)
-constexpr int kGrpB = 32 * kRowB + DCNV3_WIN_GRP_SKEW;   // per group
-constexpr int kWmB = kWarps * kGrpB;                     // 51 264 B: [group][32 pixels]
-constexpr int kGoRowB = 48;                              // grad_output rows of the band: 32 B + 16 B skew
-constexpr int kGoGrpB = 32 * kGoRowB;
-constexpr int kGoB = kWarps * kGoGrpB;                   // 6 144 B
-constexpr int kScatB = kWmB + kGoB;                      // 57 408 B: three CTAs per SM
-constexpr int kDwinB = kBandRows * kWinW * 128;          // dots role: the band's 12x16-cell x 64-channel window, 24 576 B
+// +16 B per group so the groups' rows start on different banks.  (A/B on one box, round 2: skews of 16 / 32 / 64 bytes
+// all gave the same time at P3: the read-modify-write bank conflicts of the interpolation matrix are not what bounds the kernel.)
+constexpr int kGrpB = 32 * kRowB + DCNV3_WIN_GRP_SKEW;   // 9 744 B per group
+constexpr int kWmB = kWarps * kGrpB;                     // 38 976 B: [group][32 pixels][9 relative rows][16 columns]
+constexpr int kGoGrpB = 32 * 32;                         // grad_output (B operand) of a group: 32 pixels x 32 B, 16-byte halves
+constexpr int kGoB = kWarps * kGoGrpB;                   // XOR-swizzled by (pixel >> 2) & 1: 4 096 B
+constexpr int kDwinB = kBandRows * kWinW * 128;          // the band's 12x16-cell x 64-channel window, 24 576 B (later: flush staging)
+constexpr int kFlushWarpB = kDwinB / 8;                  // 3 072 B per warp = 6 band rows x 16 cells x 32 B
 // Staging area for the band's offsets / masks (in) and grad_offset / grad_mask (out): the four groups of a pixel are one
 // contiguous 144-byte (offsets) resp. 72-byte (masks) run in global memory, so they move as whole 16- / 8-byte
 // chunks (cp.async in, vector stores out) instead of one 4- / 2-byte access per lane and point (ncu, round 2: those
@@ -69,18 +69,20 @@ constexpr int kStMaskPx = 80;
 constexpr int kStOffB = 32 * kStOffPx;                   // 5 120 B
 constexpr int kStMaskB = 32 * kStMaskPx;                 // 2 560 B
 constexpr int kStageB = kStOffB + kStMaskB;
-constexpr int kStageOff = kScatB > kDwinB ? kScatB : kDwinB;  // behind either role's buffers
+// shared memory of a CTA: [window | Wm | Gos | staging | one zero row]; nothing aliases, so a warp walks from the dots of
+// its lanes straight into their scatter without waiting for the other warps
+constexpr int kWmOff = kDwinB;
+constexpr int kGosOff = kWmOff + kWmB;
+constexpr int kStageOff = kGosOff + kGoB;
+constexpr int kZeroOff = kStageOff + kStageB;            // 32 zero bytes: ldmatrix rows of pixels that cannot reach a band row
 #ifndef DCNV3_WIN_EXTRA_SMEM
 #define DCNV3_WIN_EXTRA_SMEM 0  // occupancy experiments: pad the CTA's shared memory (profiles/r02_bwd_kernel_history.md)
 #endif
-constexpr int kSmemB = kStageOff + kStageB + DCNV3_WIN_EXTRA_SMEM;  // 65 088 B: still three CTAs per SM
-#ifndef DCNV3_WIN_PREFETCH_UNITS
-#define DCNV3_WIN_PREFETCH_UNITS 320
-#endif
-constexpr unsigned kPrefetchUnits = DCNV3_WIN_PREFETCH_UNITS;  // L2 prefetch distance in units (~2/3 of a wave of 444 CTAs apart... see bwd_win_kernel)
+constexpr int kSmemB = kZeroOff + 32 + DCNV3_WIN_EXTRA_SMEM;  // 75 360 B: three CTAs per SM (limit 76 800 - static)
+static_assert(kSmemB - DCNV3_WIN_EXTRA_SMEM <= 76000, "three CTAs per SM");
 constexpr int kFarLanes = kThreadsW / 4;                 // a band is "far" when more lanes than this see a >= 3 px offset
 static_assert(kWmB % 16 == 0 && kGrpB % 16 == 0 && kRowB % 16 == 0, "ldmatrix rows are 16-byte aligned");
-static_assert(kDwinB % (16 * kThreadsW) == 0 && kDwinB <= kWmB, "the window aliases the start of the interpolation matrix");
+static_assert(kFlushWarpB == 6 * 16 * 32, "flush staging: 6 band rows x 16 cells x 32 B per warp");
 
 using imat::Mix;
 
@@ -260,16 +262,12 @@ __device__ __forceinline__ int slot_i(int k, int h) { return k == 4 ? 2 : (h ? (
 __device__ __forceinline__ int slot_j(int k, int h) { return k == 4 ? 2 : (h ? (4 + k) % 3 : k % 3); }
 
 // ===========================================================================================================
-// One CTA per unit u = (image, 4-row band, 8-column tile, group quad), two phases in sequence:
-//   1. "dots"    grad_offset / grad_mask from the staged 12x16-cell window (24 KB at the start of shared memory);
-//   2. "scatter" grad_input: the interpolation matrix (51 KB) is built OVER the window once every warp has left phase 1,
-//                expanded by the tensor cores and flushed.
-// Round 2 first ran the two phases as two CTAs of one launch (CTA 2u / 2u + 1: 190.5 us at P3).  The occupancy
-// experiment (profiles/r02_bwd_kernel_history.md: T = 117 us + 226 us / CTAs per SM) showed two thirds of that CTA
-// lifetime to be latency — first loads, barriers, dependent chains — that only co-resident work hides.  With the phases
-// in ONE CTA the shared-memory footprint is the same 65 KB (the buffers alias), three CTAs per SM still fit, but each
-// now carries a whole unit: twice the work in flight per SM, one prologue (unit decode, offset / mask / grad_output
-// loads, far-band vote) instead of two.
+// Shared memory of a CTA (75 360 B, three CTAs per SM): [window 24 576 | Wm 38 976 | Gos 4 096 | staging 7 680 | zero row 32].
+// Nothing aliases: the interpolation matrix is zeroed in the shadow of the first loads and a warp goes from a point's dots
+// straight to the same point's matrix updates.  The one CTA barrier after the far-band vote is in front of the tensor
+// cores; behind it the window is dead and becomes the flush staging area (3 KB per warp).
+// The occupancy experiments (profiles/r02_bwd_kernel_history.md) are why a CTA carries a whole unit: the kernel's time is
+// T = 136 us + 109 us / (CTAs per SM) at P3, and only co-resident work hides the per-CTA latency.
 // ===========================================================================================================
 __device__ __forceinline__ void stmatrix_x4(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
     asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
@@ -347,13 +345,14 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         }
         asm volatile("cp.async.commit_group;" ::: "memory");  // group 1: the window (needed behind barrier A)
     }
-    {   // zero the part of the interpolation matrix that lies behind the window (the rest: after phase 1)
+    {   // zero the interpolation matrix and the zero row (in the shadow of the loads above)
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-        for (int i = 0; i < ((kWmB - kDwinB) / 16 + kThreadsW - 1) / kThreadsW; ++i) {
+        for (int i = 0; i < (kWmB / 16 + kThreadsW - 1) / kThreadsW; ++i) {
             const int id = i * kThreadsW + tid;
-            if (id < (kWmB - kDwinB) / 16) sts128(smem_s + kDwinB + id * 16, z);
+            if (id < kWmB / 16) sts128(smem_s + kWmOff + id * 16, z);
         }
+        if (tid < 2) sts128(smem_s + kZeroOff + tid * 16, z);
     }
 
     // lanes: 8 per pixel = 4 groups x 2 point halves; the band's 32 pixels
@@ -423,8 +422,15 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         for (int k = 0; k < 5; ++k) mk[k] = rm[k];
     }
 
+    // Per point, ONE location: the corner dots out of the window (grad_offset / grad_mask) and the point's packed fp16
+    // contributions into the pixel's interpolation-matrix row (grad_input) — the matrix has its own memory, zeroed before
+    // barrier A, and a lane only touches its own rows of it until barrier B, so nothing separates the two.
+    const uint32_t wm_s = smem_s + kWmOff, gos_base = smem_s + kGosOff;
+    const uint32_t row_s = wm_s + gl * kGrpB + px * kRowB;
+    const int rband = px >> 3;  // band row of this lane's pixel: its Wm row holds window rows rband .. rband + 8
+    uint32_t slowmask2 = 0u;    // points whose grad_input contributions leave the pixel's reach
     {
-        // =================================================================== phase 1: grad_offset / grad_mask
+        // =================================================================== grad_offset / grad_mask (+ Wm build)
         const uint32_t own16 = (uint32_t)sub << 4, oth16 = (uint32_t)(sub ^ 1) << 4;
         const T *img_g = in + img_off + gl * 16;
         uint32_t win_s = smem_s;
@@ -466,6 +472,24 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
             const float sm = q.scale * mk[k];
             res_off[k] = fast ? imat::pack2<T>(sm * s_w, sm * s_h) : 0u;
             res_m[k] = fast ? s_m : 0.f;
+            {   // interpolation-matrix pairs (top: band row vb, bottom: vb + 1), stored at the row RELATIVE to the pixel's
+                // band row.  The lane adds the pair whose row has parity h and hands the other one to its partner, so
+                // neither ever writes a row of the other's.  (Point 8 is known to both lanes: each adds the row of its parity.)
+                const unsigned rel = vb - (unsigned)rband;  // 0 .. 7 when in reach
+                const bool fast2 = t.inside && valid && u <= (unsigned)(kWinW - 2) && rel <= (unsigned)(kRelRows - 2);
+                slowmask2 |= (t.inside && valid && !fast2 ? 1u : 0u) << k;  // same for both lanes of the pair
+                const uint32_t e = fast2 ? rel * kWinW + u : 0u;
+                const float hm = hh * mk[k], lm = lh * mk[k];
+                const uint32_t top = imat::pack2<__half>(hm * hw, hm * lw), bot = imat::pack2<__half>(lm * hw, lm * lw);
+                const bool keep_top = ((vb & 1u) == (unsigned)h);
+                wm_add(row_s, keep_top ? e : e + kWinW, keep_top ? top : bot, fast2);
+                if (k < 4) {
+                    const uint32_t se = (keep_top ? e + kWinW : e) | (fast2 ? 256u : 0u);
+                    const uint32_t re = __shfl_xor_sync(0xffffffffu, se, 1);
+                    const uint32_t rw = __shfl_xor_sync(0xffffffffu, keep_top ? bot : top, 1);
+                    wm_add(row_s, re & 255u, rw, (re & 256u) != 0u);
+                }
+            }
         }
         if (slowmask) {  // rare: points inside the map but outside the band's window (|offset * scale| >= 3 px)
 #pragma unroll
@@ -523,15 +547,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         }
     }
 
-    // ======================================================================= phase 2: grad_input
-    __syncthreads();  // barrier C: every warp has left the window
-    {   // zero the part of the interpolation matrix that aliases it
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-        for (int i = 0; i < kDwinB / 16 / kThreadsW; ++i) sts128(smem_s + (i * kThreadsW + tid) * 16, z);
-    }
-    const uint32_t wm_s = smem_s, gos_base = smem_s + kWmB;
-    const uint32_t row_s = wm_s + gl * kGrpB + px * kRowB;
+    // ======================================================================= grad_input: expansion + flush
     T *gin_g = gin + img_off + gl * 16;
     // B operand of the mma (an idle lane stores zeros).  The interpolation matrix is fp16 for both storage dtypes
     // (11-bit weights; bf16 weights, 8 bits, miss the atol 2e-3 bar on ~1e-5 of the elements), so bf16 grad_output enters
@@ -540,7 +556,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     // (absolute error below 2^-24 of the band's largest gradient).
     int e_ref = 127;
     {
-        const uint32_t gos_s = gos_base + gl * kGoGrpB + px * kGoRowB + 16 * h;
+        const uint32_t gos_s = gos_base + gl * kGoGrpB + px * 32 + ((uint32_t)(h ^ ((px >> 2) & 1)) << 4);
         if constexpr (kScaled) {
             const uint4 s0 = *reinterpret_cast<const uint4 *>(smax), s1 = *reinterpret_cast<const uint4 *>(smax + 4);
             const uint32_t mx = max(max(max(s0.x, s0.y), max(s0.z, s0.w)), max(max(s1.x, s1.y), max(s1.z, s1.w)));
@@ -558,87 +574,19 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
             sts128(gos_s, g_own);
         }
     }
-    __syncthreads();  // barrier D: the interpolation matrix is zero
-#ifdef DCNV3_WIN_RMW_PIPE
-    uint32_t ent_e[9], ent_w[9], ent_on = 0u;
-#endif
-    uint32_t slowmask = 0u;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        const float2 o = imat::unpack2f<T>(roff[k]);
-        const LeanPoint t = imat::locate_lean(pg, p0h_, p0w_, (float)slot_i(k, h), (float)slot_j(k, h), o.x, o.y);
-        const unsigned u = (unsigned)(t.w_low - wx0), vb = (unsigned)(t.h_low - by0);
-        const bool inband = u <= (unsigned)(kWinW - 2) && vb <= (unsigned)(kBandRows - 2);
-        const bool fast = t.inside && inband && valid;
-        slowmask |= (t.inside && !inband && valid ? 1u : 0u) << k;  // same for both lanes of the pair
-        const uint32_t e = fast ? vb * kWinW + u : 0u;
-        // interpolation-matrix pairs (top: band row vb, bottom: vb + 1).  The lane adds the pair whose row has parity h
-        // and hands the other one to its partner, so neither ever writes a row of the other's.  (Point 8 is known to
-        // both lanes: each adds the row of its parity.)
-        const float hh = sub_rn(1.f, t.lh), hw = sub_rn(1.f, t.lw);
-        const float hm = hh * mk[k], lm = t.lh * mk[k];
-        const uint32_t top = imat::pack2<__half>(hm * hw, hm * t.lw), bot = imat::pack2<__half>(lm * hw, lm * t.lw);
-        const bool keep_top = ((vb & 1u) == (unsigned)h);
-#ifdef DCNV3_WIN_RMW_PIPE
-        ent_e[2 * k] = keep_top ? e : e + kWinW; ent_w[2 * k] = keep_top ? top : bot; ent_on |= (fast ? 1u : 0u) << (2 * k);
-        if (k < 4) {
-            const uint32_t se = (keep_top ? e + kWinW : e) | (fast ? 256u : 0u);
-            const uint32_t re = __shfl_xor_sync(0xffffffffu, se, 1);
-            ent_w[2 * k + 1] = __shfl_xor_sync(0xffffffffu, keep_top ? bot : top, 1);
-            ent_e[2 * k + 1] = re & 255u; ent_on |= ((re >> 8) & 1u) << (2 * k + 1);
-        }
-#else
-        wm_add(row_s, keep_top ? e : e + kWinW, keep_top ? top : bot, fast);
-        if (k < 4) {
-            const uint32_t se = (keep_top ? e + kWinW : e) | (fast ? 256u : 0u);
-            const uint32_t re = __shfl_xor_sync(0xffffffffu, se, 1);
-            const uint32_t rw = __shfl_xor_sync(0xffffffffu, keep_top ? bot : top, 1);
-            wm_add(row_s, re & 255u, rw, (re & 256u) != 0u);
-        }
-#endif
-    }
-#ifdef DCNV3_WIN_RMW_PIPE
-    {   // the nine read-modify-writes as a software pipeline: entry i + 1's two words are loaded BEFORE entry i's stores
-        // (its shared-memory latency overlaps entry i's adds and stores); if it touches a word entry i has just rewritten,
-        // the new value is forwarded in registers.  Entries further apart are ordered by the hardware (same thread,
-        // same address, program order).
-        uint32_t wa = row_s + ((ent_e[0] >> 1) << 2);
-        uint32_t w0 = lds32(wa), w1 = lds32(wa + 4);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-            uint32_t wan = 0u, n0 = 0u, n1 = 0u;
-            if (i < 8) {
-                wan = row_s + ((ent_e[i + 1] >> 1) << 2);
-                n0 = lds32(wan); n1 = lds32(wan + 4);
-            }
-            const bool on = (ent_on >> i) & 1u, odd = (ent_e[i] & 1u) != 0u;
-            const uint32_t r0 = imat::add2<__half>(w0, odd ? (ent_w[i] << 16) : ent_w[i]);
-            const uint32_t r1 = imat::add2<__half>(w1, ent_w[i] >> 16);
-            sts32(wa, r0, on);
-            sts32(wa + 4, r1, on && odd);
-            if (i < 8) {
-                if (on) {
-                    if (wan == wa) { n0 = r0; if (odd) n1 = r1; }
-                    else if (wan == wa + 4) { if (odd) n0 = r1; }
-                    else if (wan + 4 == wa) { n1 = r0; }
-                }
-                wa = wan; w0 = n0; w1 = n1;
-            }
-        }
-    }
-#endif
-    if (slowmask) {  // rare: points inside the map but outside the band's window (|offset * scale| >= 3 px)
+    if (slowmask2) {  // rare: points inside the map but out of the pixel's reach (|offset * scale| >= 3 px)
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-            if (!((slowmask >> k) & 1u)) continue;
+            if (!((slowmask2 >> k) & 1u)) continue;
             scatter_point_slow<T>(pg, p0h_, p0w_, slot_i(k, h), slot_j(k, h), roff[k], mk[k], g_own,
                                   reinterpret_cast<const T *>(gp + (h ^ 1)), k < 4 ? 2 : 1, gin_g + 8 * h, h ? -8 : 8, q.C);
         }
     }
-    __syncthreads();  // barrier B: Wm and Gos of the band are complete
+    __syncthreads();  // barrier B: Wm and Gos of the band are complete; every warp has left the window
 
     // ---- tensor cores: GW[band row][cell][ch] = Wm^T * go.  Warp = (group, parity of its band rows); m-tile = one band
-    // row (16 cells), K = the band's 32 pixels (two k-steps), N = the group's 16 channels (two n-tiles).
+    // row (16 cells), K = the band's 32 pixels (two k-steps), N = the group's 16 channels (two n-tiles).  A pixel of band
+    // row r stores band row rr at relative row rr - r; out of its reach (rr - r outside 0 .. 8) it reads the zero row.
     const int mg = warp & 3, qpar = warp >> 2;
     const uint32_t wm_g = wm_s + mg * kGrpB;
     float gw[kBandRows / 2][2][4];
@@ -651,17 +599,23 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     {
         const int jm = lane >> 3, jr = lane & 7;
         const uint32_t go_g = gos_base + mg * kGoGrpB;
+        const uint32_t zero_a = smem_s + kZeroOff + (jm & 1) * 16;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-            // B = go [16 px x 16 ch]: matrix jm = (px 8(jm & 1).., ch 8(jm >> 1)..)
+            // B = go [16 px x 16 ch]: matrix jm = (px 8(jm & 1).., ch 8(jm >> 1)..); the 16-byte half is swizzled by (px >> 2) & 1
             uint32_t b00, b01, b10, b11;
-            imat::ldmatrix_x4_trans(b00, b01, b10, b11, go_g + (16 * s + 8 * (jm & 1) + jr) * kGoRowB + (jm >> 1) * 16);
-            // A = Wm^T [16 cells x 16 px]: matrix jm = (cells 8(jm & 1).., px 8(jm >> 1)..)
-            const uint32_t abase = wm_g + (16 * s + 8 * (jm >> 1) + jr) * kRowB + (jm & 1) * 16 + qpar * (kWinW * 2);
+            {
+                const int bpx = 16 * s + 8 * (jm & 1) + jr;
+                imat::ldmatrix_x4_trans(b00, b01, b10, b11, go_g + bpx * 32 + ((uint32_t)((jm >> 1) ^ ((bpx >> 2) & 1)) << 4));
+            }
+            // A = Wm^T [16 cells x 16 px]: matrix jm = (cells 8(jm & 1).., px 8(jm >> 1)..): all 8 pixels of a matrix share a band row
+            const int apx = 16 * s + 8 * (jm >> 1) + jr, ar = 2 * s + (jm >> 1);
+            const uint32_t abase = wm_g + apx * kRowB + (jm & 1) * 16;
 #pragma unroll
             for (int i = 0; i < kBandRows / 2; ++i) {  // band row rr = qpar + 2i
+                const int rel = qpar + 2 * i - ar;
                 uint32_t a0, a1, a2, a3;
-                imat::ldmatrix_x4_trans(a0, a1, a2, a3, abase + i * (2 * kWinW * 2));
+                imat::ldmatrix_x4_trans(a0, a1, a2, a3, (unsigned)rel < (unsigned)kRelRows ? abase + rel * (kWinW * 2) : zero_a);
                 imat::mma_16816<__half>(gw[i][0], a0, a1, a2, a3, b00, b01);
                 imat::mma_16816<__half>(gw[i][1], a0, a1, a2, a3, b10, b11);
             }
@@ -670,13 +624,15 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
 
     // ---- flush: the warp's 6 band rows x 16 cells x 16 channels leave as packed 16-bit vector reductions.  The mma
     // fragments (c0, c1) / (c2, c3) of n-tile nt = channels 8nt + 2tq, +1 of cells gID / gID + 8, packed to the storage
-    // dtype, are exactly stmatrix fragments: one stmatrix.x4 lays a band row out as [16 cells][16 channels] in shared
-    // memory — in the Wm rows of this warp's own parity, which nobody else reads (cell c -> pixel row c, band row slot
-    // qpar + 2i: 400-byte stride, conflict-free) — and every lane reads back the 8 channels of ONE (cell, half).
-    __syncwarp();
+    // dtype, are exactly stmatrix fragments: one stmatrix.x4 lays a band row out as [16 cells][16 channels] — in this
+    // warp's 3 KB of the window, which nobody reads any more (barrier B) — and every lane reads back the 8 channels of
+    // ONE (cell, half).  A cell is 32 B; its halves swap places for cells 4-7 / 12-15 so that the 8 rows of an stmatrix
+    // matrix (and the 8 lanes of an LDS.128 phase) fall into 8 different 16-byte bank groups.
     {
         const int jm = lane >> 3, jr = lane & 7;
-        const uint32_t st_addr = wm_g + (jr + 8 * (jm & 1)) * kRowB + qpar * (kWinW * 2) + (jm >> 1) * 16;
+        const uint32_t fb = smem_s + warp * kFlushWarpB;
+        const int scell = jr + 8 * (jm & 1);
+        const uint32_t st_addr = fb + scell * 32 + ((uint32_t)((jm >> 1) ^ ((scell >> 2) & 1)) << 4);
         const float unscale = __uint_as_float((uint32_t)e_ref << 23);  // 2^(e_ref - 127), bf16 storage only
 #pragma unroll
         for (int i = 0; i < kBandRows / 2; ++i) {
@@ -686,19 +642,19 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
 #pragma unroll
                     for (int c = 0; c < 4; ++c) gw[i][n2][c] *= unscale;
             }
-            stmatrix_x4(st_addr + i * (2 * kWinW * 2), imat::pack2<T>(gw[i][0][0], gw[i][0][1]), imat::pack2<T>(gw[i][0][2], gw[i][0][3]),
+            stmatrix_x4(st_addr + i * 512, imat::pack2<T>(gw[i][0][0], gw[i][0][1]), imat::pack2<T>(gw[i][0][2], gw[i][0][3]),
                         imat::pack2<T>(gw[i][1][0], gw[i][1][1]), imat::pack2<T>(gw[i][1][2], gw[i][1][3]));
         }
         __syncwarp();
         const int cell = lane >> 1, half = lane & 1;
         const int ix = wx0 + cell;
         const bool col_ok = (unsigned)ix < (unsigned)q.W;
-        const uint32_t ld_addr = wm_g + cell * kRowB + qpar * (kWinW * 2) + half * 16;
+        const uint32_t ld_addr = fb + cell * 32 + ((uint32_t)(half ^ ((cell >> 2) & 1)) << 4);
         T *dst0 = gin + img_off + mg * 16 + half * 8 + (size_t)ix * q.C;
 #pragma unroll
         for (int i = 0; i < kBandRows / 2; ++i) {
             const int iy = by0 + qpar + 2 * i;
-            const uint4 o = imat::lds128(ld_addr + i * (2 * kWinW * 2));
+            const uint4 o = imat::lds128(ld_addr + i * 512);
             const bool nz = ((o.x | o.y | o.z | o.w) & 0x7fff7fffu) != 0u;
             const bool ok = col_ok && (unsigned)iy < (unsigned)q.H && nz;
             red_add_v4<T>(ok ? dst0 + (size_t)iy * q.W * q.C : gin, o, ok);
