@@ -319,6 +319,7 @@ bool win_eligible(const Geo &q, const void *in, const void *off, const void *mas
     if (!aligned16(off) || !aligned16(goff) || (reinterpret_cast<uintptr_t>(mask) & 7u) ||
         (reinterpret_cast<uintptr_t>(gmask) & 7u)) return false;
     if ((q.opitch * 2) % 16 || (q.mpitch * 2) % 8) return false;  // packed heads: every pixel's run starts on a chunk boundary
+    if (q.N > 65535 || (q.Ho + 3) / 4 > 65535) return false;      // grid.z / grid.y
     const unsigned long long blocks = (unsigned long long)q.N * ((q.Ho + 3) / 4) * ((q.Wo + 7) / 8) * (q.G / imat::kWarps);
     if (blocks == 0 || blocks >= (1ull << 30)) return false;
     // the far-band fallback indexes (pixel, 8-channel vector) lanes with 32 bits
@@ -331,7 +332,11 @@ template <typename T>
 int launch_bwd_win(const T *in, const T *off, const T *mask, const T *gout, T *gin, T *goff, T *gmask,
                    const Geo &q, bool logits, cudaStream_t st) {
     const int tiles_x = (q.Wo + 7) / 8, bands_y = (q.Ho + 3) / 4, GQ = q.G / imat::kWarps;
-    const unsigned grid = (unsigned)((size_t)q.N * bands_y * tiles_x * GQ);
+#ifdef DCNV3_WIN_GRID1D
+    const dim3 grid((unsigned)((size_t)q.N * bands_y * tiles_x * GQ));
+#else
+    const dim3 grid((unsigned)(tiles_x * GQ), (unsigned)bands_y, (unsigned)q.N);
+#endif
     int rc;
     if (logits) {
         if ((rc = set_smem(win::bwd_win_kernel<T, true>, win::kSmemB, "cudaFuncSetAttribute(bwd_win_kernel)"))) return rc;

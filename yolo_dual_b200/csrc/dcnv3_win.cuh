@@ -296,6 +296,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     pdl_enter();  // (waiting only in front of the first grad_input access instead measured nothing: 190.4 vs 191.0 us at P3)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     TileCoord tc;  // (image, band row, tile column, group quad)
+#ifdef DCNV3_WIN_GRID1D
     {
         unsigned b = blockIdx.x;
         tc.gq = (int)(b % (unsigned)GQ); b /= (unsigned)GQ;
@@ -303,6 +304,12 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         tc.ty = (int)(b % (unsigned)bands_y);
         tc.n = (int)(b / (unsigned)bands_y);
     }
+#else
+    // grid = (tiles_x * GQ, bands_y, N): one division by a run-time extent instead of three; same CTA order as a flat grid
+    tc.tx = (int)(blockIdx.x / (unsigned)GQ); tc.gq = (int)(blockIdx.x - (unsigned)tc.tx * (unsigned)GQ);
+    tc.ty = (int)blockIdx.y; tc.n = (int)blockIdx.z;
+    (void)tiles_x; (void)bands_y;
+#endif
     const int by0 = tc.ty * 4 + (q.half_h - q.ph) - 4;      // input row / column of band-window cell (0, 0)
     const int wx0 = tc.tx * kTile + (q.half_w - q.pw) - 4;
     const size_t img_off = (size_t)tc.n * q.H * q.W * q.C + tc.gq * 64;
