@@ -235,6 +235,34 @@ void launch(void (*kernel)(P...), dim3 grid, unsigned block, size_t smem, cudaSt
     cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
 }
 
+#ifndef DCNV3_NO_TMA
+// the input [N, H, W, C] (16-bit) as a TMA tensor map: dims (C, W, H, N), box (64 channels, box_w columns, box_h rows, 1 image);
+// coordinates outside the map are legal and read as zeros
+int make_window_tmap(const void *in, const Geo &q, unsigned box_w, unsigned box_h, CUtensorMap *tm) {
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn enc = nullptr;  // benign race: idempotent
+    if (!enc) {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) != cudaSuccess || !f) {
+            cudaGetLastError();
+            return fail(DCNV3_B200_EDEVICE, "cuTensorMapEncodeTiled is not available from this driver");
+        }
+        enc = (encode_fn)f;
+    }
+    const cuuint64_t dims[4] = {(cuuint64_t)q.C, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.N};
+    const cuuint64_t strides[3] = {(cuuint64_t)q.C * 2, (cuuint64_t)q.W * q.C * 2, (cuuint64_t)q.H * q.W * q.C * 2};
+    const cuuint32_t box[4] = {64, box_w, box_h, 1}, estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void *>(in), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DCNV3_B200_EINVAL, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+#endif
+
 // ---------------------------------------------- interpolation-matrix family
 // Knobs: DCNV3_B200_FWD / DCNV3_B200_BWD = vec | imat force a family.  Defaults: the backward takes the
 // interpolation-matrix kernel when eligible (16-bit, gc = 16, 3x3 s1 d1, fp32 accumulation), the forward the
@@ -338,13 +366,21 @@ int launch_bwd_win(const T *in, const T *off, const T *mask, const T *gout, T *g
     const dim3 grid((unsigned)(tiles_x * GQ), (unsigned)bands_y, (unsigned)q.N);
 #endif
     int rc;
+#ifdef DCNV3_WIN_TMA
+    alignas(64) CUtensorMap tm;
+    if ((rc = make_window_tmap(in, q, 16, 12, &tm))) return rc;
+#define WIN_EXTRA , tm
+#else
+#define WIN_EXTRA
+#endif
     if (logits) {
         if ((rc = set_smem(win::bwd_win_kernel<T, true>, win::kSmemB, "cudaFuncSetAttribute(bwd_win_kernel)"))) return rc;
-        launch(win::bwd_win_kernel<T, true>, grid, win::kThreadsW, win::kSmemB, st, in, off, mask, gout, gin, goff, gmask, q, GQ, tiles_x, bands_y);
+        launch(win::bwd_win_kernel<T, true>, grid, win::kThreadsW, win::kSmemB, st, in, off, mask, gout, gin, goff, gmask, q, GQ, tiles_x, bands_y WIN_EXTRA);
     } else {
         if ((rc = set_smem(win::bwd_win_kernel<T, false>, win::kSmemB, "cudaFuncSetAttribute(bwd_win_kernel)"))) return rc;
-        launch(win::bwd_win_kernel<T, false>, grid, win::kThreadsW, win::kSmemB, st, in, off, mask, gout, gin, goff, gmask, q, GQ, tiles_x, bands_y);
+        launch(win::bwd_win_kernel<T, false>, grid, win::kThreadsW, win::kSmemB, st, in, off, mask, gout, gin, goff, gmask, q, GQ, tiles_x, bands_y WIN_EXTRA);
     }
+#undef WIN_EXTRA
     return 0;
 }
 
@@ -369,13 +405,21 @@ int forward_t(const void *in_, const void *off_, const void *mask_, void *out_, 
             const int tiles_y = (q.Ho + 7) / 8, tiles_x = (q.Wo + 7) / 8, GQ = q.G / imat::kWarps;
             const dim3 grid((unsigned)(tiles_x * GQ), (unsigned)tiles_y, (unsigned)q.N);
             int rc;
+#ifdef DCNV3_FWD_TMA
+            alignas(64) CUtensorMap tm;
+            if ((rc = make_window_tmap(in, q, imat::kFwin, imat::kFwin, &tm))) return rc;
+#define FWD_EXTRA , tm
+#else
+#define FWD_EXTRA
+#endif
             if (logits) {
                 if ((rc = set_smem(imat::fwd_tile_kernel<T, true>, imat::kFwinBytes, "cudaFuncSetAttribute(fwd_tile_kernel)"))) return rc;
-                launch(imat::fwd_tile_kernel<T, true>, grid, imat::kFwdTileThreads, imat::kFwinBytes, st, in, off, mask, out, q, GQ);
+                launch(imat::fwd_tile_kernel<T, true>, grid, imat::kFwdTileThreads, imat::kFwinBytes, st, in, off, mask, out, q, GQ FWD_EXTRA);
             } else {
                 if ((rc = set_smem(imat::fwd_tile_kernel<T, false>, imat::kFwinBytes, "cudaFuncSetAttribute(fwd_tile_kernel)"))) return rc;
-                launch(imat::fwd_tile_kernel<T, false>, grid, imat::kFwdTileThreads, imat::kFwinBytes, st, in, off, mask, out, q, GQ);
+                launch(imat::fwd_tile_kernel<T, false>, grid, imat::kFwdTileThreads, imat::kFwinBytes, st, in, off, mask, out, q, GQ FWD_EXTRA);
             }
+#undef FWD_EXTRA
             return 0;
         }
         if (packed) return fail(DCNV3_B200_ENOTSUP, "packed heads: this shape / alignment does not take the staged-window forward");

@@ -27,6 +27,15 @@
 
 #include "dcnv3_kernels.cuh"
 
+// The staged windows of the default 16-bit kernels are ONE TMA box load each (cp.async.bulk.tensor.4d over the input as a
+// (C, W, H, N) tensor, out-of-map cells zero-filled by the hardware).  A/B on one box, round 2: backward P3 168.5 ->
+// 162.4 us, step 0.4093 -> 0.3978 ms against the per-thread cp.async fill (-DDCNV3_NO_TMA keeps that path).
+#ifndef DCNV3_NO_TMA
+#define DCNV3_WIN_TMA 1
+#define DCNV3_FWD_TMA 1
+#include <cuda.h>
+#endif
+
 namespace dcnv3 {
 namespace imat {
 
@@ -50,6 +59,25 @@ static_assert(kW16Bytes % 512 == 0, "zero fill: whole 512-byte warp stores");
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
+#ifndef DCNV3_NO_TMA
+// thread-0 side of a TMA box load into shared memory: mbarrier (1 arrival + `bytes` of transaction), then the copy
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, uint32_t bar_s, uint32_t bytes, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_s), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// phase 0 of the mbarrier completes when all bytes have landed (bounded: a descriptor the hardware rejects must not hang the GPU)
+__device__ __forceinline__ void tma_wait(uint32_t bar_s) {
+    uint32_t done = 0u;
+    for (int spin = 0; !done && spin < (1 << 22); ++spin)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar_s) : "memory");
+}
+#endif
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
 }
@@ -1228,8 +1256,15 @@ __device__ __forceinline__ void corner16(float2 (&acc)[8], uint32_t a0, uint32_t
 template <typename T, bool LOGITS>
 __global__ void __launch_bounds__(kFwdTileThreads, DCNV3_FWD_MIN_CTAS)
 fwd_tile_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
-                T *__restrict__ out, const Geo q, const int GQ) {
+                T *__restrict__ out, const Geo q, const int GQ
+#ifdef DCNV3_FWD_TMA
+                , const __grid_constant__ CUtensorMap tmap   // input as a 4-D tensor (C, W, H, N), box (64, 20, 20, 1)
+#endif
+                ) {
     extern __shared__ __align__(128) unsigned char smem[];
+#ifdef DCNV3_FWD_TMA
+    __shared__ __align__(8) unsigned long long win_bar;
+#endif
     pdl_enter();
     const int tid = threadIdx.x;
     // grid = (tiles_x * GQ, tiles_y, N): no divisions by run-time extents except this one
@@ -1239,8 +1274,12 @@ fwd_tile_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
     const int wy0 = tc.ty * kTile + (q.half_h - q.ph) - kFhalo;  // input row of window cell (0, 0)
     const int wx0 = tc.tx * kTile + (q.half_w - q.pw) - kFhalo;
     const T *img = in + (size_t)tc.n * q.H * q.W * q.C + tc.gq * 64;
+#ifdef DCNV3_FWD_TMA
+    if (tid == 0) tma_load_4d(smem_u32(smem), &tmap, smem_u32(&win_bar), kFwinCells * 128, tc.gq * 64, wx0, wy0, tc.n);
+#else
     fill_window_plain<T>(smem, in, img, q, wy0, wx0, tid);
     asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
     if (tid < kFzeroCells * 8) reinterpret_cast<uint4 *>(smem + kFwinCells * 128)[tid] = make_uint4(0u, 0u, 0u, 0u);
 
     const PtGeo pg{q.H, q.W, q.scale};
@@ -1296,7 +1335,11 @@ fwd_tile_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
             const uint32_t a = roff[it][k] & 0x7fff7fffu;
             far |= (a >= (thr << 16) || (a & 0xffffu) >= thr) ? 1u : 0u;
         }
+#ifdef DCNV3_FWD_TMA
+    if (tid == 0) tma_wait(smem_u32(&win_bar));
+#else
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
     const bool cta_far = __syncthreads_count(far != 0u) * 16 > kFwdTileThreads;  // (also the barrier for the window)
     if (cta_far) {
 #pragma unroll 1

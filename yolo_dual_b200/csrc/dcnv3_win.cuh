@@ -289,10 +289,17 @@ template <typename T, bool LOGITS>
 __global__ void __launch_bounds__(kThreadsW, DCNV3_WIN_MIN_CTAS)
 bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
                const T *__restrict__ gout, T *__restrict__ gin, T *__restrict__ goff, T *__restrict__ gmask,
-               const Geo q, const int GQ, const int tiles_x, const int bands_y) {
+               const Geo q, const int GQ, const int tiles_x, const int bands_y
+#ifdef DCNV3_WIN_TMA
+               , const __grid_constant__ CUtensorMap tmap   // input as a 4-D tensor (C, W, H, N), box (64, 16, 12, 1)
+#endif
+               ) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool kScaled = std::is_same<T, __nv_bfloat16>::value;
     __shared__ __align__(16) uint32_t smax[8];
+#ifdef DCNV3_WIN_TMA
+    __shared__ __align__(8) unsigned long long win_bar;
+#endif
     pdl_enter();  // (waiting only in front of the first grad_input access instead measured nothing: 190.4 vs 191.0 us at P3)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     TileCoord tc;  // (image, band row, tile column, group quad)
@@ -336,6 +343,12 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");  // group 0: this warp's offsets / masks
+#ifdef DCNV3_WIN_TMA
+    // The window as ONE TMA box load (cp.async.bulk.tensor.4d): coordinates may lie outside the map, the hardware fills
+    // those cells with zeros (= the reference's per-corner validity); completion is signalled on an mbarrier that
+    // thread 0 waits for in front of barrier A.
+    if (tid == 0) imat::tma_load_4d(smem_s, &tmap, imat::smem_u32(&win_bar), kDwinB, tc.gq * 64, wx0, by0, tc.n);
+#else
     {  // stage the 12x16-cell x 64-channel window, unswizzled; zero outside the map
         const int ch = tid & 7, col = (tid >> 3) & 15, r0 = tid >> 7;
         const int ix = wx0 + col;
@@ -352,6 +365,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         }
         asm volatile("cp.async.commit_group;" ::: "memory");  // group 1: the window (needed behind barrier A)
     }
+#endif
     {   // zero the interpolation matrix and the zero row (in the shadow of the loads above)
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
@@ -376,7 +390,11 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         g_own = __ldg(gp + h);
         g_oth = __ldg(gp + (h ^ 1));
     }
+#ifdef DCNV3_WIN_TMA
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#else
     asm volatile("cp.async.wait_group 1;" ::: "memory");
+#endif
     __syncwarp();  // this warp's offsets / masks are staged (the window may still be in flight)
 
     // ---- this lane's offsets of points 4h..4h+3 and 8, their masks (all nine for the softmax), grad_output
@@ -405,7 +423,11 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         mx = __reduce_max_sync(0xffffffffu, mx);
         if (lane == 0) smax[warp] = mx;
     }
+#ifdef DCNV3_WIN_TMA
+    if (tid == 0) imat::tma_wait(imat::smem_u32(&win_bar));
+#else
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
     // barrier A: the window is staged / Wm is zero and the per-warp maxima are visible.  A far band is skipped by the
     // dots CTA and handled as a whole by the scatter CTA (same count in both: same lanes, same offsets).
     const bool far_band = __syncthreads_count(lane_far<T>(roff, q.scale)) > kFarLanes;
