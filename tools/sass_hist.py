@@ -20,14 +20,17 @@ for line in sass.splitlines():
         key = op if op.startswith(("LDS", "STS", "LDSM", "STSM", "LDG", "STG", "RED", "ATOM", "HMMA", "LDGSTS", "FHFMA", "UTC", "LDTM", "STTM", "UTMA", "BAR", "SHFL")) else op.split(".")[0]
         hist[cur][key] += 1
 print("# SASS opcode histograms of the hot kernels (static instruction counts, `cuobjdump -sass` of the built library)\n")
-print("Blackwell-only mnemonics to look for: `UTCHMMA/UTCQMMA` (tcgen05.mma), `LDTM/STTM` (TMEM), `UTMALDG/UTMASTG` (TMA): none —")
-print("the kernels stage with `LDGSTS` (cp.async), gather with `LDS.128`, multiply with `FHFMA` (mixed-precision FMA, sm_100) /")
-print("`HMMA.16816` (mma.sync) and reduce with `REDG.E.ADD.BF16x8 / F16x8` vectors.\n")
+print("Blackwell / Hopper-class mnemonics: the windows of `bwd_win_kernel` and `fwd_tile_kernel` are TMA box loads (`UTMALDG.4D`, completion")
+print("on an mbarrier: `SYNCS.EXCH` / `SYNCS.ARRIVE.TRANS64`); offsets / masks are staged with `LDGSTS` (cp.async); gathers are `LDS.128`, the")
+print("multiplies `FHFMA` (mixed-precision FMA, sm_100) / `HMMA.16816` (mma.sync), the reductions `REDG.E.ADD.BF16x8 / F16x8` vectors.  No")
+print("`UTCHMMA` / `LDTM` (tcgen05 / TMEM): DESIGN.md par. 4.0 and 7-0 say where they would pay.\n")
 for fn, h in hist.items():
     if not any(w in fn for w in want):
         continue
     n = sum(h.values())
     print(f"## `{fn}` — {n} instructions\n")
+    notable = {k: v for k, v in h.items() if k.startswith(("UTMA", "SYNCS", "HMMA", "FHFMA", "RED", "LDGSTS", "LDSM", "STSM", "UTC", "LDTM", "UBLKCP"))}
+    print("notable: " + ", ".join(f"`{k}` x{v}" for k, v in sorted(notable.items())) + "\n")
     print("| opcode | count | % |\n|---|---|---|")
     for op, c in h.most_common(32):
         print(f"| `{op}` | {c} | {100 * c / n:.1f} |")
