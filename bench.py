@@ -143,6 +143,9 @@ class SiteBuffers:
         self.name = name
         self.input = rn(N, H, W, C).to(dtype)
         self.offset = rn(N, H, W, G * P * 2).to(dtype)          # sigma = 1 px
+        clip = float(os.environ.get("BENCH_OFFSET_CLIP", "0"))  # experiments only (profiles/r02_slow_path.md): |offset| <= clip px
+        if clip > 0:
+            self.offset = self.offset.clamp(-clip, clip)
         logits = rn(N, H, W, G, P)
         self.mask = (logits if fused_softmax else torch.softmax(logits, -1)).reshape(N, H, W, G * P).to(dtype).contiguous()
         self.grad_out = rn(N, H, W, C).to(dtype)

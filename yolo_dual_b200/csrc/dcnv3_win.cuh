@@ -182,6 +182,9 @@ __device__ __forceinline__ float dot_chunk(const uint4 &x, const uint4 &g) {
     return s0 + s1;
 }
 
+#ifndef DCNV3_WIN_COOP_SLOW
+#define DCNV3_WIN_COOP_SLOW 1  // 0: every lane runs its own rare points (dots_point_slow / scatter_point_slow), round 2's first version
+#endif
 // ---- slow paths (rare: |offset * scale| >= 3 px resp. 5 px; non-inlined) ---------------------------------------
 // Corner dots of a point outside the staged window: global gathers with the reference's per-corner validity.  `img_c`
 // points at the first channel of chunk a of the group's slab, chunk b is `delta_b` elements away.
@@ -520,6 +523,83 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                 }
             }
         }
+#if DCNV3_WIN_COOP_SLOW
+        // Rare points (|offset * scale| >= 3 px: inside the map but outside the band's window -> dots, or out of the
+        // pixel's reach -> grad_input) are handled by the WARP, four at a time: a lane that runs one alone costs the
+        // warp ~400 issue slots per point (measured: 16 us of 164 at P3 with offsets ~ N(0, 1) px,
+        // profiles/r02_slow_path.md).  Eight lanes per point = 4 corners x 2 channel chunks: one 16-byte gather, 8 FMAs
+        // and one packed vector reduction each; the point's owner gets its dots back by shuffle.
+        {
+            uint32_t need = slowmask | (slowmask2 << 8);          // bits 0-4: dots, bits 8-12: grad_input
+            if (h) need &= ~((1u << 4) | (1u << 12));             // point 8 is known to both lanes: the even one reports it
+            const int grp = lane >> 3, crn = (lane >> 1) & 3, hf = lane & 1;
+            while (true) {
+                const uint32_t bal = __ballot_sync(0xffffffffu, need != 0u);
+                if (bal == 0u) break;
+                int src = -1;                                     // lane that owns this group's point
+                {
+                    uint32_t bb = bal;
+#pragma unroll
+                    for (int gi = 0; gi < 4; ++gi) {
+                        if (gi == grp) src = __ffs(bb) - 1;
+                        bb &= bb - 1u;
+                    }
+                }
+                const bool act = src >= 0;
+                const int srcl = act ? src : 0;
+                // owner side: its lowest pending slot
+                const int ks = __ffs((need | (need >> 8)) & 31u) - 1;   // -1: nothing pending
+                uint32_t s_off = 0u, s_fl = 0u;
+                float s_mk = 0.f;
+#pragma unroll
+                for (int k = 0; k < 5; ++k)
+                    if (k == ks) {
+                        s_off = roff[k]; s_mk = mk[k];
+                        s_fl = (uint32_t)k | (((need >> k) & 1u) << 3) | (((need >> (8 + k)) & 1u) << 4);
+                    }
+                const uint32_t offw = __shfl_sync(0xffffffffu, s_off, srcl);
+                const float pm = __shfl_sync(0xffffffffu, s_mk, srcl);
+                const uint32_t fl = __shfl_sync(0xffffffffu, s_fl, srcl);
+                const float sp0h = __shfl_sync(0xffffffffu, p0h_, srcl), sp0w = __shfl_sync(0xffffffffu, p0w_, srcl);
+                const int spx = warp * 4 + (srcl >> 3), sgl = (srcl >> 1) & 3, sh = srcl & 1;   // the owner's pixel / group / half
+                const int sk = (int)(fl & 7u);
+                const bool want_d = act && ((fl >> 3) & 1u), want_s = act && ((fl >> 4) & 1u);
+                const int pnt = sk == 4 ? 8 : 4 * sh + sk, pi = pnt / 3, pj = pnt - 3 * pi;
+                const Geo gq_ = imat::geo_of(pg);
+                const float2 o = imat::unpack2f<T>(offw);
+                Point<float> t;
+                locate<float>(gq_, sp0h, sp0w, pi, pj, o.x, o.y, t);
+                const bool okc = crn == 0 ? t.ok1 : crn == 1 ? t.ok2 : crn == 2 ? t.ok3 : t.ok4;
+                const float wc = (crn & 2 ? t.lh : t.hh) * (crn & 1 ? t.lw : t.hw);
+                const size_t spix = ((size_t)tc.n * q.Ho + (tc.ty * 4 + (spx >> 3))) * q.Wo + (tc.tx * kTile + (spx & 7));
+                const size_t ce = img_off + (okc ? ((size_t)(t.h_low + (crn >> 1)) * q.W + (t.w_low + (crn & 1))) * q.C : 0)
+                                  + sgl * 16 + hf * 8;
+                uint4 gch = make_uint4(0u, 0u, 0u, 0u);
+                if (act) gch = __ldg(reinterpret_cast<const uint4 *>(gout + spix * q.C + (tc.gq * kWarps + sgl) * 16 + hf * 8));
+                float d = 0.f;
+                if (want_d && okc) d = dot_chunk<T>(__ldg(reinterpret_cast<const uint4 *>(in + ce)), gch);
+                d += __shfl_xor_sync(0xffffffffu, d, 1);
+                const float d0 = __shfl_sync(0xffffffffu, d, grp * 8), d1 = __shfl_sync(0xffffffffu, d, grp * 8 + 2);
+                const float d2 = __shfl_sync(0xffffffffu, d, grp * 8 + 4), d3 = __shfl_sync(0xffffffffu, d, grp * 8 + 6);
+                const float c_m = (t.hh * t.hw) * d0 + (t.hh * t.lw) * d1 + (t.lh * t.hw) * d2 + (t.lh * t.lw) * d3;
+                const float c_w = t.hh * (d1 - d0) + t.lh * (d3 - d2);
+                const float c_h = t.hw * (d2 - d0) + t.lw * (d3 - d1);
+                const float sm = q.scale * pm;
+                const uint32_t c_off = imat::pack2<T>(sm * c_w, sm * c_h);
+                red_add_v4<T>(want_s && okc ? gin + ce : gin, scale_chunk<T>(gch, wc * pm), want_s && okc);
+                // back to the owners: the r-th pending lane was served by group r
+                const int rnk = __popc(bal & ((1u << lane) - 1u));
+                const uint32_t got_off = __shfl_sync(0xffffffffu, c_off, (rnk & 3) * 8);
+                const float got_m = __shfl_sync(0xffffffffu, c_m, (rnk & 3) * 8);
+                if (need != 0u && rnk < 4) {
+#pragma unroll
+                    for (int k = 0; k < 5; ++k)
+                        if (k == ks && ((need >> k) & 1u)) { res_off[k] = got_off; res_m[k] = got_m; }
+                    need &= ~((1u | (1u << 8)) << ks);
+                }
+            }
+        }
+#else
         if (slowmask) {  // rare: points inside the map but outside the band's window (|offset * scale| >= 3 px)
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
@@ -538,6 +618,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                 res_m[k] = s_m;
             }
         }
+#endif
         // grad_offset / grad_mask (cuh:144-146); fused softmax: dl_p = m_p (gm_p - sum_q m_q gm_q)
         if (LOGITS) {
             float dot = 0.f;
@@ -603,6 +684,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
             sts128(gos_s, g_own);
         }
     }
+#if !DCNV3_WIN_COOP_SLOW
     if (slowmask2) {  // rare: points inside the map but out of the pixel's reach (|offset * scale| >= 3 px)
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
@@ -611,6 +693,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                                   reinterpret_cast<const T *>(gp + (h ^ 1)), k < 4 ? 2 : 1, gin_g + 8 * h, h ? -8 : 8, q.C);
         }
     }
+#endif
     __syncthreads();  // barrier B: Wm and Gos of the band are complete; every warp has left the window
 
     // ---- tensor cores: GW[band row][cell][ch] = Wm^T * go.  Warp = (group, parity of its band rows); m-tile = one band
