@@ -7,7 +7,7 @@ rep, kname, which = sys.argv[1], sys.argv[2], int(sys.argv[3])
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 sort = sys.argv[5] if len(sys.argv) > 5 else "samples"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-lib = os.path.join(ROOT, "yolo_dual_b200", "csrc", "libdcnv3_b200.so")
+lib = os.environ.get("NCU_LINES_LIB") or os.path.join(ROOT, "yolo_dual_b200", "csrc", "libdcnv3_b200.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]

@@ -182,6 +182,9 @@ __device__ __forceinline__ float dot_chunk(const uint4 &x, const uint4 &g) {
     return s0 + s1;
 }
 
+#ifndef DCNV3_WIN_STBULK
+#define DCNV3_WIN_STBULK 0  // 1: one thread zeroes the interpolation matrix with st.bulk (UMEMSETS.64); measured +2 us at P3, profiles/r02_bwd_kernel_history.md #14
+#endif
 #ifndef DCNV3_WIN_COOP_SLOW
 #define DCNV3_WIN_COOP_SLOW 1  // 0: every lane runs its own rare points (dots_point_slow / scatter_point_slow), round 2's first version
 #endif
@@ -369,6 +372,12 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         asm volatile("cp.async.commit_group;" ::: "memory");  // group 1: the window (needed behind barrier A)
     }
 #endif
+#if DCNV3_WIN_STBULK
+    // zero the interpolation matrix with ONE instruction of one thread (st.bulk -> UMEMSETS.64, sm_100); barrier A publishes
+    // it.  Measured slower than the 10 x 16-byte stores per thread it replaces (154.0 vs 152.0 us at P3): kept for A/B only.
+    if (tid == 32) asm volatile("st.bulk.weak.shared::cta [%0], %1, 0;" ::"r"(smem_s + kWmOff), "l"((unsigned long long)kWmB) : "memory");
+    if (tid < 2) sts128(smem_s + kZeroOff + tid * 16, make_uint4(0u, 0u, 0u, 0u));
+#else
     {   // zero the interpolation matrix and the zero row (in the shadow of the loads above)
         const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
@@ -379,6 +388,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         if (tid < 2) sts128(smem_s + kZeroOff + tid * 16, z);
     }
 
+#endif
     // lanes: 8 per pixel = 4 groups x 2 point halves; the band's 32 pixels
     const int px = tid >> 3, sub = tid & 7, gl = sub >> 1, h = sub & 1;
     const int g = tc.gq * kWarps + gl;
