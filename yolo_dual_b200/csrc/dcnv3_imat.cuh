@@ -1250,6 +1250,9 @@ __device__ __forceinline__ void corner16(float2 (&acc)[8], uint32_t a0, uint32_t
 // chunk 2g + 1 - h second, so in either LDS.128 the eight lanes of a quarter-warp still touch eight different
 // bank groups; one shuffle exchange per pixel merges the halves.  4.5 locates per lane instead of 9.
 // (The same split over L1 — fwd_pts_kernel — lost: there a 32-byte request costs L1 two passes.)
+#ifndef DCNV3_FWD_ROLL_IT
+#define DCNV3_FWD_ROLL_IT 0  // 1: roll the loop over the lane's two pixels (5 432 -> 3 392 SASS instructions); measured slower, 55.7 vs 53.7 us at P3
+#endif
 #ifndef DCNV3_FWD_MIN_CTAS
 #define DCNV3_FWD_MIN_CTAS 3  // A/B on one box (round 2): 4 CTAs per SM at 64 registers — see profiles/r02_fwd_occupancy.md
 #endif
@@ -1353,22 +1356,37 @@ fwd_tile_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
         return;
     }
 
+    // The loop over the lane's two pixels can be rolled (-DDCNV3_FWD_ROLL_IT=1: the pixel's registers are picked with
+    // selects, the kernel shrinks from 84 to 53 KB of SASS); the instruction-fetch stalls it removes (ncu no_instruction 4 %)
+    // are worth less than the overlap between the two pixels' points it loses: 55.7 vs 53.7 us at P3.
+#if DCNV3_FWD_ROLL_IT
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int it = 0; it < 2; ++it) {
+        uint32_t roff_c[5];
+        float rm_c[9];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) roff_c[k] = it ? roff[1][k] : roff[0][k];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) rm_c[k] = it ? rm[1][k] : rm[0][k];
+        const int oy_c = it ? oy[1] : oy[0], ox_c = it ? ox[1] : ox[0];
+        const bool valid_c = it ? valid[1] : valid[0];
         // (a pair shares its pixel, so both lanes take the same branch and the shuffle below is safe)
-        if (__ballot_sync(0xffffffffu, valid[it]) == 0u) continue;
+        if (__ballot_sync(0xffffffffu, valid_c) == 0u) continue;
         float p0h_, p0w_;
-        window_origin<float>(q, oy[it], ox[it], p0h_, p0w_);
+        window_origin<float>(q, oy_c, ox_c, p0h_, p0w_);
         float mk[5];  // masks of points 4h..4h+3 and 8
         if (LOGITS) {
-            softmax9<T, LOGITS>(rm[it]);
+            softmax9<T, LOGITS>(rm_c);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) mk[k] = h ? rm[it][4 + k] : rm[it][k];
+            for (int k = 0; k < 4; ++k) mk[k] = h ? rm_c[4 + k] : rm_c[k];
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) mk[k] = rm[it][k];
+            for (int k = 0; k < 4; ++k) mk[k] = rm_c[k];
         }
-        mk[4] = rm[it][8];
+        mk[4] = rm_c[8];
         float2 acc[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = make_float2(0.f, 0.f);
@@ -1382,11 +1400,11 @@ fwd_tile_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
                     acc[c].y += __shfl_xor_sync(0xffffffffu, acc[4 + c].y, 1);
                 }
             }
-            const float2 o = unpack2f<T>(roff[it][k]);
+            const float2 o = unpack2f<T>(roff_c[k]);
             const LeanPoint t = locate_lean(pg, p0h_, p0w_, k == 4 ? 2.f : fi[k], k == 4 ? 2.f : fj[k], o.x, o.y);
             const unsigned u = (unsigned)(t.w_low - wx0), v = (unsigned)(t.h_low - wy0);
             const bool inwin = u <= (unsigned)(kFwin - 2) && v <= (unsigned)(kFwin - 2);
-            const bool fast = t.inside && inwin && valid[it];
+            const bool fast = t.inside && inwin && valid_c;
             const float m = fast ? mk[k] : 0.f;
             const uint32_t a = win_s + (fast ? v * kFwin + u : (unsigned)kFwinCells) * 128u;  // closed point: the zero cells (0 * Inf would be NaN)
             const float hh = sub_rn(1.f, t.lh), hw = sub_rn(1.f, t.lw);
@@ -1405,7 +1423,7 @@ fwd_tile_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
                 fma8<T>(lo, lds128(a + own16 + kFwin * 128), w3);
                 fma8<T>(lo, lds128(a + own16 + kFwin * 128 + 128), w4);
             }
-            if (t.inside && !inwin && valid[it]) {
+            if (t.inside && !inwin && valid_c) {
                 // rare: the point left the staged window; gather from global memory with the reference's
                 // validity (whole points before the merge: both chunks; point 8: the own chunk).  Inline on
                 // purpose: as a non-inlined function the accumulators live in local memory (72 -> 97 us).
@@ -1427,8 +1445,8 @@ fwd_tile_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
                 }
             }
         }
-        if (valid[it]) {
-            const size_t pix = ((size_t)tc.n * q.Ho + oy[it]) * q.Wo + ox[it];
+        if (valid_c) {
+            const size_t pix = ((size_t)tc.n * q.Ho + oy_c) * q.Wo + ox_c;
             uint4 r;
             r.x = pack2<T>(acc[0].x, acc[0].y); r.y = pack2<T>(acc[1].x, acc[1].y);
             r.z = pack2<T>(acc[2].x, acc[2].y); r.w = pack2<T>(acc[3].x, acc[3].y);
