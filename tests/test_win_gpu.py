@@ -34,6 +34,11 @@ CASES = {
     "P5_like_G32": ((1, 20, 20, 32, 16), dict()),
     "pad2": ((1, 10, 14, 4, 16), dict(pad=2)),
     "one_band": ((3, 4, 33, 4, 16), dict()),
+    # maps whose width leaves 1-4 columns beyond the last whole tile column: the strip of transposed 8x4 tiles
+    # (partial_tiles_G8, P5_like_G32, pad0 and one_band above take it too)
+    "strip_w12_h9": ((1, 9, 12, 4, 16), dict()),
+    "strip_w28_h37_G8": ((2, 37, 28, 8, 16), dict()),
+    "strip_w9_scale1.5": ((1, 16, 9, 4, 16), dict(scale=1.5)),
 }
 
 

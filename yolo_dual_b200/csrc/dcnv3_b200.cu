@@ -359,27 +359,46 @@ bool win_eligible(const Geo &q, const void *in, const void *off, const void *mas
 template <typename T>
 int launch_bwd_win(const T *in, const T *off, const T *mask, const T *gout, T *gin, T *goff, T *gmask,
                    const Geo &q, bool logits, cudaStream_t st) {
-    const int tiles_x = (q.Wo + 7) / 8, bands_y = (q.Ho + 3) / 4, GQ = q.G / imat::kWarps;
+    int tiles_x = (q.Wo + 7) / 8;
+    const int bands_y = (q.Ho + 3) / 4, GQ = q.G / imat::kWarps;
+    // 1-4 columns beyond the last whole tile column: a strip of transposed tiles (8 rows x 4 columns) instead of a third,
+    // half-empty tile column (dcnv3_win.cuh, STRIP).  They take the grid rows behind the bands.
+    int strip_tiles = 0, strip_rows = 0;
+#if defined(DCNV3_WIN_TMA) && !defined(DCNV3_WIN_GRID1D) && !defined(DCNV3_WIN_NO_STRIP)
+    if (q.Wo >= 8 && q.Wo % 8 >= 1 && q.Wo % 8 <= 4) {
+        const int tx_n = q.Wo / 8, nt = (q.Ho + 7) / 8, rows = (nt + tx_n - 1) / tx_n;
+        if (bands_y + rows <= 65535) { tiles_x = tx_n; strip_tiles = nt; strip_rows = rows; }
+    }
+#endif
 #ifdef DCNV3_WIN_GRID1D
     const dim3 grid((unsigned)((size_t)q.N * bands_y * tiles_x * GQ));
 #else
-    const dim3 grid((unsigned)(tiles_x * GQ), (unsigned)bands_y, (unsigned)q.N);
+    const dim3 grid((unsigned)(tiles_x * GQ), (unsigned)(bands_y + strip_rows), (unsigned)q.N);
 #endif
     int rc;
 #ifdef DCNV3_WIN_TMA
-    alignas(64) CUtensorMap tm;
+    alignas(64) CUtensorMap tm, tms;
     if ((rc = make_window_tmap(in, q, 16, 12, &tm))) return rc;
-#define WIN_EXTRA , tm
+    if (strip_tiles) { if ((rc = make_window_tmap(in, q, 12, 16, &tms))) return rc; }
+    else tms = tm;
+#define WIN_EXTRA , tm, tms
 #else
 #define WIN_EXTRA
 #endif
-    if (logits) {
-        if ((rc = set_smem(win::bwd_win_kernel<T, true>, win::kSmemB, "cudaFuncSetAttribute(bwd_win_kernel)"))) return rc;
-        launch(win::bwd_win_kernel<T, true>, grid, win::kThreadsW, win::kSmemB, st, in, off, mask, gout, gin, goff, gmask, q, GQ, tiles_x, bands_y WIN_EXTRA);
-    } else {
-        if ((rc = set_smem(win::bwd_win_kernel<T, false>, win::kSmemB, "cudaFuncSetAttribute(bwd_win_kernel)"))) return rc;
-        launch(win::bwd_win_kernel<T, false>, grid, win::kThreadsW, win::kSmemB, st, in, off, mask, gout, gin, goff, gmask, q, GQ, tiles_x, bands_y WIN_EXTRA);
+#define WIN_LAUNCH(LG, SP)                                                                                              \
+    do {                                                                                                                \
+        if ((rc = set_smem(win::bwd_win_kernel<T, LG, SP>, win::kSmemB, "cudaFuncSetAttribute(bwd_win_kernel)"))) return rc; \
+        launch(win::bwd_win_kernel<T, LG, SP>, grid, win::kThreadsW, win::kSmemB, st, in, off, mask, gout, gin, goff, gmask, q, \
+               GQ, tiles_x, bands_y WIN_EXTRA, strip_tiles);                                                            \
+    } while (0)
+#ifdef DCNV3_WIN_TMA
+    if (strip_tiles) {
+        if (logits) WIN_LAUNCH(true, true); else WIN_LAUNCH(false, true);
+        return 0;
     }
+#endif
+    if (logits) WIN_LAUNCH(true, false); else WIN_LAUNCH(false, false);
+#undef WIN_LAUNCH
 #undef WIN_EXTRA
     return 0;
 }

@@ -291,15 +291,21 @@ __global__ void __launch_bounds__(256) zero_fill_kernel(uint4 *__restrict__ p, c
 #ifndef DCNV3_WIN_MIN_CTAS
 #define DCNV3_WIN_MIN_CTAS 3
 #endif
-template <typename T, bool LOGITS>
+// STRIP (maps whose width leaves 1-4 columns beyond the last whole 8-column tile, e.g. 20 x 20): those columns are not
+// a third, half-empty tile column but a strip of TRANSPOSED tiles, 8 rows x 4 columns each (grid rows bands_y and up).
+// A strip tile's window is 16 rows x 12 columns (the same 192 cells, row pitch 12); in the interpolation matrix, the
+// tensor-core expansion and the flush the roles of x and y are swapped (A = the 16-cell axis, B = the 12-cell axis), so
+// everything behind the window gathers is the same code.  20 x 20: 13 CTAs per (image, group quad) instead of 15.
+template <typename T, bool LOGITS, bool STRIP>
 __global__ void __launch_bounds__(kThreadsW, DCNV3_WIN_MIN_CTAS)
 bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
                const T *__restrict__ gout, T *__restrict__ gin, T *__restrict__ goff, T *__restrict__ gmask,
                const Geo q, const int GQ, const int tiles_x, const int bands_y
 #ifdef DCNV3_WIN_TMA
                , const __grid_constant__ CUtensorMap tmap   // input as a 4-D tensor (C, W, H, N), box (64, 16, 12, 1)
+               , const __grid_constant__ CUtensorMap tmap_s // the same tensor, box (64, 12, 16, 1): strip tiles
 #endif
-               ) {
+               , const int strip_tiles) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr bool kScaled = std::is_same<T, __nv_bfloat16>::value;
     __shared__ __align__(16) uint32_t smax[8];
@@ -321,10 +327,20 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     // grid = (tiles_x * GQ, bands_y, N): one division by a run-time extent instead of three; same CTA order as a flat grid
     tc.tx = (int)(blockIdx.x / (unsigned)GQ); tc.gq = (int)(blockIdx.x - (unsigned)tc.tx * (unsigned)GQ);
     tc.ty = (int)blockIdx.y; tc.n = (int)blockIdx.z;
-    (void)tiles_x; (void)bands_y;
 #endif
-    const int by0 = tc.ty * 4 + (q.half_h - q.ph) - 4;      // input row / column of band-window cell (0, 0)
-    const int wx0 = tc.tx * kTile + (q.half_w - q.pw) - 4;
+    int py0 = tc.ty * 4, px0 = tc.tx * kTile;               // output row / column of the tile's pixel 0
+    bool tm = false;                                         // CTA-uniform: a strip tile (8 rows x 4 columns, A = y, B = x)
+    if (STRIP && tc.ty >= bands_y) {
+        const int t = (tc.ty - bands_y) * tiles_x + tc.tx;
+        if (t >= strip_tiles) return;
+        tm = true; py0 = t * 8; px0 = tiles_x * kTile;
+    }
+    (void)tiles_x; (void)bands_y; (void)strip_tiles;
+    const int by0 = py0 + (q.half_h - q.ph) - 4;            // input row / column of window cell (0, 0)
+    const int wx0 = px0 + (q.half_w - q.pw) - 4;
+    // pixel p of the tile: (row, column) = (p >> 3, p & 7), transposed in a strip tile
+    auto pix_y = [&](int p) { return py0 + (tm ? (p & 7) : (p >> 3)); };
+    auto pix_x = [&](int p) { return px0 + (tm ? (p >> 3) : (p & 7)); };
     const size_t img_off = (size_t)tc.n * q.H * q.W * q.C + tc.gq * 64;
     const PtGeo pg{q.H, q.W, q.scale};
     const uint32_t smem_s = imat::smem_u32(smem);
@@ -339,7 +355,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         const int t = it * 32 + lane;           // chunk 0..35 of the warp
         if (t < 36) {
             const int ppx = warp * 4 + t / 9, chk = t % 9;
-            const int poy = tc.ty * 4 + (ppx >> 3), pox = tc.tx * kTile + (ppx & 7);
+            const int poy = pix_y(ppx), pox = pix_x(ppx);
             const bool ok = poy < q.Ho && pox < q.Wo;
             const size_t pp = ((size_t)tc.n * q.Ho + min(poy, q.Ho - 1)) * q.Wo + min(pox, q.Wo - 1);
             imat::cp_async16(stage_s + ppx * kStOffPx + chk * 16,
@@ -353,8 +369,9 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     // The window as ONE TMA box load (cp.async.bulk.tensor.4d): coordinates may lie outside the map, the hardware fills
     // those cells with zeros (= the reference's per-corner validity); completion is signalled on an mbarrier that
     // thread 0 waits for in front of barrier A.
-    if (tid == 0) imat::tma_load_4d(smem_s, &tmap, imat::smem_u32(&win_bar), kDwinB, tc.gq * 64, wx0, by0, tc.n);
+    if (tid == 0) imat::tma_load_4d(smem_s, STRIP && tm ? &tmap_s : &tmap, imat::smem_u32(&win_bar), kDwinB, tc.gq * 64, wx0, by0, tc.n);
 #else
+    static_assert(!STRIP, "strip tiles are loaded by TMA");
     {  // stage the 12x16-cell x 64-channel window, unswizzled; zero outside the map
         const int ch = tid & 7, col = (tid >> 3) & 15, r0 = tid >> 7;
         const int ix = wx0 + col;
@@ -392,7 +409,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     // lanes: 8 per pixel = 4 groups x 2 point halves; the band's 32 pixels
     const int px = tid >> 3, sub = tid & 7, gl = sub >> 1, h = sub & 1;
     const int g = tc.gq * kWarps + gl;
-    const int oy = tc.ty * 4 + (px >> 3), ox = tc.tx * kTile + (px & 7);
+    const int oy = pix_y(px), ox = pix_x(px);
     const bool valid = oy < q.Ho && ox < q.Wo;
     const int cy = min(oy, q.Ho - 1), cx = min(ox, q.Wo - 1);  // clamped: addresses of an idle lane stay legal
     const size_t pix = ((size_t)tc.n * q.Ho + cy) * q.Wo + cx;
@@ -477,6 +494,8 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         const T *img_g = in + img_off + gl * 16;
         uint32_t win_s = smem_s;
         asm volatile("" : "+r"(win_s));  // the window gathers below depend on this: they stay behind barrier A
+        const uint32_t pitch = STRIP && tm ? 12u : (uint32_t)kWinW;  // cells per window row
+        const uint32_t rowb = pitch * 128u;
         uint32_t res_off[5];
         float res_m[5];
         uint32_t slowmask = 0u;
@@ -485,22 +504,23 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         for (int k = 0; k < 5; ++k) {
             const float2 o = imat::unpack2f<T>(roff[k]);
             const LeanPoint t = imat::locate_lean(pg, p0h_, p0w_, (float)slot_i(k, h), (float)slot_j(k, h), o.x, o.y);
-            const unsigned u = (unsigned)(t.w_low - wx0), vb = (unsigned)(t.h_low - by0);
+            const unsigned wxu = (unsigned)(t.w_low - wx0), wyu = (unsigned)(t.h_low - by0);
+            const unsigned u = STRIP && tm ? wyu : wxu, vb = STRIP && tm ? wxu : wyu;  // index along A (16 cells) / B (12 cells)
             const bool inband = u <= (unsigned)(kWinW - 2) && vb <= (unsigned)(kBandRows - 2);
             const bool fast = t.inside && inband && valid;
             slowmask |= (t.inside && !inband && valid ? 1u : 0u) << k;  // same for both lanes of the pair
-            const uint32_t a = win_s + (fast ? vb * kWinW + u : 0u) * 128u;
+            const uint32_t a = win_s + (fast ? wyu * pitch + wxu : 0u) * 128u;
             float d0, d1, d2, d3;
             if (k < 4) {
                 d0 = corner_dot16<T>(a + own16, a + oth16, g_own, g_oth);
                 d1 = corner_dot16<T>(a + own16 + 128, a + oth16 + 128, g_own, g_oth);
-                d2 = corner_dot16<T>(a + own16 + kWinW * 128, a + oth16 + kWinW * 128, g_own, g_oth);
-                d3 = corner_dot16<T>(a + own16 + kWinW * 128 + 128, a + oth16 + kWinW * 128 + 128, g_own, g_oth);
+                d2 = corner_dot16<T>(a + own16 + rowb, a + oth16 + rowb, g_own, g_oth);
+                d3 = corner_dot16<T>(a + own16 + rowb + 128, a + oth16 + rowb + 128, g_own, g_oth);
             } else {  // point 8: the two lanes take 8 channels each and meet
                 d0 = corner_dot8<T>(a + own16, g_own);
                 d1 = corner_dot8<T>(a + own16 + 128, g_own);
-                d2 = corner_dot8<T>(a + own16 + kWinW * 128, g_own);
-                d3 = corner_dot8<T>(a + own16 + kWinW * 128 + 128, g_own);
+                d2 = corner_dot8<T>(a + own16 + rowb, g_own);
+                d3 = corner_dot8<T>(a + own16 + rowb + 128, g_own);
                 d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
                 d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
                 d2 += __shfl_xor_sync(0xffffffffu, d2, 1);
@@ -522,7 +542,10 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                 slowmask2 |= (t.inside && valid && !fast2 ? 1u : 0u) << k;  // same for both lanes of the pair
                 const uint32_t e = fast2 ? rel * kWinW + u : 0u;
                 const float hm = hh * mk[k], lm = lh * mk[k];
-                const uint32_t top = imat::pack2<__half>(hm * hw, hm * lw), bot = imat::pack2<__half>(lm * hw, lm * lw);
+                // pairs run along A: (x, x + 1) of rows y / y + 1 — in a strip tile (y, y + 1) of columns x / x + 1
+                const float w01 = hm * lw, w10 = lm * hw;
+                const uint32_t top = imat::pack2<__half>(hm * hw, STRIP && tm ? w10 : w01);
+                const uint32_t bot = imat::pack2<__half>(STRIP && tm ? w01 : w10, lm * lw);
                 const bool keep_top = ((vb & 1u) == (unsigned)h);
                 wm_add(row_s, keep_top ? e : e + kWinW, keep_top ? top : bot, fast2);
                 if (k < 4) {
@@ -581,7 +604,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                 locate<float>(gq_, sp0h, sp0w, pi, pj, o.x, o.y, t);
                 const bool okc = crn == 0 ? t.ok1 : crn == 1 ? t.ok2 : crn == 2 ? t.ok3 : t.ok4;
                 const float wc = (crn & 2 ? t.lh : t.hh) * (crn & 1 ? t.lw : t.hw);
-                const size_t spix = ((size_t)tc.n * q.Ho + (tc.ty * 4 + (spx >> 3))) * q.Wo + (tc.tx * kTile + (spx & 7));
+                const size_t spix = ((size_t)tc.n * q.Ho + pix_y(spx)) * q.Wo + pix_x(spx);
                 const size_t ce = img_off + (okc ? ((size_t)(t.h_low + (crn >> 1)) * q.W + (t.w_low + (crn & 1))) * q.C : 0)
                                   + sgl * 16 + hf * 8;
                 uint4 gch = make_uint4(0u, 0u, 0u, 0u);
@@ -655,7 +678,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
             const int t = it * 32 + lane;
             if (t < 36) {
                 const int ppx = warp * 4 + t / 9, chk = t % 9;
-                const int poy = tc.ty * 4 + (ppx >> 3), pox = tc.tx * kTile + (ppx & 7);
+                const int poy = pix_y(ppx), pox = pix_x(ppx);
                 if (poy < q.Ho && pox < q.Wo) {
                     const size_t pp = ((size_t)tc.n * q.Ho + poy) * q.Wo + pox;
                     *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(goff) + (pp * q.opitch + gq_unit * 18) * 2 + chk * 16) =
@@ -769,17 +792,21 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         }
         __syncwarp();
         const int cell = lane >> 1, half = lane & 1;
-        const int ix = wx0 + cell;
-        const bool col_ok = (unsigned)ix < (unsigned)q.W;
+        // the lane's cell runs along A (x; y in a strip tile), the warp's band rows along B
+        const bool sw = STRIP && tm;
+        const int ca = (sw ? by0 : wx0) + cell, cb0 = (sw ? wx0 : by0) + qpar;
+        const unsigned ext_a = (unsigned)(sw ? q.H : q.W), ext_b = (unsigned)(sw ? q.W : q.H);
+        const size_t str_a = sw ? (size_t)q.W * q.C : (size_t)q.C, str_b = sw ? (size_t)q.C : (size_t)q.W * q.C;
+        const bool a_ok = (unsigned)ca < ext_a;
         const uint32_t ld_addr = fb + cell * 32 + ((uint32_t)(half ^ ((cell >> 2) & 1)) << 4);
-        T *dst0 = gin + img_off + mg * 16 + half * 8 + (size_t)ix * q.C;
+        T *dst0 = gin + img_off + mg * 16 + half * 8 + (size_t)ca * str_a;
 #pragma unroll
         for (int i = 0; i < kBandRows / 2; ++i) {
-            const int iy = by0 + qpar + 2 * i;
+            const int cb = cb0 + 2 * i;
             const uint4 o = imat::lds128(ld_addr + i * 512);
             const bool nz = ((o.x | o.y | o.z | o.w) & 0x7fff7fffu) != 0u;
-            const bool ok = col_ok && (unsigned)iy < (unsigned)q.H && nz;
-            red_add_v4<T>(ok ? dst0 + (size_t)iy * q.W * q.C : gin, o, ok);
+            const bool ok = a_ok && (unsigned)cb < ext_b && nz;
+            red_add_v4<T>(ok ? dst0 + (size_t)cb * str_b : gin, o, ok);
         }
     }
 }
