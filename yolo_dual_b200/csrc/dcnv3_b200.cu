@@ -238,7 +238,8 @@ void launch(void (*kernel)(P...), dim3 grid, unsigned block, size_t smem, cudaSt
 #ifndef DCNV3_NO_TMA
 // the input [N, H, W, C] (16-bit) as a TMA tensor map: dims (C, W, H, N), box (64 channels, box_w columns, box_h rows, 1 image);
 // coordinates outside the map are legal and read as zeros
-int make_window_tmap(const void *in, const Geo &q, unsigned box_w, unsigned box_h, CUtensorMap *tm) {
+int make_window_tmap(const void *in, const Geo &q, unsigned box_w, unsigned box_h, CUtensorMap *tm,
+                     unsigned box_c = 64, int dtype = 0 /* 0: 16-bit words, 1: fp16, 2: bf16 (reductions) */, bool swizzle32 = false) {
     typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -254,9 +255,24 @@ int make_window_tmap(const void *in, const Geo &q, unsigned box_w, unsigned box_
     }
     const cuuint64_t dims[4] = {(cuuint64_t)q.C, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.N};
     const cuuint64_t strides[3] = {(cuuint64_t)q.C * 2, (cuuint64_t)q.W * q.C * 2, (cuuint64_t)q.H * q.W * q.C * 2};
-    const cuuint32_t box[4] = {64, box_w, box_h, 1}, estr[4] = {1, 1, 1, 1};
-    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void *>(in), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    const cuuint32_t box[4] = {box_c, box_w, box_h, 1}, estr[4] = {1, 1, 1, 1};
+    const CUtensorMapDataType dt = dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                                                            : CU_TENSOR_MAP_DATA_TYPE_UINT16;
+#ifdef DCNV3_DBG_RMAP  // debugging the reduce map on a GPU box (tools/r2_dbg_rmap.sh)
+    const char *dbg = getenv("DCNV3_DBG_RMAP");
+    CUtensorMapDataType dt2 = dt; bool sw2 = swizzle32; CUtensorMapL2promotion l2 = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    if (dbg && dtype) {
+        if (strstr(dbg, "u16")) dt2 = CU_TENSOR_MAP_DATA_TYPE_UINT16;
+        if (strstr(dbg, "sw0")) sw2 = false;
+        if (strstr(dbg, "l2none")) l2 = CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    }
+    const CUresult r = enc(tm, dt2, 4, const_cast<void *>(in), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw2 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE, l2,
+#else
+    const CUresult r = enc(tm, dt, 4, const_cast<void *>(in), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+#endif
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(DCNV3_B200_EINVAL, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
@@ -381,7 +397,13 @@ int launch_bwd_win(const T *in, const T *off, const T *mask, const T *gout, T *g
     if ((rc = make_window_tmap(in, q, 16, 12, &tm))) return rc;
     if (strip_tiles) { if ((rc = make_window_tmap(in, q, 12, 16, &tms))) return rc; }
     else tms = tm;
+#if DCNV3_WIN_TMA_FLUSH
+    alignas(64) CUtensorMap tmr;
+    if ((rc = make_window_tmap(gin, q, 16, 6, &tmr, 16, std::is_same<T, __half>::value ? 1 : 2, true))) return rc;
+#define WIN_EXTRA , tm, tms, tmr
+#else
 #define WIN_EXTRA , tm, tms
+#endif
 #else
 #define WIN_EXTRA
 #endif

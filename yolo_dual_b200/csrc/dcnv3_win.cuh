@@ -157,7 +157,13 @@ __device__ __forceinline__ float corner_dot8(uint32_t a_own, const uint4 &g_own)
 __device__ __forceinline__ void wm_add(uint32_t row_s, uint32_t e, uint32_t pair, bool on) {
     const uint32_t wa = row_s + ((e >> 1) << 2);
     const bool odd = (e & 1u) != 0u;
+#if DCNV3_WIN_PRED_W1
+    const uint32_t w0 = lds32(wa);
+    uint32_t w1 = 0u;  // the second word only where the pair straddles it: fewer active lanes, fewer bank conflicts
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q ld.shared.u32 %0, [%1];\n\t}" : "+r"(w1) : "r"(wa + 4), "r"((int)(on && odd)));
+#else
     const uint32_t w0 = lds32(wa), w1 = lds32(wa + 4);
+#endif
     sts32(wa, imat::add2<__half>(w0, odd ? (pair << 16) : pair), on);
     sts32(wa + 4, imat::add2<__half>(w1, pair >> 16), on && odd);
 }
@@ -182,6 +188,29 @@ __device__ __forceinline__ float dot_chunk(const uint4 &x, const uint4 &g) {
     return s0 + s1;
 }
 
+#ifndef DCNV3_WIN_PRED_W1
+#define DCNV3_WIN_PRED_W1 0
+#endif
+#ifndef DCNV3_WIN_TMA_ZERO
+#define DCNV3_WIN_TMA_ZERO 1   // the interpolation matrix is zeroed by a bulk copy of zeros (TMA engine, on the window's mbarrier) instead of 10 STS.128 per thread: 148.9 -> 145.9 us at P3
+#endif
+#ifndef DCNV3_WIN_TMA_FLUSH
+#define DCNV3_WIN_TMA_FLUSH 1  // a warp's 6 band rows x 16 cells x 16 channels leave as ONE TMA reduce-add (cp.reduce.async.bulk.tensor -> UTMAREDG.4D.ADD): 145.9 -> 137.7 us at P3
+#endif
+#ifndef DCNV3_WIN_TMA  // -DDCNV3_NO_TMA: cp.async window fill, the threads' own zero fill and reductions
+#undef DCNV3_WIN_TMA_ZERO
+#define DCNV3_WIN_TMA_ZERO 0
+#undef DCNV3_WIN_TMA_FLUSH
+#define DCNV3_WIN_TMA_FLUSH 0
+#endif
+#if DCNV3_WIN_TMA_FLUSH  // band rows of warp half q: contiguous (6q .. 6q + 5: one TMA box) or interleaved (q, q + 2, ..)
+#define DCNV3_WIN_ROW(q, i) (6 * (q) + (i))
+#else
+#define DCNV3_WIN_ROW(q, i) ((q) + 2 * (i))
+#endif
+#ifndef DCNV3_WIN_SKIP_ZERO_MMA
+#define DCNV3_WIN_SKIP_ZERO_MMA 1  // skip the two (k-step, band row) pairs per warp whose A operand is out of every pixel's reach
+#endif
 #ifndef DCNV3_WIN_STBULK
 #define DCNV3_WIN_STBULK 0  // 1: one thread zeroes the interpolation matrix with st.bulk (UMEMSETS.64); measured +2 us at P3, profiles/r02_bwd_kernel_history.md #14
 #endif
@@ -288,6 +317,9 @@ __global__ void __launch_bounds__(256) zero_fill_kernel(uint4 *__restrict__ p, c
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n16; i += (size_t)gridDim.x * 256) p[i] = z;
 }
 
+#if DCNV3_WIN_TMA_ZERO
+__device__ __align__(128) uint4 g_wm_zeros[kWmB / 16];  // zero-initialised: the source of the bulk copy that clears Wm
+#endif
 #ifndef DCNV3_WIN_MIN_CTAS
 #define DCNV3_WIN_MIN_CTAS 3
 #endif
@@ -304,9 +336,12 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
 #ifdef DCNV3_WIN_TMA
                , const __grid_constant__ CUtensorMap tmap   // input as a 4-D tensor (C, W, H, N), box (64, 16, 12, 1)
                , const __grid_constant__ CUtensorMap tmap_s // the same tensor, box (64, 12, 16, 1): strip tiles
+#if DCNV3_WIN_TMA_FLUSH
+               , const __grid_constant__ CUtensorMap tmap_r // grad_input (C, W, H, N) in the storage dtype, box (16, 16, 6, 1), 32-byte swizzle
+#endif
 #endif
                , const int strip_tiles) {
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(256) unsigned char smem[];  // 256: the period of the TMA 32-byte swizzle (flush staging)
     constexpr bool kScaled = std::is_same<T, __nv_bfloat16>::value;
     __shared__ __align__(16) uint32_t smax[8];
 #ifdef DCNV3_WIN_TMA
@@ -369,7 +404,21 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     // The window as ONE TMA box load (cp.async.bulk.tensor.4d): coordinates may lie outside the map, the hardware fills
     // those cells with zeros (= the reference's per-corner validity); completion is signalled on an mbarrier that
     // thread 0 waits for in front of barrier A.
+#if DCNV3_WIN_TMA_ZERO
+    if (tid == 0) {  // the window box and the interpolation matrix's zeros on one mbarrier
+        const uint32_t bar_s = imat::smem_u32(&win_bar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(kDwinB + kWmB) : "memory");
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(smem_s), "l"(reinterpret_cast<uint64_t>(STRIP && tm ? &tmap_s : &tmap)), "r"(bar_s), "r"(tc.gq * 64), "r"(wx0), "r"(by0), "r"(tc.n) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_s + kWmOff), "l"(reinterpret_cast<uint64_t>(g_wm_zeros)), "r"(kWmB), "r"(bar_s) : "memory");
+    }
+#else
     if (tid == 0) imat::tma_load_4d(smem_s, STRIP && tm ? &tmap_s : &tmap, imat::smem_u32(&win_bar), kDwinB, tc.gq * 64, wx0, by0, tc.n);
+#endif
 #else
     static_assert(!STRIP, "strip tiles are loaded by TMA");
     {  // stage the 12x16-cell x 64-channel window, unswizzled; zero outside the map
@@ -393,6 +442,8 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     // zero the interpolation matrix with ONE instruction of one thread (st.bulk -> UMEMSETS.64, sm_100); barrier A publishes
     // it.  Measured slower than the 10 x 16-byte stores per thread it replaces (154.0 vs 152.0 us at P3): kept for A/B only.
     if (tid == 32) asm volatile("st.bulk.weak.shared::cta [%0], %1, 0;" ::"r"(smem_s + kWmOff), "l"((unsigned long long)kWmB) : "memory");
+    if (tid < 2) sts128(smem_s + kZeroOff + tid * 16, make_uint4(0u, 0u, 0u, 0u));
+#elif DCNV3_WIN_TMA_ZERO
     if (tid < 2) sts128(smem_s + kZeroOff + tid * 16, make_uint4(0u, 0u, 0u, 0u));
 #else
     {   // zero the interpolation matrix and the zero row (in the shadow of the loads above)
@@ -757,8 +808,14 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
             const int apx = 16 * s + 8 * (jm >> 1) + jr, ar = 2 * s + (jm >> 1);
             const uint32_t abase = wm_g + apx * kRowB + (jm & 1) * 16;
 #pragma unroll
-            for (int i = 0; i < kBandRows / 2; ++i) {  // band row rr = qpar + 2i
-                const int rel = qpar + 2 * i - ar;
+            for (int i = 0; i < kBandRows / 2; ++i) {
+                const int rr = DCNV3_WIN_ROW(qpar, i);  // band row
+#if DCNV3_WIN_SKIP_ZERO_MMA
+                // band rows 10 / 11 are out of reach of the pixels of band rows 0 / 1 (k-step 0), band rows 0 / 1 lie above
+                // the pixels of band rows 2 / 3 (k-step 1): A = 0 whatever the data  (warp-uniform)
+                if (s == 0 ? rr >= 10 : rr <= 1) continue;
+#endif
+                const int rel = rr - ar;
                 uint32_t a0, a1, a2, a3;
                 imat::ldmatrix_x4_trans(a0, a1, a2, a3, (unsigned)rel < (unsigned)kRelRows ? abase + rel * (kWinW * 2) : zero_a);
                 imat::mma_16816<__half>(gw[i][0], a0, a1, a2, a3, b00, b01);
@@ -790,11 +847,31 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
             stmatrix_x4(st_addr + i * 512, imat::pack2<T>(gw[i][0][0], gw[i][0][1]), imat::pack2<T>(gw[i][0][2], gw[i][0][3]),
                         imat::pack2<T>(gw[i][1][0], gw[i][1][1]), imat::pack2<T>(gw[i][1][2], gw[i][1][3]));
         }
+#if DCNV3_WIN_TMA_FLUSH
+        // (a box that STARTS at a negative coordinate is an illegal instruction for the reduce — unlike the loads, and unlike
+        // a box that overhangs the far edges, which is clipped: tools/tma_reduce_probe.cu — so the warps of the left tile
+        // column and of the top band's upper half keep their own reductions)
+        if (!(STRIP && tm) && wx0 >= 0 && by0 + 6 * qpar >= 0) {
+            // the staging area is exactly a TMA box in shared memory ([6 rows][16 cells][32 B], the two 16-byte halves of a
+            // cell swapped where address bit 7 is set = CU_TENSOR_MAP_SWIZZLE_32B): the copy engine adds it into grad_input,
+            // clips what lies outside the map, and the warp issues no loads, predicates or reductions of its own
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tmap_r)), "r"(fb), "r"(tc.gq * 64 + mg * 16), "r"(wx0),
+                               "r"(by0 + 6 * qpar), "r"(tc.n) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the engine has read the staging area
+            }
+            return;
+        }
+#endif
         __syncwarp();
         const int cell = lane >> 1, half = lane & 1;
         // the lane's cell runs along A (x; y in a strip tile), the warp's band rows along B
         const bool sw = STRIP && tm;
-        const int ca = (sw ? by0 : wx0) + cell, cb0 = (sw ? wx0 : by0) + qpar;
+        const int ca = (sw ? by0 : wx0) + cell, cb0 = (sw ? wx0 : by0);
         const unsigned ext_a = (unsigned)(sw ? q.H : q.W), ext_b = (unsigned)(sw ? q.W : q.H);
         const size_t str_a = sw ? (size_t)q.W * q.C : (size_t)q.C, str_b = sw ? (size_t)q.C : (size_t)q.W * q.C;
         const bool a_ok = (unsigned)ca < ext_a;
@@ -802,7 +879,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         T *dst0 = gin + img_off + mg * 16 + half * 8 + (size_t)ca * str_a;
 #pragma unroll
         for (int i = 0; i < kBandRows / 2; ++i) {
-            const int cb = cb0 + 2 * i;
+            const int cb = cb0 + DCNV3_WIN_ROW(qpar, i);
             const uint4 o = imat::lds128(ld_addr + i * 512);
             const bool nz = ((o.x | o.y | o.z | o.w) & 0x7fff7fffu) != 0u;
             const bool ok = a_ok && (unsigned)cb < ext_b && nz;
