@@ -239,7 +239,7 @@ void launch(void (*kernel)(P...), dim3 grid, unsigned block, size_t smem, cudaSt
 // the input [N, H, W, C] (16-bit) as a TMA tensor map: dims (C, W, H, N), box (64 channels, box_w columns, box_h rows, 1 image);
 // coordinates outside the map are legal and read as zeros
 int make_window_tmap(const void *in, const Geo &q, unsigned box_w, unsigned box_h, CUtensorMap *tm,
-                     unsigned box_c = 64, int dtype = 0 /* 0: 16-bit words, 1: fp16, 2: bf16 (reductions) */, bool swizzle32 = false) {
+                     unsigned box_c = 64, int dtype = 0 /* 0: 16-bit words, 1: fp16, 2: bf16 (reductions) */, int swizzle = 0 /* 0, 32, 128 */) {
     typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -260,17 +260,17 @@ int make_window_tmap(const void *in, const Geo &q, unsigned box_w, unsigned box_
                                                                                             : CU_TENSOR_MAP_DATA_TYPE_UINT16;
 #ifdef DCNV3_DBG_RMAP  // debugging the reduce map on a GPU box (tools/r2_dbg_rmap.sh)
     const char *dbg = getenv("DCNV3_DBG_RMAP");
-    CUtensorMapDataType dt2 = dt; bool sw2 = swizzle32; CUtensorMapL2promotion l2 = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    CUtensorMapDataType dt2 = dt; int sw2 = swizzle; CUtensorMapL2promotion l2 = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     if (dbg && dtype) {
         if (strstr(dbg, "u16")) dt2 = CU_TENSOR_MAP_DATA_TYPE_UINT16;
-        if (strstr(dbg, "sw0")) sw2 = false;
+        if (strstr(dbg, "sw0")) sw2 = 0;
         if (strstr(dbg, "l2none")) l2 = CU_TENSOR_MAP_L2_PROMOTION_NONE;
     }
     const CUresult r = enc(tm, dt2, 4, const_cast<void *>(in), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw2 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE, l2,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw2 == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : sw2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, l2,
 #else
     const CUresult r = enc(tm, dt, 4, const_cast<void *>(in), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
 #endif
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -399,7 +399,8 @@ int launch_bwd_win(const T *in, const T *off, const T *mask, const T *gout, T *g
     else tms = tm;
 #if DCNV3_WIN_TMA_FLUSH
     alignas(64) CUtensorMap tmr;
-    if ((rc = make_window_tmap(gin, q, 16, 6, &tmr, 16, std::is_same<T, __half>::value ? 1 : 2, true))) return rc;
+    if ((rc = make_window_tmap(gin, q, 16, 6, &tmr, DCNV3_WIN_TMA_FLUSH == 2 ? 64 : 16, std::is_same<T, __half>::value ? 1 : 2,
+                               DCNV3_WIN_TMA_FLUSH == 2 ? 128 : 32))) return rc;
 #define WIN_EXTRA , tm, tms, tmr
 #else
 #define WIN_EXTRA , tm, tms

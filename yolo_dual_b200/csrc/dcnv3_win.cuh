@@ -195,7 +195,7 @@ __device__ __forceinline__ float dot_chunk(const uint4 &x, const uint4 &g) {
 #define DCNV3_WIN_TMA_ZERO 1   // the interpolation matrix is zeroed by a bulk copy of zeros (TMA engine, on the window's mbarrier) instead of 10 STS.128 per thread: 148.9 -> 145.9 us at P3
 #endif
 #ifndef DCNV3_WIN_TMA_FLUSH
-#define DCNV3_WIN_TMA_FLUSH 1  // a warp's 6 band rows x 16 cells x 16 channels leave as ONE TMA reduce-add (cp.reduce.async.bulk.tensor -> UTMAREDG.4D.ADD): 145.9 -> 137.7 us at P3
+#define DCNV3_WIN_TMA_FLUSH 1  // (2: one box per warp half, 64 channels wide) a warp's 6 band rows x 16 cells x 16 channels leave as ONE TMA reduce-add (cp.reduce.async.bulk.tensor -> UTMAREDG.4D.ADD): 145.9 -> 137.7 us at P3
 #endif
 #ifndef DCNV3_WIN_TMA  // -DDCNV3_NO_TMA: cp.async window fill, the threads' own zero fill and reductions
 #undef DCNV3_WIN_TMA_ZERO
@@ -341,7 +341,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
 #endif
 #endif
                , const int strip_tiles) {
-    extern __shared__ __align__(256) unsigned char smem[];  // 256: the period of the TMA 32-byte swizzle (flush staging)
+    extern __shared__ __align__(DCNV3_WIN_TMA_FLUSH == 2 ? 1024 : 256) unsigned char smem[];  // the period of the TMA 128- / 32-byte swizzle (flush staging)
     constexpr bool kScaled = std::is_same<T, __nv_bfloat16>::value;
     __shared__ __align__(16) uint32_t smax[8];
 #ifdef DCNV3_WIN_TMA
@@ -832,9 +832,18 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     // matrix (and the 8 lanes of an LDS.128 phase) fall into 8 different 16-byte bank groups.
     {
         const int jm = lane >> 3, jr = lane & 7;
-        const uint32_t fb = smem_s + warp * kFlushWarpB;
         const int scell = jr + 8 * (jm & 1);
+#if DCNV3_WIN_TMA_FLUSH == 2
+        // staging of a warp half (4 groups): [6 band rows][16 cells][64 channels = 128 B], the cell's eight 16-byte chunks
+        // XOR-ed with cell & 7 (= CU_TENSOR_MAP_SWIZZLE_128B; also what keeps the stmatrix rows on distinct bank groups)
+        constexpr uint32_t kStRow = kWinW * 128;
+        const uint32_t fb = smem_s + qpar * (6 * kStRow);
+        const uint32_t st_addr = fb + scell * 128 + ((uint32_t)((2 * mg + (jm >> 1)) ^ (scell & 7)) << 4);
+#else
+        constexpr uint32_t kStRow = 512;
+        const uint32_t fb = smem_s + warp * kFlushWarpB;
         const uint32_t st_addr = fb + scell * 32 + ((uint32_t)((jm >> 1) ^ ((scell >> 2) & 1)) << 4);
+#endif
         const float unscale = __uint_as_float((uint32_t)e_ref << 23);  // 2^(e_ref - 127), bf16 storage only
 #pragma unroll
         for (int i = 0; i < kBandRows / 2; ++i) {
@@ -844,7 +853,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
 #pragma unroll
                     for (int c = 0; c < 4; ++c) gw[i][n2][c] *= unscale;
             }
-            stmatrix_x4(st_addr + i * 512, imat::pack2<T>(gw[i][0][0], gw[i][0][1]), imat::pack2<T>(gw[i][0][2], gw[i][0][3]),
+            stmatrix_x4(st_addr + i * kStRow, imat::pack2<T>(gw[i][0][0], gw[i][0][1]), imat::pack2<T>(gw[i][0][2], gw[i][0][3]),
                         imat::pack2<T>(gw[i][1][0], gw[i][1][1]), imat::pack2<T>(gw[i][1][2], gw[i][1][3]));
         }
 #if DCNV3_WIN_TMA_FLUSH
@@ -856,6 +865,18 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
             // cell swapped where address bit 7 is set = CU_TENSOR_MAP_SWIZZLE_32B): the copy engine adds it into grad_input,
             // clips what lies outside the map, and the warp issues no loads, predicates or reductions of its own
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#if DCNV3_WIN_TMA_FLUSH == 2
+            // one box per warp half: 64 channels (128-byte rows for the copy engine instead of four times as many 32-byte
+            // ones) x 16 cells x 6 band rows; the half's four warps meet at a named barrier, one lane issues
+            if (qpar) asm volatile("bar.sync 2, 128;" ::: "memory"); else asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (mg == 0 && lane == 0) {
+                asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tmap_r)), "r"(fb), "r"(tc.gq * 64), "r"(wx0),
+                               "r"(by0 + 6 * qpar), "r"(tc.n) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the engine has read the staging area
+            }
+#else
             __syncwarp();
             if (lane == 0) {
                 asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -864,6 +885,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the engine has read the staging area
             }
+#endif
             return;
         }
 #endif
@@ -875,12 +897,16 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
         const unsigned ext_a = (unsigned)(sw ? q.H : q.W), ext_b = (unsigned)(sw ? q.W : q.H);
         const size_t str_a = sw ? (size_t)q.W * q.C : (size_t)q.C, str_b = sw ? (size_t)q.C : (size_t)q.W * q.C;
         const bool a_ok = (unsigned)ca < ext_a;
+#if DCNV3_WIN_TMA_FLUSH == 2
+        const uint32_t ld_addr = fb + cell * 128 + ((uint32_t)((2 * mg + half) ^ (cell & 7)) << 4);
+#else
         const uint32_t ld_addr = fb + cell * 32 + ((uint32_t)(half ^ ((cell >> 2) & 1)) << 4);
+#endif
         T *dst0 = gin + img_off + mg * 16 + half * 8 + (size_t)ca * str_a;
 #pragma unroll
         for (int i = 0; i < kBandRows / 2; ++i) {
             const int cb = cb0 + DCNV3_WIN_ROW(qpar, i);
-            const uint4 o = imat::lds128(ld_addr + i * 512);
+            const uint4 o = imat::lds128(ld_addr + i * kStRow);
             const bool nz = ((o.x | o.y | o.z | o.w) & 0x7fff7fffu) != 0u;
             const bool ok = a_ok && (unsigned)cb < ext_b && nz;
             red_add_v4<T>(ok ? dst0 + (size_t)cb * str_b : gin, o, ok);
