@@ -238,8 +238,9 @@ void launch(void (*kernel)(P...), dim3 grid, unsigned block, size_t smem, cudaSt
 #ifndef DCNV3_NO_TMA
 // the input [N, H, W, C] (16-bit) as a TMA tensor map: dims (C, W, H, N), box (64 channels, box_w columns, box_h rows, 1 image);
 // coordinates outside the map are legal and read as zeros
-int make_window_tmap(const void *in, const Geo &q, unsigned box_w, unsigned box_h, CUtensorMap *tm,
-                     unsigned box_c = 64, int dtype = 0 /* 0: 16-bit words, 1: fp16, 2: bf16 (reductions) */, int swizzle = 0 /* 0, 32, 128 */) {
+// a 4-D tiled tensor map over 16-bit elements: dims / box innermost first, rows of dims[0] elements `pitch0` elements apart
+int make_tmap4(const void *base, const cuuint64_t (&dims)[4], cuuint64_t pitch0, const cuuint32_t (&box)[4], int dtype, int swizzle,
+               CUtensorMap *tm) {
     typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -253,29 +254,21 @@ int make_window_tmap(const void *in, const Geo &q, unsigned box_w, unsigned box_
         }
         enc = (encode_fn)f;
     }
-    const cuuint64_t dims[4] = {(cuuint64_t)q.C, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.N};
-    const cuuint64_t strides[3] = {(cuuint64_t)q.C * 2, (cuuint64_t)q.W * q.C * 2, (cuuint64_t)q.H * q.W * q.C * 2};
-    const cuuint32_t box[4] = {box_c, box_w, box_h, 1}, estr[4] = {1, 1, 1, 1};
+    const cuuint64_t strides[3] = {pitch0 * 2, dims[1] * pitch0 * 2, dims[2] * dims[1] * pitch0 * 2};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUtensorMapDataType dt = dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                                                                             : CU_TENSOR_MAP_DATA_TYPE_UINT16;
-#ifdef DCNV3_DBG_RMAP  // debugging the reduce map on a GPU box (tools/r2_dbg_rmap.sh)
-    const char *dbg = getenv("DCNV3_DBG_RMAP");
-    CUtensorMapDataType dt2 = dt; int sw2 = swizzle; CUtensorMapL2promotion l2 = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
-    if (dbg && dtype) {
-        if (strstr(dbg, "u16")) dt2 = CU_TENSOR_MAP_DATA_TYPE_UINT16;
-        if (strstr(dbg, "sw0")) sw2 = 0;
-        if (strstr(dbg, "l2none")) l2 = CU_TENSOR_MAP_L2_PROMOTION_NONE;
-    }
-    const CUresult r = enc(tm, dt2, 4, const_cast<void *>(in), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw2 == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : sw2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, l2,
-#else
-    const CUresult r = enc(tm, dt, 4, const_cast<void *>(in), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-#endif
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = enc(tm, dt, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           swizzle == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(DCNV3_B200_EINVAL, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
+}
+int make_window_tmap(const void *in, const Geo &q, unsigned box_w, unsigned box_h, CUtensorMap *tm,
+                     unsigned box_c = 64, int dtype = 0 /* 0: 16-bit words, 1: fp16, 2: bf16 (reductions) */, int swizzle = 0 /* 0, 32, 128 */) {
+    const cuuint64_t dims[4] = {(cuuint64_t)q.C, (cuuint64_t)q.W, (cuuint64_t)q.H, (cuuint64_t)q.N};
+    const cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+    return make_tmap4(in, dims, (cuuint64_t)q.C, box, dtype, swizzle, tm);
 }
 #endif
 
@@ -391,19 +384,33 @@ int launch_bwd_win(const T *in, const T *off, const T *mask, const T *gout, T *g
 #else
     const dim3 grid((unsigned)(tiles_x * GQ), (unsigned)(bands_y + strip_rows), (unsigned)q.N);
 #endif
-    int rc;
+    int rc, stage_tma = 0;
 #ifdef DCNV3_WIN_TMA
     alignas(64) CUtensorMap tm, tms;
     if ((rc = make_window_tmap(in, q, 16, 12, &tm))) return rc;
     if (strip_tiles) { if ((rc = make_window_tmap(in, q, 12, 16, &tms))) return rc; }
     else tms = tm;
+    // offsets / masks of a tile as two more boxes (80 / 40 elements = the staging area's pixel pitch x 8 columns x 4 rows) when
+    // their rows are 16-byte multiples (G a multiple of 8 with unpacked heads); otherwise the warps' own cp.async chunks
+    alignas(64) CUtensorMap tmo, tmm;
+#if DCNV3_WIN_TMA_STAGE
+    if ((q.opitch * 2) % 16 == 0 && (q.mpitch * 2) % 16 == 0 && aligned16(mask)) {
+        const cuuint64_t od[4] = {(cuuint64_t)q.opitch, (cuuint64_t)q.Wo, (cuuint64_t)q.Ho, (cuuint64_t)q.N};
+        const cuuint64_t md[4] = {(cuuint64_t)q.mpitch, (cuuint64_t)q.Wo, (cuuint64_t)q.Ho, (cuuint64_t)q.N};
+        const cuuint32_t ob[4] = {win::kStOffPx / 2, 8, 4, 1}, mb[4] = {win::kStMaskPx / 2, 8, 4, 1};
+        if ((rc = make_tmap4(off, od, (cuuint64_t)q.opitch, ob, 0, 0, &tmo))) return rc;
+        if ((rc = make_tmap4(mask, md, (cuuint64_t)q.mpitch, mb, 0, 0, &tmm))) return rc;
+        stage_tma = 1;
+    }
+#endif
+    if (!stage_tma) { tmo = tm; tmm = tm; }
 #if DCNV3_WIN_TMA_FLUSH
     alignas(64) CUtensorMap tmr;
     if ((rc = make_window_tmap(gin, q, 16, 6, &tmr, DCNV3_WIN_TMA_FLUSH == 2 ? 64 : 16, std::is_same<T, __half>::value ? 1 : 2,
                                DCNV3_WIN_TMA_FLUSH == 2 ? 128 : 32))) return rc;
-#define WIN_EXTRA , tm, tms, tmr
+#define WIN_EXTRA , tm, tms, tmo, tmm, tmr
 #else
-#define WIN_EXTRA , tm, tms
+#define WIN_EXTRA , tm, tms, tmo, tmm
 #endif
 #else
 #define WIN_EXTRA
@@ -412,7 +419,7 @@ int launch_bwd_win(const T *in, const T *off, const T *mask, const T *gout, T *g
     do {                                                                                                                \
         if ((rc = set_smem(win::bwd_win_kernel<T, LG, SP>, win::kSmemB, "cudaFuncSetAttribute(bwd_win_kernel)"))) return rc; \
         launch(win::bwd_win_kernel<T, LG, SP>, grid, win::kThreadsW, win::kSmemB, st, in, off, mask, gout, gin, goff, gmask, q, \
-               GQ, tiles_x, bands_y WIN_EXTRA, strip_tiles);                                                            \
+               GQ, tiles_x, bands_y WIN_EXTRA, strip_tiles, stage_tma);                                                            \
     } while (0)
 #ifdef DCNV3_WIN_TMA
     if (strip_tiles) {

@@ -69,12 +69,13 @@ constexpr int kStMaskPx = 80;
 constexpr int kStOffB = 32 * kStOffPx;                   // 5 120 B
 constexpr int kStMaskB = 32 * kStMaskPx;                 // 2 560 B
 constexpr int kStageB = kStOffB + kStMaskB;
-// shared memory of a CTA: [window | Wm | Gos | staging | one zero row]; nothing aliases, so a warp walks from the dots of
+// shared memory of a CTA: [window | staging | Wm | Gos | one zero row]; nothing aliases, so a warp walks from the dots of
 // its lanes straight into their scatter without waiting for the other warps
-constexpr int kWmOff = kDwinB;
+constexpr int kStageOff = kDwinB;                        // (behind the window: TMA destinations are 128-byte aligned)
+constexpr int kWmOff = kStageOff + kStageB;
 constexpr int kGosOff = kWmOff + kWmB;
-constexpr int kStageOff = kGosOff + kGoB;
-constexpr int kZeroOff = kStageOff + kStageB;            // 32 zero bytes: ldmatrix rows of pixels that cannot reach a band row
+constexpr int kZeroOff = kGosOff + kGoB;                 // 32 zero bytes: ldmatrix rows of pixels that cannot reach a band row
+static_assert(kStageOff % 128 == 0 && kStOffB % 128 == 0, "TMA destinations (offsets, masks) are 128-byte aligned");
 #ifndef DCNV3_WIN_EXTRA_SMEM
 #define DCNV3_WIN_EXTRA_SMEM 0  // occupancy experiments: pad the CTA's shared memory (profiles/r02_bwd_kernel_history.md)
 #endif
@@ -197,11 +198,16 @@ __device__ __forceinline__ float dot_chunk(const uint4 &x, const uint4 &g) {
 #ifndef DCNV3_WIN_TMA_FLUSH
 #define DCNV3_WIN_TMA_FLUSH 1  // (2: one box per warp half, 64 channels wide) a warp's 6 band rows x 16 cells x 16 channels leave as ONE TMA reduce-add (cp.reduce.async.bulk.tensor -> UTMAREDG.4D.ADD): 145.9 -> 137.7 us at P3
 #endif
+#ifndef DCNV3_WIN_TMA_STAGE
+#define DCNV3_WIN_TMA_STAGE 1  // the tile's offsets / masks arrive as two TMA boxes (when their rows are 16-byte multiples) instead of per-warp cp.async chunks
+#endif
 #ifndef DCNV3_WIN_TMA  // -DDCNV3_NO_TMA: cp.async window fill, the threads' own zero fill and reductions
 #undef DCNV3_WIN_TMA_ZERO
 #define DCNV3_WIN_TMA_ZERO 0
 #undef DCNV3_WIN_TMA_FLUSH
 #define DCNV3_WIN_TMA_FLUSH 0
+#undef DCNV3_WIN_TMA_STAGE
+#define DCNV3_WIN_TMA_STAGE 0
 #endif
 #if DCNV3_WIN_TMA_FLUSH  // band rows of warp half q: contiguous (6q .. 6q + 5: one TMA box) or interleaved (q, q + 2, ..)
 #define DCNV3_WIN_ROW(q, i) (6 * (q) + (i))
@@ -297,7 +303,7 @@ __device__ __forceinline__ int slot_i(int k, int h) { return k == 4 ? 2 : (h ? (
 __device__ __forceinline__ int slot_j(int k, int h) { return k == 4 ? 2 : (h ? (4 + k) % 3 : k % 3); }
 
 // ===========================================================================================================
-// Shared memory of a CTA (75 360 B, three CTAs per SM): [window 24 576 | Wm 38 976 | Gos 4 096 | staging 7 680 | zero row 32].
+// Shared memory of a CTA (75 360 B, three CTAs per SM): [window 24 576 | staging 7 680 | Wm 38 976 | Gos 4 096 | zero row 32].
 // Nothing aliases: the interpolation matrix is zeroed in the shadow of the first loads and a warp goes from a point's dots
 // straight to the same point's matrix updates.  The one CTA barrier after the far-band vote is in front of the tensor
 // cores; behind it the window is dead and becomes the flush staging area (3 KB per warp).
@@ -336,16 +342,18 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
 #ifdef DCNV3_WIN_TMA
                , const __grid_constant__ CUtensorMap tmap   // input as a 4-D tensor (C, W, H, N), box (64, 16, 12, 1)
                , const __grid_constant__ CUtensorMap tmap_s // the same tensor, box (64, 12, 16, 1): strip tiles
+               , const __grid_constant__ CUtensorMap tmap_o // offsets (opitch, Wo, Ho, N), box (80, 8, 4, 1)
+               , const __grid_constant__ CUtensorMap tmap_m // masks (mpitch, Wo, Ho, N), box (40, 8, 4, 1)
 #if DCNV3_WIN_TMA_FLUSH
                , const __grid_constant__ CUtensorMap tmap_r // grad_input (C, W, H, N) in the storage dtype, box (16, 16, 6, 1), 32-byte swizzle
 #endif
 #endif
-               , const int strip_tiles) {
+               , const int strip_tiles, const int stage_tma) {
     extern __shared__ __align__(DCNV3_WIN_TMA_FLUSH == 2 ? 1024 : 256) unsigned char smem[];  // the period of the TMA 128- / 32-byte swizzle (flush staging)
     constexpr bool kScaled = std::is_same<T, __nv_bfloat16>::value;
     __shared__ __align__(16) uint32_t smax[8];
 #ifdef DCNV3_WIN_TMA
-    __shared__ __align__(8) unsigned long long win_bar;
+    __shared__ __align__(8) unsigned long long win_bar, st_bar;
 #endif
     pdl_enter();  // (waiting only in front of the first grad_input access instead measured nothing: 190.4 vs 191.0 us at P3)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -385,6 +393,32 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     // own four pixels: no CTA barrier on either side, __syncwarp() is enough.
     const uint32_t stage_s = smem_s + kStageOff;
     const size_t gq_unit = (size_t)tc.gq * kWarps;
+#if DCNV3_WIN_TMA_STAGE
+    // a whole tile's offsets / masks as two TMA boxes: 80 / 40 elements per pixel (the staging area's pixel pitch; the group
+    // quad's 72 / 36 come first), 8 columns x 4 rows; pixels outside the map are zero-filled.  Not for strip tiles (their
+    // pixel order is transposed).
+    const bool tstage = stage_tma != 0 && !(STRIP && tm);
+    // a box starts on a 16-byte boundary of its row (else: illegal instruction): the masks of an odd group quad begin 8 bytes
+    // into their box (36 elements per quad; the box is 40 wide), and so do the results that go back out of the staging area
+    const uint32_t mshift = tstage ? (uint32_t)(((int)gq_unit * 9) & 7) * 2u : 0u;
+    if (tstage) {
+        if (tid == 0) {
+            const uint32_t bar_s = imat::smem_u32(&st_bar);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(kStOffB + kStMaskB) : "memory");
+            asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                         ::"r"(stage_s), "l"(reinterpret_cast<uint64_t>(&tmap_o)), "r"(bar_s), "r"((int)gq_unit * 18), "r"(px0), "r"(py0), "r"(tc.n) : "memory");
+            asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                         ::"r"(stage_s + kStOffB), "l"(reinterpret_cast<uint64_t>(&tmap_m)), "r"(bar_s), "r"(((int)gq_unit * 9) & ~7), "r"(px0), "r"(py0), "r"(tc.n) : "memory");
+        }
+    } else
+#else
+    (void)stage_tma;
+    constexpr bool tstage = false;
+    constexpr uint32_t mshift = 0u;
+#endif
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
         const int t = it * 32 + lane;           // chunk 0..35 of the warp
@@ -476,10 +510,16 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
 #else
     asm volatile("cp.async.wait_group 1;" ::: "memory");
 #endif
+#if DCNV3_WIN_TMA_STAGE
+    if (tstage) {  // CTA-uniform: the two boxes have landed (the window may still be in flight)
+        if (tid == 0) imat::tma_wait(imat::smem_u32(&st_bar));
+        __syncthreads();
+    }
+#endif
     __syncwarp();  // this warp's offsets / masks are staged (the window may still be in flight)
 
     // ---- this lane's offsets of points 4h..4h+3 and 8, their masks (all nine for the softmax), grad_output
-    const uint32_t so_l = stage_s + px * kStOffPx + gl * 36, sm_l = stage_s + kStOffB + px * kStMaskPx + gl * 18;
+    const uint32_t so_l = stage_s + px * kStOffPx + gl * 36, sm_l = stage_s + kStOffB + px * kStMaskPx + gl * 18 + mshift;
     uint32_t roff[5];
     float rm[LOGITS ? 9 : 5];
 #pragma unroll
@@ -735,7 +775,7 @@ bwd_win_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                     *reinterpret_cast<uint4 *>(reinterpret_cast<char *>(goff) + (pp * q.opitch + gq_unit * 18) * 2 + chk * 16) =
                         imat::lds128(stage_s + ppx * kStOffPx + chk * 16);
                     *reinterpret_cast<uint2 *>(reinterpret_cast<char *>(gmask) + (pp * q.mpitch + gq_unit * 9) * 2 + chk * 8) =
-                        lds64(stage_s + kStOffB + ppx * kStMaskPx + chk * 8);
+                        lds64(stage_s + kStOffB + ppx * kStMaskPx + chk * 8 + mshift);
                 }
             }
         }
