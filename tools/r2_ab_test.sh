@@ -6,7 +6,7 @@ for f in tools/var_*.bin; do
   v=$(basename $f .bin); [ "$v" = "${SKIP_TEST:-var_a}"* ] && continue
   case $v in var_a*) continue;; esac
   cp $f $L
-  python -m pytest tests/test_win_gpu.py tests/test_dcnv3_gpu.py tests/test_imat_gpu.py tests/test_infer_gpu.py -m gpu -x -q 2>&1 | tail -2 | sed "s/^/$v: /"
+  python -m pytest tests/test_win_gpu.py tests/test_dcnv3_gpu.py tests/test_imat_gpu.py tests/test_infer_gpu.py tests/test_packed_gpu.py -m gpu -x -q 2>&1 | tail -2 | sed "s/^/$v: /"
 done
 cp /tmp/orig.so $L
 STEPS=${STEPS:-200} bash tools/ab_multi.sh

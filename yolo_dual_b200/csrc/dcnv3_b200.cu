@@ -457,16 +457,30 @@ int forward_t(const void *in_, const void *off_, const void *mask_, void *out_, 
 #ifdef DCNV3_FWD_TMA
             alignas(64) CUtensorMap tm;
             if ((rc = make_window_tmap(in, q, imat::kFwin, imat::kFwin, &tm))) return rc;
+#if DCNV3_FWD_TMA_STAGE
+            alignas(64) CUtensorMap tmo = tm, tmm = tm;
+            int stage_tma = 0;
+            if ((q.opitch * 2) % 16 == 0 && (q.mpitch * 2) % 16 == 0 && aligned16(off_) && aligned16(mask_)) {
+                const cuuint64_t od[4] = {(cuuint64_t)q.opitch, (cuuint64_t)q.Wo, (cuuint64_t)q.Ho, (cuuint64_t)q.N};
+                const cuuint64_t md[4] = {(cuuint64_t)q.mpitch, (cuuint64_t)q.Wo, (cuuint64_t)q.Ho, (cuuint64_t)q.N};
+                const cuuint32_t ob[4] = {imat::kFstOffPx / 2, 8, 8, 1}, mb[4] = {imat::kFstMaskPx / 2, 8, 8, 1};
+                if ((rc = make_tmap4(off, od, (cuuint64_t)q.opitch, ob, 0, 0, &tmo))) return rc;
+                if ((rc = make_tmap4(mask, md, (cuuint64_t)q.mpitch, mb, 0, 0, &tmm))) return rc;
+                stage_tma = 1;
+            }
+#define FWD_EXTRA , tm, tmo, tmm, stage_tma
+#else
 #define FWD_EXTRA , tm
+#endif
 #else
 #define FWD_EXTRA
 #endif
             if (logits) {
-                if ((rc = set_smem(imat::fwd_tile_kernel<T, true>, imat::kFwinBytes, "cudaFuncSetAttribute(fwd_tile_kernel)"))) return rc;
-                launch(imat::fwd_tile_kernel<T, true>, grid, imat::kFwdTileThreads, imat::kFwinBytes, st, in, off, mask, out, q, GQ FWD_EXTRA);
+                if ((rc = set_smem(imat::fwd_tile_kernel<T, true>, imat::kFwdSmemB, "cudaFuncSetAttribute(fwd_tile_kernel)"))) return rc;
+                launch(imat::fwd_tile_kernel<T, true>, grid, imat::kFwdTileThreads, imat::kFwdSmemB, st, in, off, mask, out, q, GQ FWD_EXTRA);
             } else {
-                if ((rc = set_smem(imat::fwd_tile_kernel<T, false>, imat::kFwinBytes, "cudaFuncSetAttribute(fwd_tile_kernel)"))) return rc;
-                launch(imat::fwd_tile_kernel<T, false>, grid, imat::kFwdTileThreads, imat::kFwinBytes, st, in, off, mask, out, q, GQ FWD_EXTRA);
+                if ((rc = set_smem(imat::fwd_tile_kernel<T, false>, imat::kFwdSmemB, "cudaFuncSetAttribute(fwd_tile_kernel)"))) return rc;
+                launch(imat::fwd_tile_kernel<T, false>, grid, imat::kFwdTileThreads, imat::kFwdSmemB, st, in, off, mask, out, q, GQ FWD_EXTRA);
             }
 #undef FWD_EXTRA
             return 0;

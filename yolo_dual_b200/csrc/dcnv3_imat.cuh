@@ -1192,6 +1192,18 @@ constexpr int kFwin = 20, kFhalo = 6;            // window of the staged forward
 constexpr int kFwinCells = kFwin * kFwin;
 constexpr int kFzeroCells = kFwin + 2;            // zero cells behind the window: where a closed point's four corners read
 constexpr int kFwinBytes = (kFwinCells + kFzeroCells) * 128;  // 54 016 B: three CTAs per SM
+// staging area of the tile's offsets / masks (two TMA boxes, as in win::bwd_win_kernel): 64 pixels x 160 B / 80 B
+constexpr int kFstOffPx = 160, kFstMaskPx = 80;
+constexpr int kFstOffB = 64 * kFstOffPx, kFstMaskB = 64 * kFstMaskPx;
+#ifndef DCNV3_FWD_TMA_STAGE
+#define DCNV3_FWD_TMA_STAGE 1
+#endif
+#if defined(DCNV3_FWD_TMA) && DCNV3_FWD_TMA_STAGE
+constexpr int kFwdSmemB = kFwinBytes + kFstOffB + kFstMaskB;   // 69 376 B: still three CTAs per SM
+#else
+constexpr int kFwdSmemB = kFwinBytes;
+#endif
+static_assert(kFwinBytes % 128 == 0 && kFstOffB % 128 == 0, "TMA destinations are 128-byte aligned");
 
 template <typename T>
 __device__ __forceinline__ void fill_window_plain(unsigned char *win, const T *in, const T *img, const Geo &q,
@@ -1250,6 +1262,16 @@ __device__ __forceinline__ void corner16(float2 (&acc)[8], uint32_t a0, uint32_t
 // chunk 2g + 1 - h second, so in either LDS.128 the eight lanes of a quarter-warp still touch eight different
 // bank groups; one shuffle exchange per pixel merges the halves.  4.5 locates per lane instead of 9.
 // (The same split over L1 — fwd_pts_kernel — lost: there a 32-byte request costs L1 two passes.)
+__device__ __forceinline__ uint32_t lds32s(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16s(uint32_t addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
 #ifndef DCNV3_FWD_ROLL_IT
 #define DCNV3_FWD_ROLL_IT 0  // 1: roll the loop over the lane's two pixels (5 432 -> 3 392 SASS instructions); measured slower, 55.7 vs 53.7 us at P3
 #endif
@@ -1262,11 +1284,16 @@ fwd_tile_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
                 T *__restrict__ out, const Geo q, const int GQ
 #ifdef DCNV3_FWD_TMA
                 , const __grid_constant__ CUtensorMap tmap   // input as a 4-D tensor (C, W, H, N), box (64, 20, 20, 1)
+#if DCNV3_FWD_TMA_STAGE
+                , const __grid_constant__ CUtensorMap tmap_o // offsets (opitch, Wo, Ho, N), box (80, 8, 8, 1)
+                , const __grid_constant__ CUtensorMap tmap_m // masks (mpitch, Wo, Ho, N), box (40, 8, 8, 1)
+                , const int stage_tma
+#endif
 #endif
                 ) {
     extern __shared__ __align__(128) unsigned char smem[];
 #ifdef DCNV3_FWD_TMA
-    __shared__ __align__(8) unsigned long long win_bar;
+    __shared__ __align__(8) unsigned long long win_bar, st_bar;
 #endif
     pdl_enter();
     const int tid = threadIdx.x;
@@ -1278,6 +1305,25 @@ fwd_tile_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
     const int wx0 = tc.tx * kTile + (q.half_w - q.pw) - kFhalo;
     const T *img = in + (size_t)tc.n * q.H * q.W * q.C + tc.gq * 64;
 #ifdef DCNV3_FWD_TMA
+#if DCNV3_FWD_TMA_STAGE
+    // the tile's offsets / masks as two TMA boxes on their own mbarrier (80 / 40 elements per pixel: the group quad's 72 / 36
+    // first; a box starts on a 16-byte boundary of its row, so the masks of an odd quad sit 8 bytes into theirs), when their
+    // rows are 16-byte multiples; otherwise the lanes' own loads below
+    const bool tstage = stage_tma != 0;
+    const uint32_t stg_s = smem_u32(smem) + kFwinBytes;
+    const uint32_t mshift = tstage ? (uint32_t)((tc.gq * kWarps * 9) & 7) * 2u : 0u;
+    if (tstage && tid == 0) {
+        const uint32_t bar_s = smem_u32(&st_bar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(kFstOffB + kFstMaskB) : "memory");
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(stg_s), "l"(reinterpret_cast<uint64_t>(&tmap_o)), "r"(bar_s), "r"(tc.gq * kWarps * 18), "r"(tc.tx * kTile), "r"(tc.ty * kTile), "r"(tc.n) : "memory");
+        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                     ::"r"(stg_s + kFstOffB), "l"(reinterpret_cast<uint64_t>(&tmap_m)), "r"(bar_s), "r"((tc.gq * kWarps * 9) & ~7), "r"(tc.tx * kTile), "r"(tc.ty * kTile), "r"(tc.n) : "memory");
+    }
+#endif
     if (tid == 0) tma_load_4d(smem_u32(smem), &tmap, smem_u32(&win_bar), kFwinCells * 128, tc.gq * 64, wx0, wy0, tc.n);
 #else
     fill_window_plain<T>(smem, in, img, q, wy0, wx0, tid);
@@ -1303,6 +1349,32 @@ fwd_tile_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
     float rm[2][9];
     int oy[2], ox[2];
     bool valid[2];
+#if defined(DCNV3_FWD_TMA) && DCNV3_FWD_TMA_STAGE
+    if (tstage) {  // CTA-uniform: the two boxes have landed (the window may still be in flight)
+        if (tid == 0) tma_wait(smem_u32(&st_bar));
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int px = it * 32 + (tid >> 3);
+            oy[it] = tc.ty * kTile + (px >> 3);
+            ox[it] = tc.tx * kTile + (px & 7);
+            valid[it] = oy[it] < q.Ho && ox[it] < q.Wo;
+            // (a pixel outside the map was zero-filled by the copy engine: zero offsets, zero masks)
+            const uint32_t so = stg_s + px * kFstOffPx + (sub >> 1) * 36, sm = stg_s + kFstOffB + px * kFstMaskPx + (sub >> 1) * 18 + mshift;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) roff[it][k] = lds32s(so + (4 * h + k) * 4);
+            roff[it][4] = lds32s(so + 32);
+            if (LOGITS) {
+#pragma unroll
+                for (int p = 0; p < 9; ++p) rm[it][p] = half_to_float<T>((unsigned short)lds16s(sm + p * 2));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) rm[it][k] = half_to_float<T>((unsigned short)lds16s(sm + (4 * h + k) * 2));
+                rm[it][8] = half_to_float<T>((unsigned short)lds16s(sm + 16));
+            }
+        }
+    } else
+#endif
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
         const int px = it * 32 + (tid >> 3);
