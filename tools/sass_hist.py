@@ -20,10 +20,13 @@ for line in sass.splitlines():
         key = op if op.startswith(("LDS", "STS", "LDSM", "STSM", "LDG", "STG", "RED", "ATOM", "HMMA", "LDGSTS", "FHFMA", "UTC", "LDTM", "STTM", "UTMA", "BAR", "SHFL")) else op.split(".")[0]
         hist[cur][key] += 1
 print("# SASS opcode histograms of the hot kernels (static instruction counts, `cuobjdump -sass` of the built library)\n")
-print("Blackwell / Hopper-class mnemonics: the windows of `bwd_win_kernel` and `fwd_tile_kernel` are TMA box loads (`UTMALDG.4D`, completion")
-print("on an mbarrier: `SYNCS.EXCH` / `SYNCS.ARRIVE.TRANS64`); offsets / masks are staged with `LDGSTS` (cp.async); gathers are `LDS.128`, the")
-print("multiplies `FHFMA` (mixed-precision FMA, sm_100) / `HMMA.16816` (mma.sync), the reductions `REDG.E.ADD.BF16x8 / F16x8` vectors.  No")
-print("`UTCHMMA` / `LDTM` (tcgen05 / TMEM): DESIGN.md par. 4.0 and 7-0 say where they would pay.\n")
+print("Blackwell / Hopper-class mnemonics.  TMA does the bulk data movement of both kernels: the windows are box loads (`UTMALDG.4D`,")
+print("completion on an mbarrier: `SYNCS.EXCH` / `SYNCS.ARRIVE.TRANS64`), so are the tile's offsets and masks (two more `UTMALDG.4D`; `LDGSTS` =")
+print("cp.async only where their rows are not 16-byte multiples and in strip tiles); the backward's interpolation matrix is zeroed by a bulk copy")
+print("(`UBLKCP`) and its `grad_input` window leaves as one TMA reduce-add per warp (`UTMAREDG.4D.ADD` + `UTMACMDFLUSH`; `REDG.E.ADD.BF16x8 / F16x8`")
+print("vectors only for boxes that start at a negative coordinate, strip tiles and rare points).  Gathers are `LDS.128`, the multiplies `FHFMA`")
+print("(mixed-precision FMA, sm_100) / `HMMA.16816` (mma.sync).  No `UTCHMMA` / `LDTM` (tcgen05 / TMEM): DESIGN.md par. 4.0 and 7-0 say where")
+print("they would pay.\n")
 for fn, h in hist.items():
     if not any(w in fn for w in want):
         continue

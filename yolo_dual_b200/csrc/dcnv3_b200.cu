@@ -475,13 +475,17 @@ int forward_t(const void *in_, const void *off_, const void *mask_, void *out_, 
 #else
 #define FWD_EXTRA
 #endif
-            if (logits) {
-                if ((rc = set_smem(imat::fwd_tile_kernel<T, true>, imat::kFwdSmemB, "cudaFuncSetAttribute(fwd_tile_kernel)"))) return rc;
-                launch(imat::fwd_tile_kernel<T, true>, grid, imat::kFwdTileThreads, imat::kFwdSmemB, st, in, off, mask, out, q, GQ FWD_EXTRA);
-            } else {
-                if ((rc = set_smem(imat::fwd_tile_kernel<T, false>, imat::kFwdSmemB, "cudaFuncSetAttribute(fwd_tile_kernel)"))) return rc;
-                launch(imat::fwd_tile_kernel<T, false>, grid, imat::kFwdTileThreads, imat::kFwdSmemB, st, in, off, mask, out, q, GQ FWD_EXTRA);
-            }
+#define FWD_LAUNCH(LG, SG)                                                                                                    \
+    do {                                                                                                                      \
+        if ((rc = set_smem(imat::fwd_tile_kernel<T, LG, SG>, imat::kFwdSmemB, "cudaFuncSetAttribute(fwd_tile_kernel)"))) return rc; \
+        launch(imat::fwd_tile_kernel<T, LG, SG>, grid, imat::kFwdTileThreads, imat::kFwdSmemB, st, in, off, mask, out, q, GQ FWD_EXTRA); \
+    } while (0)
+#if defined(DCNV3_FWD_TMA) && DCNV3_FWD_TMA_STAGE
+            if (stage_tma) { if (logits) FWD_LAUNCH(true, true); else FWD_LAUNCH(false, true); }
+            else
+#endif
+            { if (logits) FWD_LAUNCH(true, false); else FWD_LAUNCH(false, false); }
+#undef FWD_LAUNCH
 #undef FWD_EXTRA
             return 0;
         }

@@ -1278,8 +1278,8 @@ __device__ __forceinline__ uint32_t lds16s(uint32_t addr) {
 #ifndef DCNV3_FWD_MIN_CTAS
 #define DCNV3_FWD_MIN_CTAS 3  // A/B on one box (round 2): 4 CTAs per SM at 64 registers — see profiles/r02_fwd_occupancy.md
 #endif
-template <typename T, bool LOGITS>
-__global__ void __launch_bounds__(kFwdTileThreads, DCNV3_FWD_MIN_CTAS)
+template <typename T, bool LOGITS, bool STAGE = false>  // STAGE: offsets / masks as TMA boxes (its own instance: the other
+__global__ void __launch_bounds__(kFwdTileThreads, DCNV3_FWD_MIN_CTAS)  // path's code would only cost instruction-cache space)
 fwd_tile_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ mask,
                 T *__restrict__ out, const Geo q, const int GQ
 #ifdef DCNV3_FWD_TMA
@@ -1309,7 +1309,8 @@ fwd_tile_kernel(const T *__restrict__ in, const T *__restrict__ off, const T *__
     // the tile's offsets / masks as two TMA boxes on their own mbarrier (80 / 40 elements per pixel: the group quad's 72 / 36
     // first; a box starts on a 16-byte boundary of its row, so the masks of an odd quad sit 8 bytes into theirs), when their
     // rows are 16-byte multiples; otherwise the lanes' own loads below
-    const bool tstage = stage_tma != 0;
+    constexpr bool tstage = STAGE;
+    (void)stage_tma;
     const uint32_t stg_s = smem_u32(smem) + kFwinBytes;
     const uint32_t mshift = tstage ? (uint32_t)((tc.gq * kWarps * 9) & 7) * 2u : 0u;
     if (tstage && tid == 0) {
