@@ -106,6 +106,30 @@ def test_win_vs_pixel_oracle(case, dtype, sigma, pixel_oracle):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+def test_mask_not_16_byte_aligned_takes_the_chunk_path(dtype, pixel_oracle):
+    """The tile's offsets / masks arrive as TMA boxes only when their rows and base pointers are 16-byte multiples
+    (dcnv3_win.cuh / dcnv3_imat.cuh, STAGE); a mask tensor that starts 8 bytes into its allocation takes the warps' own
+    cp.async chunks (backward) and the lanes' own loads (forward) — same results."""
+    from oracle.dcnv3_oracle import make_inputs
+    from yolo_dual_b200.ops_dcnv3.functions import DCNv3Function
+    N, H, W, G, gc = 2, 24, 32, 8, 16
+    args = (3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0)
+    x, off, m, go = make_inputs(N, H, W, G, gc, 3, 3, 1, 1, 1, 1, 1, 1, dist="unit", seed=11)
+    want = _want(pixel_oracle, x, off, m, go, args, dtype)
+    xs, os_ = (t.to(DEV, dtype).contiguous().requires_grad_(True) for t in (x, off))
+    buf = torch.zeros(m.numel() + 4, device=DEV, dtype=dtype)
+    buf[4:] = m.to(DEV, dtype).reshape(-1)
+    ms = buf[4:].view(m.shape).detach().requires_grad_(True)
+    assert ms.data_ptr() % 16 == 8 and ms.is_contiguous()
+    out = DCNv3Function.apply(xs, os_, ms, *args, 256)
+    out.backward(go.to(DEV, dtype))
+    torch.cuda.synchronize()
+    got = [t.float().cpu() for t in (out.detach(), xs.grad, os_.grad, ms.grad)]
+    for g_, w_, name in zip(got, want, ("output", "grad_input", "grad_offset", "grad_mask")):
+        _close(g_, w_, name, **(_gi_tol(dtype) if name == "grad_input" else {}))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
 @pytest.mark.parametrize("case", ["cfg1_G4", "partial_tiles_G8", "pad0"])
 def test_win_reference_distribution_far_offsets(case, dtype, pixel_oracle):
     """The reference test's own distribution (test.py:35-39: offset = rand * 10): every band runs the vector
