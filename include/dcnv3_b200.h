@@ -69,10 +69,11 @@ enum {
  *               (what the reference does, dcnv3_cuda.cu:126-133,168-170);
  *   ACC_STORAGE packed 16-bit vector reductions straight into grad_input
  *               (no workspace, less traffic, one rounding per contribution);
- *   ACC_TILE    one kernel, no workspace: the contributions of an 8x8 tile of
- *               output pixels are summed in fp32 on the SM and the tile's window
- *               leaves as packed 16-bit vector reductions, so a cell of grad_input
- *               sees at most four roundings (one per tile window that reaches it)
+ *   ACC_TILE    one kernel, no workspace: the contributions of a 4x8 band of
+ *               output pixels are summed in fp32 on the SM and the band's window
+ *               is added into grad_input in the storage dtype (TMA reduce-add /
+ *               packed 16-bit vector reductions), so a cell of grad_input sees at
+ *               most six roundings (one per band window that reaches it)
  *               instead of one (ACC_OPMATH) or ~36 (ACC_STORAGE).  Sampling points
  *               further than 3 px from their kernel-grid position leave the window
  *               and are reduced one by one like ACC_STORAGE.  Shapes the tile kernel
