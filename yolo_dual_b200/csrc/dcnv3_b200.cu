@@ -398,9 +398,8 @@ int launch_bwd_win(const T *in, const T *off, const T *mask, const T *gout, T *g
         const cuuint64_t od[4] = {(cuuint64_t)q.opitch, (cuuint64_t)q.Wo, (cuuint64_t)q.Ho, (cuuint64_t)q.N};
         const cuuint64_t md[4] = {(cuuint64_t)q.mpitch, (cuuint64_t)q.Wo, (cuuint64_t)q.Ho, (cuuint64_t)q.N};
         const cuuint32_t ob[4] = {win::kStOffPx / 2, 8, 4, 1}, mb[4] = {win::kStMaskPx / 2, 8, 4, 1};
-        if ((rc = make_tmap4(off, od, (cuuint64_t)q.opitch, ob, 0, 0, &tmo))) return rc;
-        if ((rc = make_tmap4(mask, md, (cuuint64_t)q.mpitch, mb, 0, 0, &tmm))) return rc;
-        stage_tma = 1;
+        // (a shape the encoder refuses simply keeps the warps' own chunks)
+        stage_tma = !make_tmap4(off, od, (cuuint64_t)q.opitch, ob, 0, 0, &tmo) && !make_tmap4(mask, md, (cuuint64_t)q.mpitch, mb, 0, 0, &tmm);
     }
 #endif
     if (!stage_tma) { tmo = tm; tmm = tm; }
@@ -464,9 +463,9 @@ int forward_t(const void *in_, const void *off_, const void *mask_, void *out_, 
                 const cuuint64_t od[4] = {(cuuint64_t)q.opitch, (cuuint64_t)q.Wo, (cuuint64_t)q.Ho, (cuuint64_t)q.N};
                 const cuuint64_t md[4] = {(cuuint64_t)q.mpitch, (cuuint64_t)q.Wo, (cuuint64_t)q.Ho, (cuuint64_t)q.N};
                 const cuuint32_t ob[4] = {imat::kFstOffPx / 2, 8, 8, 1}, mb[4] = {imat::kFstMaskPx / 2, 8, 8, 1};
-                if ((rc = make_tmap4(off, od, (cuuint64_t)q.opitch, ob, 0, 0, &tmo))) return rc;
-                if ((rc = make_tmap4(mask, md, (cuuint64_t)q.mpitch, mb, 0, 0, &tmm))) return rc;
-                stage_tma = 1;
+                // (a shape the encoder refuses simply keeps the lanes' own loads)
+                stage_tma = !make_tmap4(off, od, (cuuint64_t)q.opitch, ob, 0, 0, &tmo) && !make_tmap4(mask, md, (cuuint64_t)q.mpitch, mb, 0, 0, &tmm);
+                if (!stage_tma) { tmo = tm; tmm = tm; }
             }
 #define FWD_EXTRA , tm, tmo, tmm, stage_tma
 #else
